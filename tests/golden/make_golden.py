@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Mint golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py          # writes tests/golden/*.pt
+
+The reference (/root/reference/src) is imported as-is; nothing is copied from it.
+Weights and inputs come from the deterministic generators in oracle/convtasnet_oracle.py
+(``synth_state_dict`` / ``synth_batch``) and are loaded into the reference modules with
+``load_state_dict(strict=True)`` -- which also proves the key names / shapes / order of
+``state_dict_spec`` match the reference.  Outputs are stored as small fixtures; the paper-size
+case stores a strided subsample plus fp64 checksums.
+
+/root/reference does not exist on the GPU box: tests only read the committed .pt files.
+"""
+import os
+import sys
+import warnings
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_SRC = "/root/reference/src"
+
+sys.path.insert(0, REF_SRC)
+warnings.simplefilter("ignore")
+from models.conv_tasnet import ConvTasNet  # noqa: E402  (reference)
+from models.tdcn import TimeDilatedConvNet  # noqa: E402
+from models.filterbank import Encoder, Decoder  # noqa: E402
+from modules.norm import GlobalLayerNorm, CumulativeLayerNorm1d  # noqa: E402
+from criterion.sdr import NegSISDR, sisdr  # noqa: E402
+from criterion.pit import PIT1d  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import convtasnet_oracle as O  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def build_reference(cfg: O.OracleConfig):
+    m = ConvTasNet(
+        cfg.n_basis, cfg.kernel_size, stride=cfg.stride, enc_basis="trainable", dec_basis="trainable",
+        enc_nonlinear=cfg.enc_nonlinear,
+        sep_hidden_channels=cfg.sep_hidden_channels, sep_bottleneck_channels=cfg.sep_bottleneck_channels,
+        sep_skip_channels=cfg.sep_skip_channels, sep_kernel_size=cfg.sep_kernel_size,
+        sep_num_blocks=cfg.sep_num_blocks, sep_num_layers=cfg.sep_num_layers,
+        dilated=cfg.dilated, separable=cfg.separable, sep_nonlinear=cfg.sep_nonlinear, sep_norm=cfg.sep_norm,
+        mask_nonlinear=cfg.mask_nonlinear, causal=cfg.causal, n_sources=cfg.n_sources, eps=cfg.eps)
+    return m
+
+
+def model_case(name, cfg: O.OracleConfig, batch, T, wseed, xseed, subsample=None):
+    ref = build_reference(cfg)
+    ref_keys = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    spec = [(k, tuple(s)) for k, s in O.state_dict_spec(cfg)]
+    assert ref_keys == spec, "state_dict_spec does not match the reference for " + name
+    sd = O.synth_state_dict(cfg, seed=wseed)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    mixture, sources = O.synth_batch(batch, cfg.n_sources, T, seed=xseed)
+    with torch.no_grad():
+        out, latent = ref.extract_latent(mixture)
+        crit = PIT1d(NegSISDR(), n_sources=cfg.n_sources)
+        loss, perm = crit(out, sources)
+        loss_b, perm_b = crit(out, sources, batch_mean=False)
+        # fp64 run of the same reference = noise-floor estimate
+        ref64 = build_reference(cfg).double()
+        ref64.load_state_dict({k: v.double() for k, v in sd.items()})
+        out64, _ = ref64.extract_latent(mixture.double())
+    rec = {
+        "name": name, "cfg": cfg.to_dict(), "batch": batch, "T": T, "wseed": wseed, "xseed": xseed,
+        "weight_abs_sum": float(sum(v.double().abs().sum() for v in sd.values())),
+        "loss": loss.clone(), "perm": perm.clone(), "loss_b": loss_b.clone(), "perm_b": perm_b.clone(),
+        "out_sum": float(out.double().sum()), "out_sumsq": float((out.double() ** 2).sum()),
+        "out_absmax": float(out.abs().max()),
+        "fp32_vs_fp64_maxabs": float((out.double() - out64).abs().max()),
+        "n_params": sum(v.numel() for v in sd.values()),
+    }
+    if subsample is None:
+        rec["out"] = out.clone()
+        rec["latent"] = latent.clone()
+    else:
+        rec["out_stride"] = subsample
+        rec["out"] = out[..., ::subsample].clone()
+        rec["latent_stride"] = (37, 53)
+        rec["latent"] = latent[:, :, ::37, ::53].clone()
+    path = os.path.join(HERE, name + ".pt")
+    torch.save(rec, path)
+    print(f"{name}: out {tuple(out.shape)} absmax {rec['out_absmax']:.4f} loss {float(loss):.6f} "
+          f"perm {perm.tolist()} fp32-vs-fp64 {rec['fp32_vs_fp64_maxabs']:.2e} -> {os.path.getsize(path)} B")
+
+
+def module_cases():
+    rec = {}
+    # gLN / cLN: the reference's own self-test input (src/modules/norm.py:107-116) + a random one
+    g = torch.Generator().manual_seed(7)
+    x_ar = torch.arange(30, dtype=torch.float).view(2, 3, 5)
+    x_rn = torch.randn(3, 24, 301, generator=g) * 2.0 + 0.7
+    gam = 1.0 + 0.3 * torch.randn(24, generator=g)
+    bet = 0.2 * torch.randn(24, generator=g)
+    gl = GlobalLayerNorm(3)
+    rec["gln_arange_in"], rec["gln_arange_out"] = x_ar, gl(x_ar).detach()
+    gl = GlobalLayerNorm(24)
+    gl.load_state_dict({"norm.weight": gam, "norm.bias": bet})
+    rec["gln_in"], rec["gln_gamma"], rec["gln_beta"], rec["gln_out"] = x_rn, gam, bet, gl(x_rn).detach()
+    cl = CumulativeLayerNorm1d(24)
+    cl.load_state_dict({"gamma": gam.view(1, 24, 1), "beta": bet.view(1, 24, 1)})
+    rec["cln_out"] = cl(x_rn).detach()
+    cl3 = CumulativeLayerNorm1d(3)
+    rec["cln_arange_out"] = cl3(x_ar).detach()
+
+    # Encoder / Decoder
+    for (N, L, S, T, relu) in [(32, 16, 8, 400, False), (20, 4, 2, 131, True), (64, 2, 1, 96, False)]:
+        key = f"N{N}_L{L}_S{S}_T{T}_{int(relu)}"
+        enc = Encoder(1, N, kernel_size=L, stride=S, nonlinear="relu" if relu else None)
+        dec = Decoder(N, 1, kernel_size=L, stride=S)
+        We = (torch.rand(N, 1, L, generator=g) * 2 - 1) / L ** 0.5
+        Wd = (torch.rand(N, 1, L, generator=g) * 2 - 1) / L ** 0.5
+        enc.load_state_dict({"conv1d.weight": We})
+        dec.load_state_dict({"conv_transpose1d.weight": Wd})
+        x = torch.randn(3, 1, T, generator=g)
+        w = enc(x).detach()
+        y = dec(w).detach()
+        rec["encdec_" + key] = {"We": We, "Wd": Wd, "x": x, "w": w, "y": y}
+
+    # TimeDilatedConvNet standalone (separable, prelu, norm) causal and non-causal
+    for causal in (False, True):
+        cfg = O.OracleConfig(n_basis=8, kernel_size=4, sep_hidden_channels=24, sep_bottleneck_channels=12,
+                             sep_skip_channels=10, sep_num_blocks=2, sep_num_layers=4, causal=causal)
+        tdcn = TimeDilatedConvNet(12, hidden_channels=24, skip_channels=10, kernel_size=3, num_blocks=2, num_layers=4,
+                                  dilated=True, separable=True, causal=causal, nonlinear="prelu", norm=True)
+        full = O.synth_state_dict(cfg, seed=5)
+        sub = {k[len("separator.tdcn."):]: v for k, v in full.items() if k.startswith("separator.tdcn.")}
+        tdcn.load_state_dict(sub, strict=True)
+        x = torch.randn(2, 12, 157, generator=g)
+        rec[f"tdcn_causal{int(causal)}"] = {"cfg": cfg.to_dict(), "wseed": 5, "x": x, "y": tdcn(x).detach()}
+
+    # SI-SDR / PIT: the reference self-test (src/criterion/pit.py:226-265: seed 111, randint(2,(4,2,1024))) + S=3,4
+    torch.manual_seed(111)
+    inp = torch.randint(2, (4, 2, 1024), dtype=torch.float)
+    tgt = torch.randint(2, (4, 2, 1024), dtype=torch.float)
+    crit = PIT1d(NegSISDR(), n_sources=2)
+    loss, pattern = crit(inp, tgt)
+    rec["pit_selftest"] = {"input": inp, "target": tgt, "loss": loss, "pattern": pattern}
+    for S in (2, 3, 4):
+        e = torch.randn(5, S, 3000, generator=g)
+        t = torch.randn(5, S, 3000, generator=g)
+        # make some estimates close to permuted targets so the permutation is non-trivial
+        perm = torch.randperm(S, generator=g)
+        e = 0.3 * e + t[:, perm]
+        crit = PIT1d(NegSISDR(), n_sources=S)
+        loss_b, pattern = crit(e, t, batch_mean=False)
+        loss, _ = crit(e, t)
+        rec[f"pit_S{S}"] = {"input": e, "target": t, "loss_b": loss_b, "loss": loss, "pattern": pattern,
+                            "sisdr": sisdr(e, t)}
+    # SI-SDR limits quoted in SURVEY.md 8a-12: zero target, perfect estimate, tie (identical estimates)
+    t = torch.randn(2, 2, 500, generator=g)
+    rec["sisdr_zero_target"] = sisdr(t, torch.zeros_like(t))
+    rec["sisdr_perfect"] = sisdr(t, t.clone())
+    rec["sisdr_limits_in"] = t
+    e_tie = t[:, :1].repeat(1, 2, 1)
+    crit = PIT1d(NegSISDR(), n_sources=2)
+    l_tie, p_tie = crit(e_tie, t, batch_mean=False)
+    rec["pit_tie"] = {"input": e_tie, "target": t, "loss_b": l_tie, "pattern": p_tie}
+    path = os.path.join(HERE, "modules.pt")
+    torch.save(rec, path)
+    print("modules ->", os.path.getsize(path), "B")
+
+
+def main():
+    tiny = dict(n_basis=16, kernel_size=4, sep_hidden_channels=16, sep_bottleneck_channels=8, sep_skip_channels=8,
+                sep_num_blocks=2, sep_num_layers=3)
+    model_case("tiny_gln", O.OracleConfig(**tiny, causal=False), batch=2, T=203, wseed=11, xseed=21)
+    model_case("tiny_cln", O.OracleConfig(**tiny, causal=True), batch=2, T=203, wseed=12, xseed=22)
+    small = dict(n_basis=64, kernel_size=16, sep_hidden_channels=96, sep_bottleneck_channels=32, sep_skip_channels=48,
+                 sep_num_blocks=2, sep_num_layers=5)
+    model_case("small_relu_3spk", O.OracleConfig(**small, causal=False, n_sources=3, enc_nonlinear="relu"),
+               batch=3, T=2500, wseed=13, xseed=23)
+    paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
+                 sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
+    model_case("paper_2spk", O.OracleConfig(**paper, causal=False, n_sources=2), batch=2, T=32000, wseed=111, xseed=111,
+               subsample=61)
+    model_case("paper_3spk_short", O.OracleConfig(**paper, causal=False, n_sources=3), batch=1, T=8000, wseed=112,
+               xseed=112, subsample=17)
+    module_cases()
+
+
+if __name__ == "__main__":
+    main()
