@@ -1,0 +1,408 @@
+// extern "C" entry points + host-side orchestration of the Conv-TasNet forward (see include/ctn_b200.h).
+#include <string.h>
+#include <vector>
+#include "ctn_internal.h"
+
+thread_local int g_ctn_launches = 0;
+thread_local int g_ctn_depth = 0;
+thread_local int g_ctn_last_launches = 0;
+
+// ---- stage profiler ---------------------------------------------------------------------------------------
+struct ProfRec { int stage; cudaEvent_t e0, e1; int launches0, launches; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof_recs;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+static thread_local int g_prof_depth = 0;
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+void ctn_prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof_on || g_prof_depth++ > 0) return;
+  ProfRec r;
+  r.stage = stage; r.e0 = prof_event(); r.e1 = prof_event(); r.launches0 = g_ctn_launches; r.launches = 0;
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void ctn_prof_end(int stage, cudaStream_t st) {
+  if (!g_prof_on || --g_prof_depth > 0) return;
+  ProfRec& r = g_prof_recs.back();
+  r.launches = g_ctn_launches - r.launches0;
+  cudaEventRecord(r.e1, st);
+}
+extern "C" int ctn_profile_enable(int enable) { g_prof_on = enable != 0; g_prof_depth = 0; return CTN_OK; }
+extern "C" int ctn_profile_read(double* ms, int* launches) {
+  if (!ms || !launches) return CTN_EINVAL;
+  for (ProfRec& r : g_prof_recs) {
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e != cudaSuccess) return (int)e;
+    float t = 0.f;
+    e = cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (e != cudaSuccess) return (int)e;
+    ms[r.stage] += (double)t;
+    launches[r.stage] += r.launches;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  return CTN_OK;
+}
+
+extern "C" int ctn_version(void) { return CTN_VERSION; }
+extern "C" int ctn_last_launch_count(void) { return g_ctn_last_launches; }
+
+extern "C" const char* ctn_strerror(int s) {
+  switch (s) {
+    case CTN_OK: return "ok";
+    case CTN_EINVAL: return "invalid argument (shape / null pointer)";
+    case CTN_EUNSUPPORTED: return "configuration outside the kernel envelope";
+    case CTN_EALIGN: return "pointer or pitch alignment";
+    case CTN_EWORKSPACE: return "workspace too small";
+    case CTN_ENOTBUILT: return "kernel family not built into this library";
+    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown ctn error";
+  }
+}
+
+extern "C" int ctn_frames(int T, int kernel_size, int stride, int* pad_left, int* pad_right) {
+  if (T <= 0 || kernel_size <= 0 || stride <= 0 || kernel_size % stride != 0) return CTN_EINVAL;
+  // src/models/conv_tasnet.py:145-147
+  int r = (T - kernel_size) % stride;
+  if (r < 0) r += stride;  // python modulo
+  const int padding = (stride - r) % stride;
+  const int pl = padding / 2, pr = padding - pl;
+  if (pad_left) *pad_left = pl;
+  if (pad_right) *pad_right = pr;
+  const int Tp = T + padding;
+  if (Tp < kernel_size) return CTN_EINVAL;
+  return (Tp - kernel_size) / stride + 1;
+}
+
+extern "C" int ctn_pitch(int frames) { return frames <= 0 ? CTN_EINVAL : ctn_round_up(frames, CTN_TILE_T); }
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* b) : base((char*)b), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct TcnWs {
+  double* stats;  // [2*RX][B][2]
+  std::vector<FoldedConv> folds;  // per block, (Bc+Sc) rows
+  float *x, *skip, *h, *u, *outraw;
+  size_t stats_bytes;
+};
+
+static int check_tcn_cfg(const ctn_config_t* c) {
+  if (!c) return CTN_EINVAL;
+  if (c->bottleneck <= 0 || c->hidden <= 0 || c->skip <= 0 || c->sep_kernel <= 0 || c->num_blocks <= 0 || c->num_layers <= 0)
+    return CTN_EINVAL;
+  if (c->num_layers > 20) return CTN_EUNSUPPORTED;
+  if (c->causal) return CTN_EUNSUPPORTED;  // cLN inside the fused path: not built yet (module-level ctn_cln_fwd exists)
+  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
+  return CTN_OK;
+}
+
+static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs* ws) {
+  const int RX = c->num_blocks * c->num_layers;
+  const int Mt = c->bottleneck + c->skip;
+  ws->stats_bytes = sizeof(double) * 2 * RX * B * 2;
+  ws->stats = cv.take<double>((size_t)2 * RX * B * 2);
+  ws->folds.resize(RX);
+  for (int i = 0; i < RX; ++i) {
+    ws->folds[i].Wf = cv.take<float>((size_t)Mt * c->hidden);
+    ws->folds[i].v1 = cv.take<float>(Mt);
+    ws->folds[i].v2 = cv.take<float>(Mt);
+  }
+  const size_t bp = (size_t)B * pitch;
+  ws->x = cv.take<float>(bp * c->bottleneck);
+  ws->skip = cv.take<float>(bp * c->skip);
+  ws->h = cv.take<float>(bp * c->hidden);
+  ws->u = cv.take<float>(bp * c->hidden);
+  ws->outraw = cv.take<float>(bp * Mt);
+}
+
+static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
+  if (math == CTN_MATH_FP32) return ctn_pw_simt(a, pro, epi, st);
+  return ctn_pw_umma(a, pro, epi, math, st);
+}
+
+// TCN over ws->x (padded layout) -> ws->skip.  stats region must be zeroed by the caller.
+static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnWs* ws, int B, int frames, int pitch,
+                   cudaStream_t st) {
+  const int R = c->num_blocks, X = c->num_layers, Bc = c->bottleneck, H = c->hidden, Sc = c->skip;
+  // weight folding for all blocks (tiny kernels)
+  for (int i = 0; i < R * X; ++i) {
+    StageTimer tm(CTN_ST_PREP, st);
+    const ctn_block_params_t& p = blocks[i];
+    const bool has_out = p.out_w != nullptr;
+    if (has_out) CTN_TRY(ctn_fold_conv(p.out_w, p.out_b, p.norm2_g, p.norm2_b, Bc, H, ws->folds[i], 0, st));
+    CTN_TRY(ctn_fold_conv(p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, Sc, H, ws->folds[i], has_out ? Bc : 0, st));
+  }
+  for (int r = 0; r < R; ++r) {
+    for (int l = 0; l < X; ++l) {
+      const int i = r * X + l;
+      const ctn_block_params_t& p = blocks[i];
+      const bool has_out = p.out_w != nullptr;
+      if (!has_out && !(r == R - 1 && l == X - 1)) return CTN_EINVAL;
+      const int dilation = 1 << l;  // dilated=True (tdcn.py:52-54)
+      double* st1 = ws->stats + (size_t)(2 * i) * B * 2;
+      double* st2 = ws->stats + (size_t)(2 * i + 1) * B * 2;
+      // K_A: h = PReLU(W1 x + b1), stats1
+      PwArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = ws->x; a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
+      a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1;
+      { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_H, c->math, st)); }
+      // K_B: u = PReLU(dwconv(gLN1(h))), stats2
+      { StageTimer tm(CTN_ST_DW, st);
+        CTN_TRY(ctn_dw_fwd(ws->h, ws->u, p.norm1_g, p.norm1_b, p.dw_w, p.dw_b, p.prelu2, st1, st2, B, H, frames, pitch,
+                           c->sep_kernel, dilation, c->causal, c->eps_tcn, st)); }
+      // K_C: r = [Wo;Ws] diag(gamma2) u
+      const int Mt = has_out ? Bc + Sc : Sc;
+      memset(&a, 0, sizeof(a));
+      a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+      { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
+      // K_F: residual / skip with deferred gLN2
+      { StageTimer tm(CTN_ST_FIN, st);
+        CTN_TRY(ctn_finish_fwd(ws->outraw, ws->folds[i], st2, (double)H * (double)frames, c->eps_tcn, ws->x, ws->skip, B, Bc,
+                               Sc, has_out ? 1 : 0, i == 0 ? 1 : 0, frames, pitch, st)); }
+    }
+  }
+  return CTN_OK;
+}
+
+extern "C" int ctn_tcn_workspace_bytes(const ctn_config_t* cfg, int batch, int frames, size_t* bytes) {
+  CTN_TRY(check_tcn_cfg(cfg));
+  if (batch <= 0 || frames <= 0 || !bytes) return CTN_EINVAL;
+  Carver cv(nullptr);
+  TcnWs ws;
+  carve_tcn(cv, cfg, batch, ctn_pitch(frames), &ws);
+  *bytes = cv.off + 256;
+  return CTN_OK;
+}
+
+extern "C" int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, const float* x, float* skip_out, int B,
+                           int frames, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  CTN_TRY(check_tcn_cfg(cfg));
+  if (!blocks || !x || !skip_out || !workspace || B <= 0 || frames <= 0) return CTN_EINVAL;
+  if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
+  size_t need = 0;
+  CTN_TRY(ctn_tcn_workspace_bytes(cfg, B, frames, &need));
+  if (workspace_bytes < need) return CTN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pitch = ctn_pitch(frames);
+  Carver cv(workspace);
+  TcnWs ws;
+  carve_tcn(cv, cfg, B, pitch, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.stats, 0, ws.stats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  CTN_TRY(ctn_copy_to_pitch(x, ws.x, B * cfg->bottleneck, frames, pitch, st));
+  CTN_TRY(run_tcn(cfg, blocks, &ws, B, frames, pitch, st));
+  CTN_TRY(ctn_copy_from_pitch(ws.skip, skip_out, B * cfg->skip, frames, pitch, st));
+  return CTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// full model
+// ------------------------------------------------------------------------------------------------
+struct ModelWs {
+  double* stats0;  // [B][2]
+  FoldedConv head; // (Bc, N)
+  float* w;        // (B, N, pitch)
+  float* what;     // (B, S*N, pitch)
+  TcnWs tcn;
+};
+
+static int check_model_cfg(const ctn_config_t* c) {
+  CTN_TRY(check_tcn_cfg(c));
+  if (c->n_basis <= 0 || c->kernel_size <= 0 || c->stride <= 0 || c->n_sources <= 0) return CTN_EINVAL;
+  if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
+  if (c->mask_softmax) return CTN_EUNSUPPORTED;
+  return CTN_OK;
+}
+
+static void carve_model(Carver& cv, const ctn_config_t* c, int B, int pitch, ModelWs* ws) {
+  ws->stats0 = cv.take<double>((size_t)B * 2);
+  ws->head.Wf = cv.take<float>((size_t)c->bottleneck * c->n_basis);
+  ws->head.v1 = cv.take<float>(c->bottleneck);
+  ws->head.v2 = cv.take<float>(c->bottleneck);
+  const size_t bp = (size_t)B * pitch;
+  ws->w = cv.take<float>(bp * c->n_basis);
+  ws->what = cv.take<float>(bp * c->n_basis * c->n_sources);
+  carve_tcn(cv, c, B, pitch, &ws->tcn);
+}
+
+extern "C" int ctn_workspace_bytes(const ctn_config_t* cfg, int batch, int T, size_t* bytes) {
+  CTN_TRY(check_model_cfg(cfg));
+  if (batch <= 0 || !bytes) return CTN_EINVAL;
+  const int frames = ctn_frames(T, cfg->kernel_size, cfg->stride, nullptr, nullptr);
+  if (frames <= 0) return CTN_EINVAL;
+  Carver cv(nullptr);
+  ModelWs ws;
+  carve_model(cv, cfg, batch, ctn_pitch(frames), &ws);
+  *bytes = cv.off + 256;
+  return CTN_OK;
+}
+
+// separator on ws->w (+ stats0 already accumulated) -> ws->what (= w*mask) and optionally the raw mask
+static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* ws, int B, int frames, int pitch,
+                         float* mask_out, cudaStream_t st) {
+  const int N = c->n_basis, Bc = c->bottleneck, Sc = c->skip, S = c->n_sources;
+  // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371)
+  { StageTimer tm(CTN_ST_PREP, st); CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st)); }
+  PwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = ws->w; a.W = ws->head.Wf; a.D = ws->tcn.x; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
+  a.v1 = ws->head.v1; a.v2 = ws->head.v2; a.stats_in = ws->stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
+  { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, c->math, st)); }
+  // TCN (conv_tasnet.py:372)
+  CTN_TRY(run_tcn(c, p->blocks, &ws->tcn, B, frames, pitch, st));
+  // tail: PReLU -> mask 1x1 -> sigmoid -> * w  (conv_tasnet.py:373-376, 159-160)
+  memset(&a, 0, sizeof(a));
+  a.A = ws->tcn.skip; a.W = p->mask_w; a.D = ws->what; a.B = B; a.M = S * N; a.K = Sc; a.frames = frames; a.pitch = pitch;
+  a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws->w; a.Nb = N; a.mask_out = mask_out;
+  { StageTimer tm(CTN_ST_MASK, st); CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, c->math, st)); }
+  return CTN_OK;
+}
+
+extern "C" int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* x, int B, int T,
+                                  float* out, float* latent, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  CTN_TRY(check_model_cfg(cfg));
+  if (!params || !params->blocks || !x || !out || !workspace || B <= 0 || T <= 0) return CTN_EINVAL;
+  if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
+  size_t need = 0;
+  CTN_TRY(ctn_workspace_bytes(cfg, B, T, &need));
+  if (workspace_bytes < need) return CTN_EWORKSPACE;
+  int pl = 0, pr = 0;
+  const int frames = ctn_frames(T, cfg->kernel_size, cfg->stride, &pl, &pr);
+  if (frames <= 0) return CTN_EINVAL;
+  const int pitch = ctn_pitch(frames);
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  ModelWs ws;
+  carve_model(cv, cfg, B, pitch, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.stats0, 0, sizeof(double) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(ws.tcn.stats, 0, ws.tcn.stats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  // encoder (+ gLN0 statistics)
+  { StageTimer tm(CTN_ST_ENC, st);
+    CTN_TRY(ctn_encoder_fwd(x, params->enc_w, ws.w, B, T, pl, pr, cfg->n_basis, cfg->kernel_size, cfg->stride, cfg->enc_relu,
+                            pitch, ws.stats0, st)); }
+  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, nullptr, st));
+  // decoder + crop (conv_tasnet.py:163-169)
+  { StageTimer tm(CTN_ST_DEC, st);
+    CTN_TRY(ctn_decoder_fwd(ws.what, params->dec_w, out, B * cfg->n_sources, cfg->n_basis, frames, pitch, cfg->kernel_size,
+                            cfg->stride, pl, T, st)); }
+  if (latent) CTN_TRY(ctn_copy_from_pitch(ws.what, latent, B * cfg->n_sources * cfg->n_basis, frames, pitch, st));
+  return CTN_OK;
+}
+
+// stats of an already-encoded w in padded layout
+__global__ void __launch_bounds__(256) k_stats_pitch(const float* __restrict__ x, int C, int frames, int pitch, double* __restrict__ stats) {
+  __shared__ double red[64];
+  const int b = blockIdx.y;
+  double s = 0.0, ss = 0.0;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const float* r = x + ((size_t)b * C + c) * pitch;
+    float ls = 0.f, lss = 0.f;
+    for (int t = threadIdx.x; t < frames; t += 256) { const float v = r[t]; ls += v; lss += v * v; }
+    s += ls; ss += lss;
+  }
+  block_sum2_d(s, ss, red);
+  if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+}
+
+extern "C" int ctn_separator_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* w, int B, int frames,
+                                 float* mask, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  CTN_TRY(check_model_cfg(cfg));
+  if (!params || !params->blocks || !w || !mask || !workspace || B <= 0 || frames <= 0) return CTN_EINVAL;
+  if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
+  const int pitch = ctn_pitch(frames);
+  Carver cv0(nullptr);
+  ModelWs ws;
+  carve_model(cv0, cfg, B, pitch, &ws);
+  const size_t mask_elems = (size_t)B * cfg->n_sources * cfg->n_basis * pitch;
+  if (workspace_bytes < cv0.off + 512 + mask_elems * sizeof(float)) return CTN_EWORKSPACE;
+  Carver cv(workspace);
+  carve_model(cv, cfg, B, pitch, &ws);
+  float* mask_p = cv.take<float>(mask_elems);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(ws.stats0, 0, sizeof(double) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(ws.tcn.stats, 0, ws.tcn.stats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  CTN_TRY(ctn_copy_to_pitch(w, ws.w, B * cfg->n_basis, frames, pitch, st));
+  int gx = cfg->n_basis < 64 ? cfg->n_basis : 64;
+  k_stats_pitch<<<dim3(gx, B), 256, 0, st>>>(ws.w, cfg->n_basis, frames, pitch, ws.stats0);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, mask_p, st));
+  CTN_TRY(ctn_copy_from_pitch(mask_p, mask, B * cfg->n_sources * cfg->n_basis, frames, pitch, st));
+  return CTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// end-to-end with host buffers
+// ------------------------------------------------------------------------------------------------
+struct HostIo {
+  float *x, *tgt, *out, *loss_b, *loss_mean;
+  int64_t* perm;
+  double* scratch;
+};
+static void carve_io(Carver& cv, const ctn_config_t* c, int B, int T, HostIo* io) {
+  const int S = c->n_sources;
+  io->x = cv.take<float>((size_t)B * T);
+  io->tgt = cv.take<float>((size_t)B * S * T);
+  io->out = cv.take<float>((size_t)B * S * T);
+  io->loss_b = cv.take<float>(B);
+  io->loss_mean = cv.take<float>(1);
+  io->perm = cv.take<int64_t>((size_t)B * S);
+  io->scratch = cv.take<double>(ctn_sisdr_pit_scratch_bytes(B, S) / sizeof(double));
+}
+
+extern "C" size_t ctn_host_io_bytes(const ctn_config_t* cfg, int B, int T) {
+  if (!cfg || B <= 0 || T <= 0) return 0;
+  Carver cv(nullptr);
+  HostIo io;
+  carve_io(cv, cfg, B, T, &io);
+  return cv.off + 256;
+}
+
+extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params, const float* x_host,
+                                        const float* tgt_host, int B, int T, float* out_host, float* loss_mean_host,
+                                        int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
+                                        ctn_stream_t stream) {
+  LaunchScope scope;
+  if (!cfg || !x_host || !tgt_host || !loss_mean_host || !perm_host || !dev_io) return CTN_EINVAL;
+  if (((uintptr_t)dev_io) & 255) return CTN_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = cfg->n_sources;
+  Carver cv(dev_io);
+  HostIo io;
+  carve_io(cv, cfg, B, T, &io);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(io.x, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyAsync(io.tgt, tgt_host, sizeof(float) * (size_t)B * S * T, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+  CTN_TRY(ctn_convtasnet_fwd(cfg, params, io.x, B, T, io.out, nullptr, workspace, workspace_bytes, stream));
+  CTN_TRY(ctn_sisdr_pit_fwd(io.out, io.tgt, B, S, T, 1e-12f, io.loss_b, io.perm, io.loss_mean, nullptr, io.scratch, stream));
+  if (out_host && (e = cudaMemcpyAsync(out_host, io.out, sizeof(float) * (size_t)B * S * T, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyAsync(loss_mean_host, io.loss_mean, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyAsync(perm_host, io.perm, sizeof(int64_t) * (size_t)B * S, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+  return CTN_OK;
+}

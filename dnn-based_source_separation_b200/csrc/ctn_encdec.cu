@@ -1,0 +1,198 @@
+// Encoder (strided 1-D conv) and decoder (transposed conv, overlap-add) kernels.  HBM-bound:
+//   encoder writes N*frames floats per sample (262 MB at cfg2), decoder reads S*N*frames floats.
+// Lanes run along time so every global access is a 128-byte coalesced row segment; the 16-tap filter bank
+// lives transposed in shared memory and is read with broadcast 128-bit LDS.
+#include "ctn_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Encoder: w[b][n][f] = sum_k W[n][k] * xpad[b][f*stride + k]      (src/models/filterbank.py:222-229)
+// grid (pitch/128, B), block 128: thread = frame; loops over n in groups of 4.
+// ------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(128) k_encoder(const float* __restrict__ x, const float* __restrict__ W,
+                                                 float* __restrict__ w, int T, int pad_left, int N, int stride,
+                                                 int frames, int pitch, int relu, double* __restrict__ stats) {
+  extern __shared__ float sm[];
+  float* Wt = sm;                       // [L][N4]  (N4 = N rounded up to 4)
+  const int N4 = (N + 3) & ~3;
+  float* xs = sm + L * N4;              // [127*stride + L]
+  __shared__ double red[64];
+  const int b = blockIdx.y, f0 = blockIdx.x * 128, tid = threadIdx.x;
+  for (int i = tid; i < L * N4; i += 128) {
+    const int k = i / N4, n = i - k * N4;
+    Wt[i] = n < N ? W[n * L + k] : 0.f;
+  }
+  const int seg = 127 * stride + L;
+  const float* xb = x + (size_t)b * T;
+  for (int i = tid; i < seg; i += 128) {
+    const int t = f0 * stride + i - pad_left;
+    xs[i] = (t >= 0 && t < T) ? xb[t] : 0.f;
+  }
+  __syncthreads();
+  float xw[L];
+#pragma unroll
+  for (int k = 0; k < L; ++k) xw[k] = xs[tid * stride + k];
+  const int f = f0 + tid;
+  const bool valid = f < frames;
+  const bool inb = f < pitch;
+  float* wb = w + (size_t)b * N * pitch + (inb ? f : 0);
+  double s = 0.0, ss = 0.0;
+  float ls = 0.f, lss = 0.f;
+  for (int n = 0; n < N; n += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const float4 wv = *reinterpret_cast<const float4*>(&Wt[k * N4 + n]);
+      a0 = fmaf(wv.x, xw[k], a0);
+      a1 = fmaf(wv.y, xw[k], a1);
+      a2 = fmaf(wv.z, xw[k], a2);
+      a3 = fmaf(wv.w, xw[k], a3);
+    }
+    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+    if (!valid) { a0 = a1 = a2 = a3 = 0.f; }
+    if (inb) wb[(size_t)n * pitch] = a0;
+    if (n + 1 < N) { if (inb) wb[(size_t)(n + 1) * pitch] = a1; } else a1 = 0.f;
+    if (n + 2 < N) { if (inb) wb[(size_t)(n + 2) * pitch] = a2; } else a2 = 0.f;
+    if (n + 3 < N) { if (inb) wb[(size_t)(n + 3) * pitch] = a3; } else a3 = 0.f;
+    ls += (a0 + a1) + (a2 + a3);
+    lss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    if ((n & 63) == 60) { s += ls; ss += lss; ls = 0.f; lss = 0.f; }  // spill fp32 partials to double
+  }
+  if (stats != nullptr) {
+    s += ls; ss += lss;
+    block_sum2_d(s, ss, red);
+    if (tid == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+  }
+}
+
+template <int L>
+static int launch_encoder(const float* x, const float* W, float* w, int B, int T, int pad_left, int N, int stride,
+                          int frames, int pitch, int relu, double* stats, cudaStream_t st) {
+  const int N4 = (N + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)L * N4 + 127 * stride + L);
+  if (smem > 200 * 1024) return CTN_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_encoder<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((pitch + 127) / 128, B);
+  k_encoder<L><<<grid, 128, smem, st>>>(x, W, w, T, pad_left, N, stride, frames, pitch, relu, stats);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+extern "C" int ctn_encoder_fwd(const float* x, const float* enc_w, float* w, int B, int T, int pad_left, int pad_right,
+                               int N, int L, int stride, int relu, int w_pitch, double* stats, ctn_stream_t stream) {
+  LaunchScope scope;
+  if (!x || !enc_w || !w || B <= 0 || T <= 0 || N <= 0 || L <= 0 || stride <= 0) return CTN_EINVAL;
+  const int Tp = T + pad_left + pad_right;
+  if (Tp < L || (Tp - L) % stride != 0) return CTN_EINVAL;
+  const int frames = (Tp - L) / stride + 1;
+  if (w_pitch < frames) return CTN_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+#define ENC_CASE(LL) case LL: return launch_encoder<LL>(x, enc_w, w, B, T, pad_left, N, stride, frames, w_pitch, relu, stats, st)
+  switch (L) {
+    ENC_CASE(2); ENC_CASE(4); ENC_CASE(8); ENC_CASE(16); ENC_CASE(20); ENC_CASE(32); ENC_CASE(40); ENC_CASE(64);
+    default: return CTN_EUNSUPPORTED;
+  }
+#undef ENC_CASE
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder: full[bs][j*stride + q] = sum_{r<R} sum_n what[bs][n][j-r] * Wd[n][r*stride + q]
+//          (ConvTranspose1d, src/models/filterbank.py:245-247), R = L/stride overlapping frames.
+// thread = output segment j (stride consecutive samples); grid (ceil(nseg/128), BS), block 128.
+// The crop of src/models/conv_tasnet.py:169 is fused: y[t] = full[t + crop_left].
+// ------------------------------------------------------------------------------------------------
+template <int STRIDE, int R>
+__global__ void __launch_bounds__(128) k_decoder(const float* __restrict__ what, const float* __restrict__ Wd,
+                                                 float* __restrict__ y, int N, int frames, int in_pitch,
+                                                 int crop_left, int T_out) {
+  constexpr int L = STRIDE * R;
+  extern __shared__ float sm[];  // Wd as [N][L]
+  const int tid = threadIdx.x, bs = blockIdx.y;
+  for (int i = tid; i < N * L; i += 128) sm[i] = Wd[i];
+  __syncthreads();
+  const int j = blockIdx.x * 128 + tid;  // segment index, 0 .. frames+R-2
+  const float* wb = what + (size_t)bs * N * in_pitch;
+  float acc[STRIDE];
+#pragma unroll
+  for (int q = 0; q < STRIDE; ++q) acc[q] = 0.f;
+  bool ok[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) ok[r] = (j - r) >= 0 && (j - r) < frames;
+  for (int n = 0; n < N; ++n) {
+    const float* wrow = wb + (size_t)n * in_pitch;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float v = ok[r] ? __ldg(wrow + (j - r)) : 0.f;
+#pragma unroll
+      for (int q = 0; q < STRIDE; ++q) acc[q] = fmaf(v, sm[n * L + r * STRIDE + q], acc[q]);
+    }
+  }
+  float* yb = y + (size_t)bs * T_out;
+#pragma unroll
+  for (int q = 0; q < STRIDE; ++q) {
+    const int t = j * STRIDE + q - crop_left;
+    if (t >= 0 && t < T_out && j < frames + R - 1) yb[t] = acc[q];
+  }
+}
+
+// generic fallback: thread = output sample
+__global__ void __launch_bounds__(128) k_decoder_generic(const float* __restrict__ what, const float* __restrict__ Wd,
+                                                         float* __restrict__ y, int N, int frames, int in_pitch, int L,
+                                                         int stride, int crop_left, int T_out) {
+  const int bs = blockIdx.y;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T_out) return;
+  const int tf = t + crop_left;
+  const int R = L / stride;
+  const int j = tf / stride, q = tf - j * stride;
+  const float* wb = what + (size_t)bs * N * in_pitch;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const int f = j - r;
+    if (f < 0 || f >= frames) continue;
+    for (int n = 0; n < N; ++n) acc = fmaf(__ldg(wb + (size_t)n * in_pitch + f), __ldg(Wd + n * L + r * stride + q), acc);
+  }
+  y[(size_t)bs * T_out + t] = acc;
+}
+
+template <int STRIDE, int R>
+static int launch_decoder(const float* what, const float* Wd, float* y, int BS, int N, int frames, int in_pitch,
+                          int crop_left, int T_out, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)N * STRIDE * R;
+  if (smem > 200 * 1024) return CTN_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_decoder<STRIDE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int nseg = frames + R - 1;
+  dim3 grid((nseg + 127) / 128, BS);
+  k_decoder<STRIDE, R><<<grid, 128, smem, st>>>(what, Wd, y, N, frames, in_pitch, crop_left, T_out);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+extern "C" int ctn_decoder_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int N, int frames,
+                               int in_pitch, int L, int stride, int crop_left, int T_out, ctn_stream_t stream) {
+  LaunchScope scope;
+  if (!w_hat || !dec_w || !y || BS <= 0 || N <= 0 || frames <= 0 || L <= 0 || stride <= 0 || L % stride != 0)
+    return CTN_EINVAL;
+  if (in_pitch < frames) return CTN_EINVAL;
+  const int full = (frames - 1) * stride + L;
+  if (crop_left < 0 || T_out <= 0 || crop_left + T_out > full) return CTN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = L / stride;
+  if (stride == 8 && R == 2) return launch_decoder<8, 2>(w_hat, dec_w, y, BS, N, frames, in_pitch, crop_left, T_out, st);
+  if (stride == 1 && R == 2) return launch_decoder<1, 2>(w_hat, dec_w, y, BS, N, frames, in_pitch, crop_left, T_out, st);
+  if (stride == 10 && R == 2) return launch_decoder<10, 2>(w_hat, dec_w, y, BS, N, frames, in_pitch, crop_left, T_out, st);
+  if (stride == 2 && R == 2) return launch_decoder<2, 2>(w_hat, dec_w, y, BS, N, frames, in_pitch, crop_left, T_out, st);
+  dim3 grid((T_out + 127) / 128, BS);
+  k_decoder_generic<<<grid, 128, 0, st>>>(w_hat, dec_w, y, N, frames, in_pitch, L, stride, crop_left, T_out);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}

@@ -1,0 +1,58 @@
+// Internal (non-ABI) declarations shared by the .cu translation units.
+#pragma once
+#include "ctn_common.cuh"
+
+// ---- folded / derived parameters (built per forward by ctn_prep_*; weights may change every step) ----------
+// For a 1x1 conv applied to a gLN output,  W (gamma*(u-mu)*rstd + beta) + b  ==  rstd * (W diag(gamma)) u
+//   + (b + W beta) - mu*rstd * (W gamma):   Wf = W diag(gamma),  v1 = b + W beta,  v2 = W gamma.
+struct FoldedConv {
+  float* Wf;  // (M, K)
+  float* v1;  // (M)
+  float* v2;  // (M)
+};
+
+// epilogue / prologue selectors of the pointwise (1x1) contraction kernels
+enum { PRO_NONE = 0, PRO_PRELU = 1 };
+enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3 };
+
+struct PwArgs {
+  const float* A;      // (B, K, pitch) activations
+  const float* W;      // (M, K) row-major weights
+  float* D;            // (B, M, pitch)
+  int B, M, K, frames, pitch;
+  // prologue
+  const float* pro_slope;  // PRO_PRELU
+  // epilogue
+  const float* bias;       // EPI_H / EPI_MASK: (M)
+  const float* slope;      // EPI_H: PReLU slope (1)
+  const float* v1;         // EPI_HEAD
+  const float* v2;         // EPI_HEAD
+  const double* stats_in;  // EPI_HEAD: (B,2) of the input tensor
+  double n_in;             // EPI_HEAD: element count of a gLN group of the input
+  float eps;               // EPI_HEAD
+  double* stats_out;       // EPI_H: (B,2) += (sum, sumsq) over valid outputs
+  const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
+  int Nb;                  // EPI_MASK: n_basis
+  float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)
+};
+
+// fp32 CUDA-core path (ctn_tcn_simt.cu)
+int ctn_pw_simt(const PwArgs& a, int pro, int epi, cudaStream_t st);
+// tcgen05 path (ctn_umma.cu); math = CTN_MATH_TF32X3 / CTN_MATH_TF32
+int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st);
+int ctn_umma_selftest_available(void);
+
+int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
+                  int row_offset, cudaStream_t st);
+
+// depthwise stage: u = PReLU(dwconv(gLN1(h))) (+ stats2), all (B,H,pitch)
+int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_b, const float* dw_w, const float* dw_b,
+               const float* slope, const double* stats_in, double* stats_out, int B, int H, int frames, int pitch, int P,
+               int dilation, int causal, float eps, cudaStream_t st);
+
+// finishing: x += rstd2*outraw[:Bc] + c ; skip (+)= rstd2*outraw[Bc:] + c
+int ctn_finish_fwd(const float* outraw, const FoldedConv f, const double* stats2, double n2, float eps, float* x,
+                   float* skip, int B, int Bc, int Sc, int has_out, int skip_init, int frames, int pitch, cudaStream_t st);
+
+int ctn_copy_to_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);
+int ctn_copy_from_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);

@@ -1,0 +1,239 @@
+"""Conv-TasNet on hand-written sm_100a kernels, behind the reference's class API.
+
+Mirrors src/models/conv_tasnet.py of the reference: ``ConvTasNet`` (:16-320; constructor :57-66, forward :116-119,
+extract_latent :121-171, get_config :173-198, build_model :199-236) and ``Separator`` (:322-378).  Module tree and
+``state_dict`` keys are identical, so reference checkpoints load with ``load_state_dict``.
+
+One forward is one C call (ctn_convtasnet_fwd, include/ctn_b200.h): encoder (+gLN statistics) -> gLN folded into the
+bottleneck 1x1 -> R*X fused residual blocks -> PReLU + mask 1x1 + sigmoid + (w * mask) -> transposed-conv decoder with
+the crop fused.  Internally activations are (batch, channels, pitch) fp32 with pitch = frames rounded up to 128.
+
+Kernel envelope (anything else raises NotImplementedError, there is no eager fallback): enc_basis = dec_basis =
+'trainable', in_channels = 1, 3-D input, dilated, separable, sep_nonlinear='prelu', sep_norm, mask_nonlinear='sigmoid',
+causal=False.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ..utils.filterbank import choose_filterbank
+from ..utils.tasnet import choose_layer_norm
+from . import tdcn as _tdcn
+from .tdcn import TimeDilatedConvNet, block_param_array, resolve_math
+
+EPS = 1e-12
+DEFAULT_MATH = None
+
+
+def _norm_affine(norm):
+    return (norm.norm.weight, norm.norm.bias) if hasattr(norm, "norm") else (norm.gamma, norm.beta)
+
+
+class Separator(nn.Module):
+    def __init__(self, num_features, bottleneck_channels=128, hidden_channels=256, skip_channels=128, kernel_size=3,
+                 num_blocks=3, num_layers=8, dilated=True, separable=True, causal=True, nonlinear='prelu', norm=True,
+                 mask_nonlinear='sigmoid', n_sources=2, eps=EPS):
+        super().__init__()
+        self.num_features, self.n_sources, self.eps, self.causal = num_features, n_sources, eps, causal
+        self.norm1d = choose_layer_norm('cLN' if causal else 'gLN', num_features, causal=causal, eps=eps)
+        self.bottleneck_conv1d = nn.Conv1d(num_features, bottleneck_channels, kernel_size=1, stride=1)
+        # the reference builds the TDCN without forwarding eps (conv_tasnet.py:336-339) -> default 1e-12
+        self.tdcn = TimeDilatedConvNet(bottleneck_channels, hidden_channels=hidden_channels, skip_channels=skip_channels,
+                                       kernel_size=kernel_size, num_blocks=num_blocks, num_layers=num_layers, dilated=dilated,
+                                       separable=separable, causal=causal, nonlinear=nonlinear, norm=norm)
+        self.prelu = nn.PReLU()
+        self.mask_conv1d = nn.Conv1d(skip_channels, n_sources * num_features, kernel_size=1, stride=1)
+        if mask_nonlinear == 'sigmoid':
+            self.mask_softmax = False
+        elif mask_nonlinear == 'softmax':
+            raise NotImplementedError("mask_nonlinear='softmax' is outside the sm_100a kernel envelope")
+        else:
+            raise ValueError("Cannot support {}".format(mask_nonlinear))
+        self.math = None
+
+    # ---- native plumbing -------------------------------------------------------------------------
+    def native_config(self, kernel_size=1, stride=1, enc_relu=False):
+        mode = self.math if self.math is not None else (DEFAULT_MATH if DEFAULT_MATH is not None else _tdcn.DEFAULT_MATH)
+        cfg = self.tdcn.native_config(n_basis=self.num_features, kernel_size=kernel_size, stride=stride,
+                                      n_sources=self.n_sources, enc_relu=int(enc_relu), mask_softmax=0)
+        cfg.math = resolve_math(mode)
+        cfg.eps = float(self.eps)
+        return cfg
+
+    def native_params(self, dev, enc_w=None, dec_w=None):
+        arr, keep = block_param_array(self.tdcn.residual_blocks(), dev)
+        g0, b0 = _norm_affine(self.norm1d)
+        tensors = dict(enc_w=enc_w, norm0_g=g0, norm0_b=b0, bn_w=self.bottleneck_conv1d.weight, bn_b=self.bottleneck_conv1d.bias,
+                       prelu_out=self.prelu.weight, mask_w=self.mask_conv1d.weight, mask_b=self.mask_conv1d.bias, dec_w=dec_w)
+        p = N.Params()
+        for name, t in tensors.items():
+            if t is None:
+                setattr(p, name, None)
+                continue
+            if t.device != dev or t.dtype != torch.float32:
+                raise RuntimeError("parameter {} must be float32 on {}".format(name, dev))
+            if not t.is_contiguous():
+                t = t.contiguous()
+                keep.append(t)
+            setattr(p, name, t.data_ptr())
+        p.blocks = arr
+        keep.append(arr)
+        return p, keep
+
+    def forward(self, input):
+        """input (batch_size, num_features, n_frames) -> mask (batch_size, n_sources, num_features, n_frames)"""
+        if input.dim() != 3 or input.size(1) != self.num_features:
+            raise ValueError("input.size() is expected (?, {}, ?), but given {}".format(self.num_features, tuple(input.size())))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+        w = input.contiguous()
+        dev = N.require_cuda(w)
+        B, _, frames = w.shape
+        cfg = self.native_config()
+        params, keep = self.native_params(dev)
+        need = C.c_size_t(0)
+        N.check(N.ctn_workspace_bytes(C.byref(cfg), B, frames, C.byref(need)), "ctn_workspace_bytes")  # kernel 1, stride 1: T == frames
+        pitch = N.ctn_pitch(frames)
+        extra = 4 * B * self.n_sources * self.num_features * pitch + 1024
+        ws = N.workspace(dev, need.value + extra)
+        base = (ws.data_ptr() + 255) & ~255
+        mask = torch.empty(B, self.n_sources, self.num_features, frames, dtype=torch.float32, device=dev)
+        N.check(N.ctn_separator_fwd(C.byref(cfg), C.byref(params), w.data_ptr(), B, frames, mask.data_ptr(), base,
+                                    ws.numel() - (base - ws.data_ptr()), N.stream_ptr(dev)), "ctn_separator_fwd")
+        return mask
+
+
+class ConvTasNet(nn.Module):
+    def __init__(self, n_basis, kernel_size, stride=None, enc_basis=None, dec_basis=None,
+                 sep_hidden_channels=256, sep_bottleneck_channels=128, sep_skip_channels=128, sep_kernel_size=3,
+                 sep_num_blocks=3, sep_num_layers=8, dilated=True, separable=True, sep_nonlinear='prelu', sep_norm=True,
+                 mask_nonlinear='sigmoid', causal=True, n_sources=2, eps=EPS, **kwargs):
+        super().__init__()
+        if stride is None:
+            stride = kernel_size // 2
+        assert kernel_size % stride == 0, "kernel_size is expected divisible by stride"
+
+        self.in_channels = kwargs.get('in_channels', 1)
+        self.n_basis, self.kernel_size, self.stride = n_basis, kernel_size, stride
+        self.enc_basis, self.dec_basis = enc_basis, dec_basis
+        self.enc_nonlinear = kwargs['enc_nonlinear'] if (enc_basis == 'trainable' and dec_basis != 'pinv') else None
+        self.window_fn, self.enc_onesided, self.enc_return_complex = None, None, None
+
+        self.sep_hidden_channels, self.sep_bottleneck_channels = sep_hidden_channels, sep_bottleneck_channels
+        self.sep_skip_channels, self.sep_kernel_size = sep_skip_channels, sep_kernel_size
+        self.sep_num_blocks, self.sep_num_layers = sep_num_blocks, sep_num_layers
+        self.dilated, self.separable, self.causal = dilated, separable, causal
+        self.sep_nonlinear, self.sep_norm, self.mask_nonlinear = sep_nonlinear, sep_norm, mask_nonlinear
+        self.n_sources, self.eps = n_sources, eps
+
+        encoder, decoder = choose_filterbank(n_basis, kernel_size=kernel_size, stride=stride, enc_basis=enc_basis,
+                                             dec_basis=dec_basis, **kwargs)
+        self.encoder = encoder
+        self.separator = Separator(n_basis, bottleneck_channels=sep_bottleneck_channels, hidden_channels=sep_hidden_channels,
+                                   skip_channels=sep_skip_channels, kernel_size=sep_kernel_size, num_blocks=sep_num_blocks,
+                                   num_layers=sep_num_layers, dilated=dilated, separable=separable, causal=causal,
+                                   nonlinear=sep_nonlinear, norm=sep_norm, mask_nonlinear=mask_nonlinear, n_sources=n_sources,
+                                   eps=eps)
+        self.decoder = decoder
+        self.math = None  # numeric mode override: 'fp32' | 'tf32x3' | 'tf32'
+        self.last_launches = 0
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def forward(self, input):
+        output, _ = self._run(input, want_latent=False)
+        return output
+
+    def extract_latent(self, input):
+        """input (batch_size, 1, T) -> output (batch_size, n_sources, T), latent (batch_size, n_sources, n_basis, T')"""
+        return self._run(input, want_latent=True)
+
+    def get_config(self):
+        return {
+            'in_channels': self.in_channels, 'n_basis': self.n_basis, 'kernel_size': self.kernel_size, 'stride': self.stride,
+            'enc_basis': self.enc_basis, 'dec_basis': self.dec_basis, 'enc_nonlinear': self.enc_nonlinear,
+            'window_fn': self.window_fn, 'enc_onesided': self.enc_onesided, 'enc_return_complex': self.enc_return_complex,
+            'sep_hidden_channels': self.sep_hidden_channels, 'sep_bottleneck_channels': self.sep_bottleneck_channels,
+            'sep_skip_channels': self.sep_skip_channels, 'sep_kernel_size': self.sep_kernel_size,
+            'sep_num_blocks': self.sep_num_blocks, 'sep_num_layers': self.sep_num_layers,
+            'dilated': self.dilated, 'separable': self.separable, 'causal': self.causal,
+            'sep_nonlinear': self.sep_nonlinear, 'sep_norm': self.sep_norm, 'mask_nonlinear': self.mask_nonlinear,
+            'n_sources': self.n_sources, 'eps': self.eps,
+        }
+
+    def get_package(self):
+        return self.get_config()
+
+    @classmethod
+    def build_model(cls, model_path, load_state_dict=False):
+        """Rebuild from a trainer checkpoint (dict = get_config() + 'state_dict'); tolerates the legacy keys
+        n_bases / enc_bases / dec_bases like the reference (conv_tasnet.py:204-206)."""
+        config = torch.load(model_path, map_location=lambda storage, loc: storage, weights_only=False)
+        get = config.get
+        model = cls(
+            get('n_bases') or config['n_basis'], in_channels=get('in_channels') or 1,
+            kernel_size=config['kernel_size'], stride=config['stride'],
+            enc_basis=get('enc_bases') or config['enc_basis'], dec_basis=get('dec_bases') or config['dec_basis'],
+            enc_nonlinear=config['enc_nonlinear'], window_fn=config['window_fn'],
+            enc_onesided=get('enc_onesided') or None, enc_return_complex=get('enc_return_complex') or None,
+            sep_hidden_channels=config['sep_hidden_channels'], sep_bottleneck_channels=config['sep_bottleneck_channels'],
+            sep_skip_channels=config['sep_skip_channels'], sep_kernel_size=config['sep_kernel_size'],
+            sep_num_blocks=config['sep_num_blocks'], sep_num_layers=config['sep_num_layers'],
+            dilated=config['dilated'], separable=config['separable'], causal=config['causal'],
+            sep_nonlinear=config['sep_nonlinear'], sep_norm=config['sep_norm'], mask_nonlinear=config['mask_nonlinear'],
+            n_sources=config['n_sources'], eps=config['eps'])
+        if load_state_dict:
+            model.load_state_dict(config['state_dict'])
+        return model
+
+    @classmethod
+    def build_from_pretrained(cls, root="./pretrained", quiet=False, load_state_dict=True, **kwargs):
+        raise NotImplementedError("pretrained download (Google Drive) is outside this path; use build_model(path)")
+
+    @property
+    def num_parameters(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    # ---- native plumbing ---------------------------------------------------------------------------
+    def native_config(self):
+        sep = self.separator
+        saved = sep.math
+        if self.math is not None:
+            sep.math = self.math
+        try:
+            cfg = sep.native_config(kernel_size=self.kernel_size, stride=self.stride, enc_relu=self.encoder.nonlinear)
+        finally:
+            sep.math = saved
+        return cfg
+
+    def native_params(self, dev):
+        return self.separator.native_params(dev, enc_w=self.encoder.conv1d.weight, dec_w=self.decoder.conv_transpose1d.weight)
+
+    def _run(self, input, want_latent):
+        n_dims = input.dim()
+        if n_dims == 3:
+            assert input.size(1) == 1, "input.size() is expected (?, 1, ?), but given {}".format(input.size())
+        elif n_dims == 4:
+            assert input.size(1) == 1, "input.size() is expected (?, 1, ?, ?), but given {}".format(input.size())
+            raise NotImplementedError("multichannel (4-D) input is outside the sm_100a kernel envelope")
+        else:
+            raise ValueError("Not support {} dimension input".format(n_dims))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+        x = input.contiguous()
+        dev = N.require_cuda(x)
+        B, _, T = x.shape
+        frames, _, _ = N.frames_of(T, self.kernel_size, self.stride)
+        cfg = self.native_config()
+        params, keep = self.native_params(dev)
+        need = C.c_size_t(0)
+        N.check(N.ctn_workspace_bytes(C.byref(cfg), B, T, C.byref(need)), "ctn_workspace_bytes")
+        ws = N.workspace(dev, need.value)
+        base = (ws.data_ptr() + 255) & ~255
+        out = torch.empty(B, self.n_sources, T, dtype=torch.float32, device=dev)
+        latent = torch.empty(B, self.n_sources, self.n_basis, frames, dtype=torch.float32, device=dev) if want_latent else None
+        N.check(N.ctn_convtasnet_fwd(C.byref(cfg), C.byref(params), x.data_ptr(), B, T, out.data_ptr(), N.ptr(latent), base,
+                                     ws.numel() - (base - ws.data_ptr()), N.stream_ptr(dev)), "ctn_convtasnet_fwd")
+        self.last_launches = N.ctn_last_launch_count()
+        return out, latent

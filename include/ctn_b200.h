@@ -1,0 +1,199 @@
+/* ctn_b200.h -- C ABI of the B200-native Conv-TasNet separation path.
+ *
+ * The reference (tky823/DNN-based_source_separation) has NO native/FFI layer: the path sits behind
+ * Python nn.Module classes.  This header is therefore the boundary a maintainer would
+ * bind from those classes (ctypes stub shown in INTEGRATION.md).  Each entry point names the reference
+ * interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw `float*` / `int64_t*`; `ctn_stream_t` is a cudaStream_t.
+ *   - every call is asynchronous on `stream`, never allocates or frees, never retains pointers.
+ *   - return 0 on success, negative CTN_E* for argument / envelope errors, positive = cudaError_t.
+ *   - activations inside the library use (batch, channels, pitch) fp32 with pitch = ctn_pitch(frames)
+ *     (frames rounded up to 128) so every row is 512-byte aligned; tensors crossing the boundary are
+ *     PyTorch-contiguous.
+ *   - there is no CPU fallback.  Unsupported configurations return CTN_EUNSUPPORTED.
+ */
+#ifndef CTN_B200_H
+#define CTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ctn_stream_t; /* cudaStream_t */
+
+#define CTN_VERSION 100 /* 0.1.0 */
+
+enum ctn_status {
+  CTN_OK = 0,
+  CTN_EINVAL = -1,       /* bad shape / null pointer              -> Python ValueError        */
+  CTN_EUNSUPPORTED = -2, /* outside the kernel envelope           -> Python NotImplementedError */
+  CTN_EALIGN = -3,       /* pointer / pitch alignment             -> Python ValueError        */
+  CTN_EWORKSPACE = -4,   /* workspace too small                   -> Python RuntimeError      */
+  CTN_ENOTBUILT = -5     /* kernel family not compiled into lib   -> Python RuntimeError      */
+};
+
+/* numeric mode of the dense 1x1 contractions */
+enum ctn_math {
+  CTN_MATH_FP32 = 0,   /* CUDA-core FFMA, exact fp32 products (verification mode)          */
+  CTN_MATH_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass hi/lo split, fp32 accumulate (default) */
+  CTN_MATH_TF32 = 2    /* tcgen05 kind::tf32 single pass (fast mode, looser tolerance)      */
+};
+
+/* Constructor arguments of ConvTasNet / Separator (src/models/conv_tasnet.py:57-66, 322-328). */
+typedef struct ctn_config {
+  int32_t n_basis;      /* N  */
+  int32_t kernel_size;  /* L  */
+  int32_t stride;       /* L/2 by default */
+  int32_t bottleneck;   /* B  (sep_bottleneck_channels) */
+  int32_t hidden;       /* H  (sep_hidden_channels)     */
+  int32_t skip;         /* Sc (sep_skip_channels)       */
+  int32_t sep_kernel;   /* P  (sep_kernel_size)         */
+  int32_t num_blocks;   /* R  */
+  int32_t num_layers;   /* X  */
+  int32_t n_sources;    /* S  */
+  int32_t causal;       /* 0: gLN (supported), 1: cLN (CTN_EUNSUPPORTED in the fused path) */
+  int32_t enc_relu;     /* enc_nonlinear == 'relu' */
+  int32_t mask_softmax; /* mask_nonlinear == 'softmax' -> CTN_EUNSUPPORTED */
+  int32_t math;         /* enum ctn_math */
+  float eps;            /* Separator head norm eps (ConvTasNet eps)            */
+  float eps_tcn;        /* eps of the norms inside the TDCN (reference passes the default 1e-12) */
+} ctn_config_t;
+
+/* Parameters of one ResidualBlock1d (+ its DepthwiseSeparableConv1d), src/models/tdcn.py:77-196.
+ * state_dict names (prefix separator.tdcn.net.{r}.net.{x}.) are given per field. */
+typedef struct ctn_block_params {
+  const float* bottleneck_w; /* bottleneck_conv1d.weight (H,B,1)                       */
+  const float* bottleneck_b; /* bottleneck_conv1d.bias   (H)                           */
+  const float* prelu1;       /* nonlinear1d.weight (1)                                 */
+  const float* norm1_g;      /* norm1d.norm.weight (H)                                 */
+  const float* norm1_b;      /* norm1d.norm.bias   (H)                                 */
+  const float* dw_w;         /* separable_conv1d.depthwise_conv1d.weight (H,1,P)       */
+  const float* dw_b;         /* separable_conv1d.depthwise_conv1d.bias   (H)           */
+  const float* prelu2;       /* separable_conv1d.nonlinear1d.weight (1)                */
+  const float* norm2_g;      /* separable_conv1d.norm1d.norm.weight (H)                */
+  const float* norm2_b;      /* separable_conv1d.norm1d.norm.bias   (H)                */
+  const float* out_w;        /* separable_conv1d.output_pointwise_conv1d.weight (B,H,1) or NULL (last block) */
+  const float* out_b;        /* ...bias (B) or NULL                                    */
+  const float* skip_w;       /* separable_conv1d.skip_pointwise_conv1d.weight (Sc,H,1) */
+  const float* skip_b;       /* ...bias (Sc)                                           */
+} ctn_block_params_t;
+
+typedef struct ctn_params {
+  const float* enc_w;      /* encoder.conv1d.weight (N,1,L)                  */
+  const float* norm0_g;    /* separator.norm1d.norm.weight (N)               */
+  const float* norm0_b;    /* separator.norm1d.norm.bias   (N)               */
+  const float* bn_w;       /* separator.bottleneck_conv1d.weight (B,N,1)     */
+  const float* bn_b;       /* separator.bottleneck_conv1d.bias   (B)         */
+  const ctn_block_params_t* blocks; /* HOST array of R*X entries (device pointers inside) */
+  const float* prelu_out;  /* separator.prelu.weight (1)                      */
+  const float* mask_w;     /* separator.mask_conv1d.weight (S*N,Sc,1)        */
+  const float* mask_b;     /* separator.mask_conv1d.bias   (S*N)             */
+  const float* dec_w;      /* decoder.conv_transpose1d.weight (N,1,L)        */
+} ctn_params_t;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int ctn_version(void);
+const char* ctn_strerror(int status);
+/* 1 if the tcgen05 (sm_100a) kernel family is compiled in */
+int ctn_has_tcgen05(void);
+
+/* ---- geometry helpers (host only) ----------------------------------------------------------
+ * ConvTasNet.extract_latent padding rule, src/models/conv_tasnet.py:145-149. */
+int ctn_frames(int T, int kernel_size, int stride, int* pad_left, int* pad_right); /* returns T' or <0 */
+int ctn_pitch(int frames);                                                         /* frames rounded up to 128 */
+/* bytes of device workspace ctn_convtasnet_fwd needs for (batch, T) */
+int ctn_workspace_bytes(const ctn_config_t* cfg, int batch, int T, size_t* bytes);
+
+/* ---- module-level entry points -------------------------------------------------------------- */
+
+/* Encoder.forward, src/models/filterbank.py:222-229 (Conv1d(1,N,L,stride,bias=False) [+ReLU]).
+ * x (B,1,T) contiguous; virtual zero padding pad_left/pad_right; w (B,N,w_pitch) with frames valid columns,
+ * columns [frames,w_pitch) are written as zero.  stats (nullable): double[B][2] += (sum, sumsq) over valid. */
+int ctn_encoder_fwd(const float* x, const float* enc_w, float* w, int B, int T, int pad_left, int pad_right,
+                    int N, int L, int stride, int relu, int w_pitch, double* stats, ctn_stream_t stream);
+
+/* Decoder.forward, src/models/filterbank.py:245-247 (ConvTranspose1d(N,1,L,stride,bias=False)), fused with the
+ * crop of conv_tasnet.py:169: y[bs][t] = full[bs][t + crop_left], t in [0,T_out).  w_hat (BS,N,in_pitch). */
+int ctn_decoder_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int N, int frames, int in_pitch,
+                    int L, int stride, int crop_left, int T_out, ctn_stream_t stream);
+
+/* GlobalLayerNorm.forward, src/modules/norm.py:18,32 (GroupNorm(1,C,eps)).  x,y (B,C,T) contiguous.
+ * scratch: double[B][2], zero-initialised by the callee. */
+int ctn_gln_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T, float eps,
+                double* scratch, ctn_stream_t stream);
+
+/* CumulativeLayerNorm1d.forward, src/modules/norm.py:78-90.  x,y (B,C,T) contiguous; scratch double[B][T][2]. */
+int ctn_cln_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T, float eps,
+                double* scratch, ctn_stream_t stream);
+
+/* TimeDilatedConvNet.forward == TemporalConvNet.forward, src/models/tdcn.py:29-41 (src/models/tcn.py:37-49).
+ * x (B,bottleneck,frames) contiguous -> skip sum (B,skip,frames) contiguous.  Uses cfg fields bottleneck, hidden,
+ * skip, sep_kernel, num_blocks, num_layers, causal, math, eps_tcn.  workspace sized by ctn_tcn_workspace_bytes. */
+int ctn_tcn_workspace_bytes(const ctn_config_t* cfg, int batch, int frames, size_t* bytes);
+int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, const float* x, float* skip_out, int B,
+                int frames, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
+
+/* ConvTasNet.forward / extract_latent, src/models/conv_tasnet.py:116-171.
+ * x (B,1,T) -> out (B,S,T); latent (nullable) (B,S,N,frames) contiguous. */
+int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* x, int B, int T, float* out,
+                       float* latent, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
+
+/* Separator.forward, src/models/conv_tasnet.py:359-378: w (B,N,frames) -> mask (B,S,N,frames), both contiguous. */
+int ctn_separator_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* w, int B, int frames,
+                      float* mask, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
+
+/* sisdr, src/criterion/sdr.py:122-139: est,tgt (rows,T) contiguous -> out (rows). scratch double[rows][4]. */
+int ctn_sisdr_fwd(const float* est, const float* tgt, int rows, int T, float eps, float* out, double* scratch,
+                  ctn_stream_t stream);
+
+/* PIT1d(NegSISDR(reduction='mean')), src/criterion/pit.py:9-44,71-77 + src/criterion/sdr.py:198-227.
+ * est,tgt (B,S,T) contiguous.  loss_b (B) = min over permutations of -mean_i SI-SDR(est_i, tgt_perm[i]);
+ * perm (B,S) int64, estimate i <-> target perm[i] (first minimum on ties, lexicographic permutation order);
+ * loss_mean (1) = mean over the batch.  pair_sisdr (nullable) (B,S,S) = SI-SDR(est_i, tgt_j).
+ * scratch: double[B][S*S*2 + S], zero-initialised by the callee.  S <= 6. */
+int ctn_sisdr_pit_fwd(const float* est, const float* tgt, int B, int S, int T, float eps, float* loss_b,
+                      int64_t* perm, float* loss_mean, float* pair_sisdr, double* scratch, ctn_stream_t stream);
+size_t ctn_sisdr_pit_scratch_bytes(int B, int S);
+
+/* End-to-end call with HOST buffers (the "e2e" leg): copies x_host (B,1,T) and tgt_host (B,S,T) (pinned or
+ * pageable) to the device staging areas, runs ctn_convtasnet_fwd + ctn_sisdr_pit_fwd, copies back out_host
+ * (nullable, (B,S,T)), loss_mean_host (1), perm_host (B,S).  All on `stream`; the caller synchronises.
+ * dev_io: device staging, at least ctn_host_io_bytes(). */
+size_t ctn_host_io_bytes(const ctn_config_t* cfg, int B, int T);
+int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params, const float* x_host,
+                             const float* tgt_host, int B, int T, float* out_host, float* loss_mean_host,
+                             int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
+                             ctn_stream_t stream);
+
+/* number of kernel launches the last ctn_* call on this thread enqueued (for bench.py's gpu_launches) */
+int ctn_last_launch_count(void);
+
+/* Stage timing with CUDA events recorded on the launching stream (bench.py's roofline leg).  ctn_profile_enable(1)
+ * makes every following ctn_* call on this thread bracket its kernel groups with events; ctn_profile_read
+ * synchronises on them, ADDS per-stage milliseconds / launch counts into the caller's arrays (length CTN_NSTAGES)
+ * and recycles the events. */
+enum ctn_stage {
+  CTN_ST_PREP = 0,   /* weight folding / operand images           */
+  CTN_ST_ENC = 1,    /* encoder                                   */
+  CTN_ST_HEAD = 2,   /* gLN0 + bottleneck 1x1                     */
+  CTN_ST_PW1 = 3,    /* per block: 1x1 B->H (+PReLU, stats)       */
+  CTN_ST_DW = 4,     /* per block: gLN1 + depthwise + PReLU       */
+  CTN_ST_PW2 = 5,    /* per block: [out;skip] 1x1 H->B+Sc         */
+  CTN_ST_FIN = 6,    /* per block: residual / skip accumulation   */
+  CTN_ST_MASK = 7,   /* PReLU + mask 1x1 + sigmoid + w*mask       */
+  CTN_ST_DEC = 8,    /* decoder                                   */
+  CTN_ST_LOSS = 9,   /* SI-SDR + PIT                              */
+  CTN_NSTAGES = 10
+};
+int ctn_profile_enable(int enable);
+int ctn_profile_read(double* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTN_B200_H */

@@ -87,11 +87,7 @@ def gln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = E
 
     Per sample: mean / biased variance over all (C, T); y = (x-mean)/sqrt(var+eps)*gamma_c+beta_c.
     """
-    dims = tuple(range(1, x.dim()))
-    mean = x.mean(dim=dims, keepdim=True)
-    var = x.var(dim=dims, unbiased=False, keepdim=True)
-    shape = [1, -1] + [1] * (x.dim() - 2)
-    return (x - mean) / torch.sqrt(var + eps) * gamma.view(shape) + beta.view(shape)
+    return F.group_norm(x, 1, gamma, beta, eps)  # the ATen op nn.GroupNorm dispatches to
 
 
 def cln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = EPS) -> torch.Tensor:
@@ -120,7 +116,7 @@ def _norm(x, sd, prefix, causal, eps):
 
 def prelu(x: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
     """nn.PReLU() with a single shared slope (src/models/tdcn.py:90,161)."""
-    return torch.where(x >= 0, x, a.view(-1)[0] * x)
+    return F.prelu(x, a.view(-1))
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,354 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``).  Every check goes through the Python mirror of the
+reference API -> ctypes -> C ABI (libctn_b200.so) -> sm_100a kernels, and is compared against
+  (a) golden vectors minted from the unmodified reference (tests/golden/*.pt), and
+  (b) the CPU oracle (oracle/convtasnet_oracle.py) on the same seeded inputs.
+
+Tolerances (the reference's own fp32-vs-fp64 noise is 1.3e-6 abs on outputs of |max| 1.3, and its
+8-thread vs 1-thread fp32 results differ by 1e-5):
+  * model outputs, fp32-parity modes ('fp32' FFMA and 'tf32x3' tcgen05 split):  rtol 1e-4, atol 2e-5
+  * PIT permutation indices: bit-exact;  loss: 1e-4 dB absolute
+  * single-pass 'tf32' fast mode: rtol 2e-2, atol 5e-3 (stated, looser)
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+import convtasnet_oracle as O
+from ctn_b200 import _native as N
+from ctn_b200.models.conv_tasnet import ConvTasNet
+from ctn_b200.models.tdcn import TimeDilatedConvNet
+from ctn_b200.models.tcn import TemporalConvNet
+from ctn_b200.models.filterbank import Encoder, Decoder
+from ctn_b200.modules.norm import GlobalLayerNorm, CumulativeLayerNorm1d
+from ctn_b200.criterion.sdr import NegSISDR, SISDR, sisdr
+from ctn_b200.criterion.pit import PIT1d
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 2e-5
+MODES = ["fp32"] + (["tf32x3"] if N.ctn_has_tcgen05() else [])
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def build_model(cfg: O.OracleConfig, sd, math=None):
+    m = ConvTasNet(cfg.n_basis, cfg.kernel_size, stride=cfg.stride, enc_basis='trainable', dec_basis='trainable',
+                   enc_nonlinear=cfg.enc_nonlinear, sep_hidden_channels=cfg.sep_hidden_channels,
+                   sep_bottleneck_channels=cfg.sep_bottleneck_channels, sep_skip_channels=cfg.sep_skip_channels,
+                   sep_kernel_size=cfg.sep_kernel_size, sep_num_blocks=cfg.sep_num_blocks, sep_num_layers=cfg.sep_num_layers,
+                   dilated=cfg.dilated, separable=cfg.separable, sep_nonlinear=cfg.sep_nonlinear, sep_norm=cfg.sep_norm,
+                   mask_nonlinear=cfg.mask_nonlinear, causal=cfg.causal, n_sources=cfg.n_sources, eps=cfg.eps)
+    m.load_state_dict(sd, strict=True)
+    m.math = math
+    return m.cuda().eval()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# module level
+# ---------------------------------------------------------------------------------------------------------------
+def test_encoder_decoder_golden(golden_dir):
+    m = _load(golden_dir, "modules")
+    for k in [k for k in m if k.startswith("encdec_")]:
+        r = m[k]
+        _, Nn, L, S, T, relu = k.split("_")
+        Nn, L, S = int(Nn[1:]), int(L[1:]), int(S[1:])
+        enc = Encoder(1, Nn, kernel_size=L, stride=S, nonlinear='relu' if int(relu) else None)
+        dec = Decoder(Nn, 1, kernel_size=L, stride=S)
+        enc.load_state_dict({"conv1d.weight": r["We"]})
+        dec.load_state_dict({"conv_transpose1d.weight": r["Wd"]})
+        enc, dec = enc.cuda(), dec.cuda()
+        with torch.no_grad():
+            w = enc(r["x"].cuda())
+            y = dec(w)
+        torch.testing.assert_close(w.cpu(), r["w"], rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(y.cpu(), r["y"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("N_,L,S,T,B", [(512, 16, 8, 32000, 2), (64, 2, 1, 777, 3), (48, 20, 10, 1000, 2), (33, 8, 4, 203, 1),
+                                       (16, 32, 16, 4096, 2), (8, 16, 8, 16, 1)])
+def test_encoder_decoder_oracle(N_, L, S, T, B):
+    g = torch.Generator().manual_seed(N_ + T)
+    enc, dec = Encoder(1, N_, kernel_size=L, stride=S).cuda(), Decoder(N_, 1, kernel_size=L, stride=S).cuda()
+    x = torch.randn(B, 1, T, generator=g)
+    with torch.no_grad():
+        w = enc(x.cuda())
+        y = dec(w)
+    w_ref = O.encoder_fwd(x, enc.conv1d.weight.detach().cpu(), S)
+    y_ref = O.decoder_fwd(w_ref, dec.conv_transpose1d.weight.detach().cpu(), S)
+    torch.testing.assert_close(w.cpu(), w_ref, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(y.cpu(), y_ref, rtol=1e-5, atol=5e-6)
+
+
+def test_norms_golden(golden_dir):
+    m = _load(golden_dir, "modules")
+    with torch.no_grad():
+        gl = GlobalLayerNorm(3).cuda()
+        torch.testing.assert_close(gl(m["gln_arange_in"].cuda()).cpu(), m["gln_arange_out"], rtol=1e-5, atol=1e-6)
+        cl = CumulativeLayerNorm1d(3).cuda()
+        torch.testing.assert_close(cl(m["gln_arange_in"].cuda()).cpu(), m["cln_arange_out"], rtol=1e-5, atol=1e-6)
+        gl = GlobalLayerNorm(24)
+        gl.load_state_dict({"norm.weight": m["gln_gamma"], "norm.bias": m["gln_beta"]})
+        torch.testing.assert_close(gl.cuda()(m["gln_in"].cuda()).cpu(), m["gln_out"], rtol=1e-5, atol=2e-6)
+        cl = CumulativeLayerNorm1d(24)
+        cl.load_state_dict({"gamma": m["gln_gamma"].view(1, 24, 1), "beta": m["gln_beta"].view(1, 24, 1)})
+        torch.testing.assert_close(cl.cuda()(m["gln_in"].cuda()).cpu(), m["cln_out"], rtol=1e-5, atol=5e-6)
+        # 4-D inputs (norm.py:69-76)
+        x4 = m["gln_in"][:, :, :300].reshape(3, 24, 15, 20)
+        torch.testing.assert_close(cl.cuda()(x4.cuda()).cpu().reshape(3, 24, 300),
+                                   O.cln(m["gln_in"][:, :, :300], m["gln_gamma"], m["gln_beta"]), rtol=1e-5, atol=5e-6)
+        torch.testing.assert_close(gl.cuda()(x4.cuda()).cpu(), O.gln(x4, m["gln_gamma"], m["gln_beta"]), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("cls", [TimeDilatedConvNet, TemporalConvNet])
+def test_tdcn_golden(golden_dir, mode, cls):
+    r = _load(golden_dir, "modules")["tdcn_causal0"]
+    cfg = O.OracleConfig(**r["cfg"])
+    full = O.synth_state_dict(cfg, seed=r["wseed"])
+    sub = {k[len("separator.tdcn."):]: v for k, v in full.items() if k.startswith("separator.tdcn.")}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = cls(12, hidden_channels=24, skip_channels=10, kernel_size=3, num_blocks=2, num_layers=4, dilated=True,
+                  separable=True, causal=False, nonlinear='prelu', norm=True)
+    net.load_state_dict(sub, strict=True)
+    net.math = mode
+    with torch.no_grad():
+        y = net.cuda()(r["x"].cuda())
+    torch.testing.assert_close(y.cpu(), r["y"], rtol=RTOL, atol=ATOL)
+
+
+def test_tdcn_causal_is_loud(golden_dir):
+    net = TimeDilatedConvNet(12, hidden_channels=24, skip_channels=10, num_blocks=1, num_layers=2, separable=True, causal=True,
+                             nonlinear='prelu').cuda()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net(torch.randn(1, 12, 50).cuda())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole model vs golden (reference outputs)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["tiny_gln", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
+def test_model_golden(golden_dir, name, mode):
+    rec = _load(golden_dir, name)
+    cfg = O.OracleConfig(**rec["cfg"])
+    sd = O.synth_state_dict(cfg, seed=rec["wseed"])
+    model = build_model(cfg, sd, math=mode)
+    mixture, sources = O.synth_batch(rec["batch"], cfg.n_sources, rec["T"], seed=rec["xseed"])
+    crit = PIT1d(NegSISDR(), n_sources=cfg.n_sources)
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        out2 = model(mixture.cuda())
+        loss, perm = crit(out, sources.cuda())
+        loss_b, perm_b = crit(out, sources.cuda(), batch_mean=False)
+    assert out.shape == (rec["batch"], cfg.n_sources, rec["T"])
+    assert torch.allclose(out, out2, rtol=0, atol=1e-6)
+    out, latent = out.cpu(), latent.cpu()
+    if "out_stride" in rec:
+        s = rec["out_stride"]
+        a, b = rec["latent_stride"]
+        torch.testing.assert_close(out[..., ::s], rec["out"], rtol=RTOL, atol=ATOL)
+        torch.testing.assert_close(latent[:, :, ::a, ::b], rec["latent"], rtol=RTOL, atol=ATOL)
+    else:
+        torch.testing.assert_close(out, rec["out"], rtol=RTOL, atol=ATOL)
+        torch.testing.assert_close(latent, rec["latent"], rtol=RTOL, atol=ATOL)
+    assert abs(float(out.double().sum()) - rec["out_sum"]) < 5e-2
+    assert torch.equal(perm.cpu(), rec["perm"]) and torch.equal(perm_b.cpu(), rec["perm_b"]) and perm.dtype == torch.int64
+    assert abs(float(loss) - float(rec["loss"])) < 1e-4
+    torch.testing.assert_close(loss_b.cpu(), rec["loss_b"], rtol=0, atol=1e-4)
+    assert model.last_launches > 0
+
+
+def test_model_causal_is_loud(golden_dir):
+    rec = _load(golden_dir, "tiny_cln")
+    cfg = O.OracleConfig(**rec["cfg"])
+    model = build_model(cfg, O.synth_state_dict(cfg, seed=rec["wseed"]))
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        model(torch.randn(1, 1, 203).cuda())
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("T", [16, 17, 24, 128 * 8 + 8, 1031, 4097])
+def test_model_ragged_lengths_vs_oracle(mode, T):
+    """padding rule conv_tasnet.py:145-149 for T not on the hop grid, single-frame inputs, tile-boundary lengths."""
+    cfg = O.OracleConfig(n_basis=32, kernel_size=16, sep_hidden_channels=48, sep_bottleneck_channels=16, sep_skip_channels=24,
+                         sep_num_blocks=2, sep_num_layers=4, causal=False, n_sources=2)
+    sd = O.synth_state_dict(cfg, seed=T)
+    model = build_model(cfg, sd, math=mode)
+    mixture, _ = O.synth_batch(2, 2, T, seed=T + 1)
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        ref_out, ref_lat = O.conv_tasnet_fwd(mixture, sd, cfg)
+    torch.testing.assert_close(out.cpu(), ref_out, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), ref_lat, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_separator_vs_oracle(mode):
+    cfg = O.OracleConfig(n_basis=40, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=24, sep_skip_channels=16,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=3)
+    sd = O.synth_state_dict(cfg, seed=9)
+    model = build_model(cfg, sd, math=mode)
+    w = torch.randn(2, 40, 333, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        mask = model.separator(w.cuda())
+        ref = O.separator_fwd(w, sd, cfg)
+    assert mask.shape == (2, 3, 40, 333)
+    torch.testing.assert_close(mask.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SI-SDR / PIT
+# ---------------------------------------------------------------------------------------------------------------
+def test_pit_golden(golden_dir):
+    m = _load(golden_dir, "modules")
+    r = m["pit_selftest"]  # the reference's own self-test inputs (src/criterion/pit.py:226-265)
+    with torch.no_grad():
+        loss, pat = PIT1d(NegSISDR(), 2)(r["input"].cuda(), r["target"].cuda())
+        assert torch.equal(pat.cpu(), r["pattern"])
+        assert abs(float(loss) - float(r["loss"])) < 1e-4
+        for S in (2, 3, 4):
+            r = m[f"pit_S{S}"]
+            crit = PIT1d(NegSISDR(), S)
+            loss_b, pat = crit(r["input"].cuda(), r["target"].cuda(), batch_mean=False)
+            loss, _ = crit(r["input"].cuda(), r["target"].cuda())
+            assert torch.equal(pat.cpu(), r["pattern"]) and pat.dtype == torch.int64
+            torch.testing.assert_close(loss_b.cpu(), r["loss_b"], rtol=0, atol=1e-4)
+            assert abs(float(loss) - float(r["loss"])) < 1e-4
+            torch.testing.assert_close(sisdr(r["input"].cuda(), r["target"].cuda()).cpu(), r["sisdr"], rtol=0, atol=1e-4)
+            # SISDR (maximize) picks the same permutation with the negated loss
+            l2, p2 = PIT1d(SISDR(), S)(r["input"].cuda(), r["target"].cuda(), batch_mean=False)
+            assert torch.equal(p2, pat)
+            torch.testing.assert_close(l2, -loss_b, rtol=0, atol=1e-6)
+            l3, p3 = PIT1d(NegSISDR(reduction='sum'), S)(r["input"].cuda(), r["target"].cuda(), batch_mean=False)
+            assert torch.equal(p3, pat)
+            torch.testing.assert_close(l3, loss_b * S, rtol=1e-6, atol=1e-5)
+        t = m["sisdr_limits_in"].cuda()
+        torch.testing.assert_close(sisdr(t, torch.zeros_like(t)).cpu(), m["sisdr_zero_target"], rtol=0, atol=1e-3)
+        torch.testing.assert_close(sisdr(t, t.clone()).cpu(), m["sisdr_perfect"], rtol=0, atol=1e-3)
+        r = m["pit_tie"]  # identical estimates -> tie -> first permutation (torch.min semantics, pit.py:39)
+        l, p = PIT1d(NegSISDR(), 2)(r["input"].cuda(), r["target"].cuda(), batch_mean=False)
+        assert torch.equal(p.cpu(), r["pattern"])
+        torch.testing.assert_close(l.cpu(), r["loss_b"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("S,T", [(2, 32000), (3, 32000), (4, 128000), (2, 1), (5, 333), (6, 64), (1, 100)])
+def test_pit_vs_oracle_and_ragged(S, T):
+    g = torch.Generator().manual_seed(S * 1000 + T)
+    B = 4
+    t = torch.randn(B, S, T, generator=g)
+    e = torch.stack([t[b, torch.randperm(S, generator=g)] for b in range(B)]) + 0.2 * torch.randn(B, S, T, generator=g)
+    with torch.no_grad():
+        loss_b, perm = PIT1d(NegSISDR(), S)(e.cuda(), t.cuda(), batch_mean=False)
+        nd = NegSISDR()(e.cuda(), t.cuda(), batch_mean=False)
+    ref_l, ref_p = O.pit_neg_sisdr(e, t, batch_mean=False)
+    if T > 8:
+        assert torch.equal(perm.cpu(), ref_p)
+    torch.testing.assert_close(loss_b.cpu(), ref_l, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(nd.cpu(), O.neg_sisdr(e, t, batch_mean=False), rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + a two-sample oracle spot check
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg2_full_size_properties(mode):
+    cfg = O.OracleConfig()  # paper hyper-parameters, 2 speakers
+    sd = O.synth_state_dict(cfg, seed=111)
+    model = build_model(cfg, sd, math=mode)
+    B, T = 32, 32000
+    mixture, sources = O.synth_batch(B, 2, T, seed=111)
+    xm, xs = mixture.cuda(), sources.cuda()
+    crit = PIT1d(NegSISDR(), 2)
+    with torch.no_grad():
+        out = model(xm)
+        loss_b, perm = crit(out, xs, batch_mean=False)
+        loss, _ = crit(out, xs)
+        # (1) batch independence: a sample processed alone / in a permuted batch gives the same separation
+        idx = torch.tensor([5, 31, 0])
+        out_sub = model(xm[idx].contiguous())
+        torch.testing.assert_close(out_sub, out[idx], rtol=1e-5, atol=2e-6)
+        # (2) PIT equivariance: swapping the target sources swaps the reported permutation, same loss
+        loss_sw, perm_sw = crit(out, xs.flip(1).contiguous(), batch_mean=False)
+        assert torch.equal(perm_sw, 1 - perm)
+        torch.testing.assert_close(loss_sw, loss_b, rtol=0, atol=1e-5)
+        # (3) scale invariance of SI-SDR w.r.t. the estimate
+        loss_sc, perm_sc = crit(out * 3.0, xs, batch_mean=False)
+        assert torch.equal(perm_sc, perm)
+        torch.testing.assert_close(loss_sc, loss_b, rtol=0, atol=2e-4)
+        # (4) batch mean == mean of the per-sample losses
+        assert abs(float(loss) - float(loss_b.double().mean())) < 1e-5
+        assert torch.isfinite(out).all()
+    # (5) oracle spot check on two of the 32 samples
+    ref, _ = O.conv_tasnet_fwd(mixture[[5, 31]], sd, cfg)
+    torch.testing.assert_close(out[[5, 31]].cpu(), ref, rtol=RTOL, atol=ATOL)
+    ref_l, ref_p = O.pit_neg_sisdr(ref, sources[[5, 31]], batch_mean=False)
+    assert torch.equal(perm[[5, 31]].cpu(), ref_p)
+    torch.testing.assert_close(loss_b[[5, 31]].cpu(), ref_l, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg5_long_context_4spk(mode):
+    """cfg5 shape (4 speakers, 8 s @ 16 kHz, T'=15999) on a reduced batch; checks determinism of the permutation and a
+    strided oracle comparison on one sample."""
+    cfg = O.OracleConfig(n_sources=4)
+    sd = O.synth_state_dict(cfg, seed=115)
+    model = build_model(cfg, sd, math=mode)
+    mixture, sources = O.synth_batch(2, 4, 128000, seed=115)
+    with torch.no_grad():
+        out = model(mixture.cuda())
+        loss_b, perm = PIT1d(NegSISDR(), 4)(out, sources.cuda(), batch_mean=False)
+    ref, _ = O.conv_tasnet_fwd(mixture[:1], sd, cfg)
+    torch.testing.assert_close(out[:1].cpu(), ref, rtol=RTOL, atol=ATOL)
+    ref_l, ref_p = O.pit_neg_sisdr(ref, sources[:1], batch_mean=False)
+    assert torch.equal(perm[:1].cpu(), ref_p)
+    torch.testing.assert_close(loss_b[:1].cpu(), ref_l, rtol=0, atol=1e-4)
+
+
+def test_host_buffer_entry_point():
+    """ctn_convtasnet_loss_host (the e2e leg of bench.py): same numbers as the module path."""
+    cfg = O.OracleConfig(n_basis=64, kernel_size=16, sep_hidden_channels=96, sep_bottleneck_channels=32, sep_skip_channels=48,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=2)
+    sd = O.synth_state_dict(cfg, seed=77)
+    model = build_model(cfg, sd)
+    B, T = 3, 4000
+    mixture, sources = O.synth_batch(B, 2, T, seed=78)
+    xh, th = mixture.pin_memory(), sources.pin_memory()
+    out_h = torch.empty(B, 2, T).pin_memory()
+    loss_h = torch.empty(1).pin_memory()
+    perm_h = torch.empty(B, 2, dtype=torch.int64).pin_memory()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ncfg = model.native_config()
+    params, keep = model.native_params(dev)
+    need = C.c_size_t(0)
+    N.check(N.ctn_workspace_bytes(C.byref(ncfg), B, T, C.byref(need)))
+    ws = torch.empty(need.value + 512, dtype=torch.uint8, device=dev)
+    io = torch.empty(N.ctn_host_io_bytes(C.byref(ncfg), B, T) + 512, dtype=torch.uint8, device=dev)
+    al = lambda t: (t.data_ptr() + 255) & ~255
+    N.check(N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(),
+                                       loss_h.data_ptr(), perm_h.data_ptr(), al(io), al(ws), need.value, N.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert N.ctn_last_launch_count() > 10
+    with torch.no_grad():
+        out = model(mixture.cuda())
+        loss, perm = PIT1d(NegSISDR(), 2)(out, sources.cuda())
+    torch.testing.assert_close(out_h, out.cpu(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(perm_h, perm.cpu()) and abs(float(loss_h) - float(loss)) < 1e-5
+
+
+@pytest.mark.skipif(not N.ctn_has_tcgen05(), reason="tcgen05 family not built")
+def test_tf32_fast_mode_stated_tolerance(golden_dir):
+    rec = _load(golden_dir, "paper_3spk_short")
+    cfg = O.OracleConfig(**rec["cfg"])
+    model = build_model(cfg, O.synth_state_dict(cfg, seed=rec["wseed"]), math="tf32")
+    mixture, sources = O.synth_batch(rec["batch"], cfg.n_sources, rec["T"], seed=rec["xseed"])
+    with torch.no_grad():
+        out = model(mixture.cuda())
+        _, perm = PIT1d(NegSISDR(), cfg.n_sources)(out, sources.cuda())
+    torch.testing.assert_close(out.cpu()[..., ::rec["out_stride"]], rec["out"], rtol=2e-2, atol=5e-3)
+    assert torch.equal(perm.cpu(), rec["perm"])
