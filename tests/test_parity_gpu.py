@@ -80,7 +80,7 @@ def test_encoder_decoder_oracle(N_, L, S, T, B):
     w_ref = O.encoder_fwd(x, enc.conv1d.weight.detach().cpu(), S)
     y_ref = O.decoder_fwd(w_ref, dec.conv_transpose1d.weight.detach().cpu(), S)
     torch.testing.assert_close(w.cpu(), w_ref, rtol=1e-5, atol=2e-6)
-    torch.testing.assert_close(y.cpu(), y_ref, rtol=1e-5, atol=5e-6)
+    torch.testing.assert_close(y.cpu(), y_ref, rtol=1e-4, atol=2e-5)  # sums of N terms; different order than ATen
 
 
 def test_norms_golden(golden_dir):
