@@ -100,6 +100,7 @@ struct Carver {
 struct TcnWs {
   double* stats;  // [2*RX][B][2]
   std::vector<FoldedConv> folds;  // per block, (Bc+Sc) rows
+  std::vector<float*> wimg1, wimg2;  // per block: tcgen05 weight images of the two pointwise convs (math != fp32)
   float *x, *skip, *h, *u, *outraw;
   size_t stats_bytes;
 };
@@ -120,10 +121,16 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
   ws->stats_bytes = sizeof(double) * 2 * RX * B * 2;
   ws->stats = cv.take<double>((size_t)2 * RX * B * 2);
   ws->folds.resize(RX);
+  ws->wimg1.assign(RX, nullptr);
+  ws->wimg2.assign(RX, nullptr);
   for (int i = 0; i < RX; ++i) {
     ws->folds[i].Wf = cv.take<float>((size_t)Mt * c->hidden);
     ws->folds[i].v1 = cv.take<float>(Mt);
     ws->folds[i].v2 = cv.take<float>(Mt);
+    if (c->math != CTN_MATH_FP32) {
+      ws->wimg1[i] = cv.take<float>(ctn_umma_wimg_bytes(c->hidden, c->bottleneck, c->math) / sizeof(float));
+      ws->wimg2[i] = cv.take<float>(ctn_umma_wimg_bytes(Mt, c->hidden, c->math) / sizeof(float));
+    }
   }
   const size_t bp = (size_t)B * pitch;
   ws->x = cv.take<float>(bp * c->bottleneck);
@@ -149,6 +156,10 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
     const bool has_out = p.out_w != nullptr;
     if (has_out) CTN_TRY(ctn_fold_conv(p.out_w, p.out_b, p.norm2_g, p.norm2_b, Bc, H, ws->folds[i], 0, st));
     CTN_TRY(ctn_fold_conv(p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, Sc, H, ws->folds[i], has_out ? Bc : 0, st));
+    if (c->math != CTN_MATH_FP32) {
+      CTN_TRY(ctn_umma_build_wimg(p.bottleneck_w, H, Bc, c->math, ws->wimg1[i], st));
+      CTN_TRY(ctn_umma_build_wimg(ws->folds[i].Wf, has_out ? Bc + Sc : Sc, H, c->math, ws->wimg2[i], st));
+    }
   }
   for (int r = 0; r < R; ++r) {
     for (int l = 0; l < X; ++l) {
@@ -163,7 +174,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       PwArgs a;
       memset(&a, 0, sizeof(a));
       a.A = ws->x; a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
-      a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1;
+      a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1; a.wimg = ws->wimg1[i];
       { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_H, c->math, st)); }
       // K_B: u = PReLU(dwconv(gLN1(h))), stats2
       { StageTimer tm(CTN_ST_DW, st);
@@ -173,6 +184,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       const int Mt = has_out ? Bc + Sc : Sc;
       memset(&a, 0, sizeof(a));
       a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+      a.wimg = ws->wimg2[i];
       { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
       // K_F: residual / skip with deferred gLN2
       { StageTimer tm(CTN_ST_FIN, st);
@@ -223,6 +235,7 @@ struct ModelWs {
   FoldedConv head; // (Bc, N)
   float* w;        // (B, N, pitch)
   float* what;     // (B, S*N, pitch)
+  float *wimg_head, *wimg_mask;
   TcnWs tcn;
 };
 
@@ -239,6 +252,11 @@ static void carve_model(Carver& cv, const ctn_config_t* c, int B, int pitch, Mod
   ws->head.Wf = cv.take<float>((size_t)c->bottleneck * c->n_basis);
   ws->head.v1 = cv.take<float>(c->bottleneck);
   ws->head.v2 = cv.take<float>(c->bottleneck);
+  ws->wimg_head = ws->wimg_mask = nullptr;
+  if (c->math != CTN_MATH_FP32) {
+    ws->wimg_head = cv.take<float>(ctn_umma_wimg_bytes(c->bottleneck, c->n_basis, c->math) / sizeof(float));
+    ws->wimg_mask = cv.take<float>(ctn_umma_wimg_bytes(c->n_sources * c->n_basis, c->skip, c->math) / sizeof(float));
+  }
   const size_t bp = (size_t)B * pitch;
   ws->w = cv.take<float>(bp * c->n_basis);
   ws->what = cv.take<float>(bp * c->n_basis * c->n_sources);
@@ -262,18 +280,25 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
                          float* mask_out, cudaStream_t st) {
   const int N = c->n_basis, Bc = c->bottleneck, Sc = c->skip, S = c->n_sources;
   // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371)
-  { StageTimer tm(CTN_ST_PREP, st); CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st)); }
+  { StageTimer tm(CTN_ST_PREP, st);
+    CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st));
+    if (c->math != CTN_MATH_FP32) {
+      CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, c->math, ws->wimg_head, st));
+      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
+    }
+  }
   PwArgs a;
   memset(&a, 0, sizeof(a));
   a.A = ws->w; a.W = ws->head.Wf; a.D = ws->tcn.x; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
   a.v1 = ws->head.v1; a.v2 = ws->head.v2; a.stats_in = ws->stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
+  a.wimg = ws->wimg_head;
   { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, c->math, st)); }
   // TCN (conv_tasnet.py:372)
   CTN_TRY(run_tcn(c, p->blocks, &ws->tcn, B, frames, pitch, st));
   // tail: PReLU -> mask 1x1 -> sigmoid -> * w  (conv_tasnet.py:373-376, 159-160)
   memset(&a, 0, sizeof(a));
   a.A = ws->tcn.skip; a.W = p->mask_w; a.D = ws->what; a.B = B; a.M = S * N; a.K = Sc; a.frames = frames; a.pitch = pitch;
-  a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws->w; a.Nb = N; a.mask_out = mask_out;
+  a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws->w; a.Nb = N; a.mask_out = mask_out; a.wimg = ws->wimg_mask;
   { StageTimer tm(CTN_ST_MASK, st); CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, c->math, st)); }
   return CTN_OK;
 }
@@ -405,4 +430,29 @@ extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_param
   if ((e = cudaMemcpyAsync(loss_mean_host, io.loss_mean, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(perm_host, io.perm, sizeof(int64_t) * (size_t)B * S, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
   return CTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctn_debug_pointwise(const float* A, const float* W, float* D, int B, int M, int K, int frames, int pitch,
+                                   const float* bias, const float* slope, double* stats_out, int epi, int math,
+                                   const uint32_t* dbg, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  if (!A || !W || !D || B <= 0 || M <= 0 || K <= 0 || frames <= 0 || pitch < frames || pitch % 128 != 0) return CTN_EINVAL;
+  if (epi != EPI_RAW && epi != EPI_H) return CTN_EUNSUPPORTED;
+  if (epi == EPI_H && (!bias || !slope || !stats_out)) return CTN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  PwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.W = W; a.D = D; a.B = B; a.M = M; a.K = K; a.frames = frames; a.pitch = pitch;
+  a.bias = bias; a.slope = slope; a.stats_out = stats_out;
+  if (math == CTN_MATH_FP32) return ctn_pw_simt(a, PRO_NONE, epi, st);
+  const size_t need = ctn_umma_wimg_bytes(M, K, math) + 512;
+  if (!workspace || workspace_bytes < need) return CTN_EWORKSPACE;
+  float* wimg = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  CTN_TRY(ctn_umma_build_wimg(W, M, K, math, wimg, st));
+  a.wimg = wimg;
+  if (dbg) { a.dbg_idesc = dbg[0]; a.dbg_lbo_a = dbg[1]; a.dbg_sbo_a = dbg[2]; a.dbg_sbo_w = dbg[3]; }
+  return ctn_pw_umma(a, PRO_NONE, epi, math, st);
 }

@@ -34,13 +34,17 @@ struct PwArgs {
   const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
   int Nb;                  // EPI_MASK: n_basis
   float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)
+  // tcgen05 path only
+  const float* wimg;       // pre-swizzled hi/lo weight images (ctn_umma_build_wimg)
+  uint32_t dbg_idesc, dbg_lbo_a, dbg_sbo_a, dbg_sbo_w;  // 0 = defaults (descriptor probing from the debug entry)
 };
 
 // fp32 CUDA-core path (ctn_tcn_simt.cu)
 int ctn_pw_simt(const PwArgs& a, int pro, int epi, cudaStream_t st);
 // tcgen05 path (ctn_umma.cu); math = CTN_MATH_TF32X3 / CTN_MATH_TF32
 int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st);
-int ctn_umma_selftest_available(void);
+size_t ctn_umma_wimg_bytes(int M, int K, int math);
+int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st);
 
 int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
                   int row_offset, cudaStream_t st);

@@ -1,4 +1,335 @@
-// tcgen05 (sm_100a) pointwise contraction path -- placeholder until the kernels land.
+// tcgen05 (5th-gen tensor core) implementation of the dense 1x1 "pointwise" contractions of the Conv-TasNet path.
+//
+//   D[b][n][t] = epi( sum_k W[n][k] * pro(A[b][k][t]) )        A: (B,K,pitch) fp32, time contiguous
+//
+// Orientation: TIME runs along the UMMA M dimension (TMEM lanes), output channels along N (TMEM columns):
+//   * the activation operand is consumed as an MN-major (time-contiguous) SWIZZLE_128B_BASE32B shared-memory tile, i.e. the
+//     (channels, time) tensor is used as it lies in HBM -- no transposition anywhere;
+//   * the weight operand is K-major (PyTorch (out,in,1) layout), pre-arranged once per forward into the exact
+//     swizzled shared-memory image so that one 1-D bulk async copy (TMA engine) brings a 32-channel slab in;
+//   * the epilogue reads a TMEM lane = one time step per thread, so every global store of a warp is a contiguous
+//     128-byte row segment of D.
+// fp32-parity numerics ("3xTF32"): x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi);
+//   D = A_hi W_hi + A_lo W_hi + A_hi W_lo  accumulated in fp32 in TMEM  (the dropped lo*lo term is ~2^-22 relative).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-3   epilogue  (TMEM -> registers -> fused epilogue -> coalesced global stores)
+//   warp  4     TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 5-12  producers (global -> registers -> prologue + hi/lo split -> swizzled st.shared; one thread also issues
+//               the bulk copies of the weight slabs)
+// Pipelines: smem ring (full/empty mbarriers, tcgen05.commit frees a stage) and a 2-deep TMEM accumulator ring.
 #include "ctn_internal.h"
-extern "C" int ctn_has_tcgen05(void) { return 0; }
-int ctn_pw_umma(const PwArgs&, int, int, int, cudaStream_t) { return CTN_ENOTBUILT; }
+#include "ctn_umma_ptx.cuh"
+
+namespace {
+
+constexpr int TM = 128;       // time steps per tile (UMMA M)
+constexpr int KS = 32;        // input channels per smem slab (one 128-byte swizzle row of tf32)
+constexpr int A_BYTES = TM * KS * 4;  // 16 KB per precision
+constexpr int MAX_STAGES = 6;
+constexpr int NUM_THREADS = 13 * 32;
+constexpr int PROD_WARPS = 8;
+constexpr int SMEM_HEADER = 1024;
+
+struct UmmaArgs {
+  PwArgs a;
+  const float* wimg;  // [n_tiles][k_slabs][NPASS][n_tile*32] swizzled images
+  int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
+  uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
+  uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
+};
+
+struct __align__(8) SmemHeader {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+template <int PRO, int EPI, int NPASS>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
+  constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  const uint32_t stage0 = base + SMEM_HEADER;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PwArgs& a = g.a;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), PROD_WARPS + 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->tfull[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->tempty[i]), 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  // item -> (b, tt, nt): nt fastest so that concurrently running CTAs share the activation tile in L2
+  const int items_per_cta = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp >= 5) {
+    // ===================================== PRODUCERS ========================================================
+    const int p = threadIdx.x - 160;  // 0..255
+    const int pw = p >> 5;            // producer warp 0..7: rows pw*4 .. pw*4+3 of the slab
+    float pslope = 0.f;
+    if (PRO == PRO_PRELU) pslope = a.pro_slope[0];
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < items_per_cta; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int nt = item % g.n_tiles;
+      const int tt = (item / g.n_tiles) % g.t_tiles;
+      const int b = item / (g.n_tiles * g.t_tiles);
+      const float* Ab = a.A + (size_t)b * a.K * a.pitch + (size_t)tt * TM + lane * 4;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(g.wimg) + (size_t)nt * g.k_slabs * NPREC * g.w_bytes;
+      for (int ks = 0; ks < g.k_slabs; ++ks) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = ks * KS + pw * 4 + j;
+          v[j] = k < a.K ? __ldg(reinterpret_cast<const float4*>(Ab + (size_t)k * a.pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
+        const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
+        if (p == 0) {
+          const uint32_t fb = ptx::smem_u32(&hdr->full[s]);
+          ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
+          ptx::bulk_g2s(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kl = pw * 4 + j;  // 0..31 within the slab
+          const int kg = kl >> 2, r = kl & 3;
+          // MN-major tf32 needs SWIZZLE_128B_BASE32B (the only MN-major layout the tensor core accepts for 32-bit
+          // operands; pinned on hardware with tools/umma_unit.cu): atoms of 4 channel rows x 128 B (32 time steps),
+          // 32-byte chunks XOR (row & 3); atoms along time 512 B apart (LBO), 4-channel groups 2048 B apart (SBO).
+          const uint32_t off = (uint32_t)kg * 2048u + (uint32_t)(lane >> 3) * 512u + (uint32_t)r * 128u +
+                               (uint32_t)(((((lane & 7) >> 1) ^ r) << 5) | ((lane & 1) << 4));
+          float4 x = v[j];
+          if (PRO == PRO_PRELU) {
+            x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
+          }
+          float4 hi = make_float4(ptx::to_tf32(x.x), ptx::to_tf32(x.y), ptx::to_tf32(x.z), ptx::to_tf32(x.w));
+          *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + off) = hi;
+          if (NPASS == 3) {
+            float4 lo = make_float4(ptx::to_tf32(x.x - hi.x), ptx::to_tf32(x.y - hi.y), ptx::to_tf32(x.z - hi.z),
+                                    ptx::to_tf32(x.w - hi.w));
+            *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off) = lo;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
+        if (++s == g.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================== MMA ISSUER =======================================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < items_per_cta; ++it) {
+        const int acc = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int ks = 0; ks < g.k_slabs; ++ks) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->full[s]), ph);
+          ptx::tc_fence_after();
+          const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
+          const uint32_t a_hi = st_base, a_lo = st_base + A_BYTES;
+          const uint32_t w_hi = st_base + NPREC * A_BYTES, w_lo = w_hi + g.w_bytes;
+#pragma unroll
+          for (int kk = 0; kk < KS / 8; ++kk) {
+            const uint64_t da_hi = ptx::make_smem_desc(a_hi + kk * 4096, g.lbo_a, g.sbo_a, 1);
+            const uint64_t dw_hi = ptx::make_smem_desc(w_hi + kk * 32, g.lbo_w, g.sbo_w);
+            ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
+            if (NPASS == 3) {
+              const uint64_t da_lo = ptx::make_smem_desc(a_lo + kk * 4096, g.lbo_a, g.sbo_a, 1);
+              const uint64_t dw_lo = ptx::make_smem_desc(w_lo + kk * 32, g.lbo_w, g.sbo_w);
+              ptx::mma_tf32(d_tmem, da_lo, dw_hi, g.idesc, 1u);
+              ptx::mma_tf32(d_tmem, da_hi, dw_lo, g.idesc, 1u);
+            }
+          }
+          ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // frees the smem stage when these MMAs have retired
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
+        }
+        ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== EPILOGUE =========================================================
+    float eslope = 0.f;
+    if (EPI == EPI_H) eslope = a.slope[0];
+    for (int it = 0; it < items_per_cta; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int nt = item % g.n_tiles;
+      const int tt = (item / g.n_tiles) % g.t_tiles;
+      const int b = item / (g.n_tiles * g.t_tiles);
+      const int acc = it & 1;
+      const int t = tt * TM + warp * 32 + lane;
+      const bool tvalid = t < a.frames;
+      float2 mr = make_float2(0.f, 1.f);
+      if (EPI == EPI_HEAD) mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps);
+      ptx::mbar_wait(ptx::smem_u32(&hdr->tfull[acc]), (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(warp * 32) << 16);
+      float* Db = a.D + (size_t)b * a.M * a.pitch + t;
+      float ls = 0.f, lss = 0.f;
+      for (int c0 = 0; c0 < g.n_tile; c0 += 16) {
+        uint32_t raw16[16];
+        ptx::tmem_ld16(taddr + (uint32_t)c0, raw16);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = nt * g.n_tile + c0 + j;
+          if (n >= a.M) break;
+          float v = __uint_as_float(raw16[j]);
+          if (EPI == EPI_HEAD) v = mr.y * v + (__ldg(a.v1 + n) - mr.x * mr.y * __ldg(a.v2 + n));
+          if (EPI == EPI_H) v = prelu_f(v + __ldg(a.bias + n), eslope);
+          float mk = 0.f;
+          if (EPI == EPI_MASK) {
+            mk = 1.f / (1.f + expf(-(v + __ldg(a.bias + n))));
+            v = mk * __ldg(a.wenc + ((size_t)b * a.Nb + (n % a.Nb)) * a.pitch + t);
+          }
+          if (!tvalid) { v = 0.f; mk = 0.f; }
+          Db[(size_t)n * a.pitch] = v;
+          if (EPI == EPI_MASK && a.mask_out) a.mask_out[((size_t)b * a.M + n) * a.pitch + t] = mk;
+          if (EPI == EPI_H) { ls += v; lss += v * v; }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+      if (EPI == EPI_H) {
+        double s = warp_sum_d((double)ls), ss = warp_sum_d((double)lss);
+        if (lane == 0) { atomicAdd(&a.stats_out[2 * b], s); atomicAdd(&a.stats_out[2 * b + 1], ss); }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- weight images ---------------------------------------------------------------------------------------------
+// grid (k_slabs, n_tiles), block 256: builds the K-major SWIZZLE_128B image(s) of one (n_tile x 32) weight slab.
+__global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs,
+                                                    int nprec, float* __restrict__ wimg) {
+  const int ks = blockIdx.x, nt = blockIdx.y;
+  const size_t per = (size_t)n_tile * 32;  // floats per precision
+  float* dst = wimg + ((size_t)nt * k_slabs + ks) * nprec * per;
+  for (int i = threadIdx.x; i < n_tile * 32; i += 256) {
+    const int nl = i >> 5, kl = i & 31;
+    const int n = nt * n_tile + nl, k = ks * 32 + kl;
+    const float x = (n < M && k < K) ? W[(size_t)n * K + k] : 0.f;
+    // K-major SW128: 8-row groups of 1024 B, row = 128 B (32 k), 16-byte chunk index XOR (row & 7)
+    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
+    const float hi = ptx::to_tf32(x);
+    dst[off] = hi;
+    if (nprec == 2) dst[per + off] = ptx::to_tf32(x - hi);
+  }
+}
+
+int pick_n_tile(int M) {
+  if (M >= 256) return 256;
+  return ((M + 15) / 16) * 16;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int PRO, int EPI, int NPASS>
+int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  k_pw_umma<PRO, EPI, NPASS><<<grid, NUM_THREADS, smem, st>>>(g);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+}  // namespace
+
+extern "C" int ctn_has_tcgen05(void) { return 1; }
+
+size_t ctn_umma_wimg_bytes(int M, int K, int math) {
+  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  const int n_tile = pick_n_tile(M);
+  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + 31) / 32;
+  return (size_t)n_tiles * k_slabs * nprec * n_tile * 32 * sizeof(float);
+}
+
+int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st) {
+  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;  // hi [, lo]
+  const int n_tile = pick_n_tile(M);
+  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + 31) / 32;
+  k_build_wimg<<<dim3(k_slabs, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, nprec, wimg);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
+  if (!a.wimg) return CTN_EINVAL;
+  if (a.pitch % TM != 0) return CTN_EALIGN;
+  if ((((uintptr_t)a.A) | ((uintptr_t)a.wimg)) & 15) return CTN_EALIGN;
+  UmmaArgs g;
+  g.a = a;
+  g.wimg = a.wimg;
+  g.n_tile = pick_n_tile(a.M);
+  g.n_tiles = (a.M + g.n_tile - 1) / g.n_tile;
+  g.k_slabs = (a.K + KS - 1) / KS;
+  g.t_tiles = a.pitch / TM;
+  g.num_items = a.B * g.t_tiles * g.n_tiles;
+  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  g.w_bytes = (uint32_t)g.n_tile * 128u;
+  g.stage_bytes = (uint32_t)nprec * (A_BYTES + g.w_bytes);
+  const size_t budget = 227 * 1024 - SMEM_HEADER - 1024;
+  int stages = (int)(budget / g.stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return CTN_EUNSUPPORTED;
+  g.stages = stages;
+  g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
+  g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
+  g.sbo_a = a.dbg_sbo_a ? a.dbg_sbo_a : 2048u;  // between 4-channel groups
+  g.lbo_w = 16u;                                 // unused for swizzled K-major
+  g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : 1024u;  // between 8-row (output channel) groups
+  const size_t smem = SMEM_HEADER + 1024 + (size_t)stages * g.stage_bytes;
+  int grid = num_sms();
+  if (grid > g.num_items) grid = g.num_items;
+#define UM_LAUNCH(P, E)                                                                   \
+  if (pro == P && epi == E)                                                               \
+    return nprec == 2 ? launch<P, E, 3>(g, smem, grid, st) : launch<P, E, 1>(g, smem, grid, st);
+  UM_LAUNCH(PRO_NONE, EPI_RAW)
+  UM_LAUNCH(PRO_NONE, EPI_HEAD)
+  UM_LAUNCH(PRO_NONE, EPI_H)
+  UM_LAUNCH(PRO_PRELU, EPI_MASK)
+#undef UM_LAUNCH
+  return CTN_EUNSUPPORTED;
+}

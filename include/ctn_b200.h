@@ -170,6 +170,14 @@ int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params
                              int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
                              ctn_stream_t stream);
 
+/* Test hook: ONE pointwise (1x1) contraction D[b][m][t] = epi(sum_k W[m][k] A[b][k][t]) in the selected numeric mode,
+ * so tests can compare the tcgen05 kernels with the FFMA kernels operand by operand.  A (B,K,pitch), D (B,M,pitch),
+ * pitch % 128 == 0.  epi: 0 = raw, 2 = +bias, PReLU(slope), (sum,sumsq) -> stats_out.  dbg (nullable): 4 words
+ * {idesc, lbo_a, sbo_a, sbo_w} overriding the UMMA descriptors (0 = default).  workspace: >= 4*M*K*2 + 64 KiB bytes. */
+int ctn_debug_pointwise(const float* A, const float* W, float* D, int B, int M, int K, int frames, int pitch,
+                        const float* bias, const float* slope, double* stats_out, int epi, int math,
+                        const uint32_t* dbg, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
+
 /* number of kernel launches the last ctn_* call on this thread enqueued (for bench.py's gpu_launches) */
 int ctn_last_launch_count(void);
 
