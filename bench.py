@@ -274,7 +274,7 @@ def main():
         ent["bound"] = bound
         ent["avg_launch_ms"] = per_launch_ms
         stages[name] = ent
-    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    dom = max((k for k in stages if k != "prep"), key=lambda k: stages[k]["ms_per_step"])
     d = stages[dom]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -176,16 +176,29 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       a.A = ws->x; a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
       a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1; a.wimg = ws->wimg1[i];
       { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_H, c->math, st)); }
-      // K_B: u = PReLU(dwconv(gLN1(h))), stats2
-      { StageTimer tm(CTN_ST_DW, st);
-        CTN_TRY(ctn_dw_fwd(ws->h, ws->u, p.norm1_g, p.norm1_b, p.dw_w, p.dw_b, p.prelu2, st1, st2, B, H, frames, pitch,
-                           c->sep_kernel, dilation, c->causal, c->eps_tcn, st)); }
-      // K_C: r = [Wo;Ws] diag(gamma2) u
       const int Mt = has_out ? Bc + Sc : Sc;
-      memset(&a, 0, sizeof(a));
-      a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
-      a.wimg = ws->wimg2[i];
-      { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
+      const int pad_left = c->causal ? (c->sep_kernel - 1) * dilation : ((c->sep_kernel - 1) * dilation) / 2;
+      if (c->math != CTN_MATH_FP32 && c->sep_kernel == 3) {
+        // K_BC fused (tcgen05): the producer warps compute u = PReLU(dwconv(gLN1(h))) (+stats2) on the fly and feed
+        // it straight to the tensor core; u never touches HBM.  r = [Wo;Ws] diag(gamma2) u
+        StageTimer tm(CTN_ST_PW2, st);
+        memset(&a, 0, sizeof(a));
+        a.A = ws->h; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+        a.wimg = ws->wimg2[i];
+        a.pro_slope = p.prelu2; a.dw_norm_g = p.norm1_g; a.dw_norm_b = p.norm1_b; a.dw_w = p.dw_w; a.dw_b = p.dw_b;
+        a.dw_stats_in = st1; a.dw_stats_out = st2; a.dw_dilation = dilation; a.dw_pad_left = pad_left; a.dw_eps = c->eps_tcn;
+        CTN_TRY(pw_dispatch(a, PRO_DW, EPI_RAW, c->math, st));
+      } else {
+        // K_B: u = PReLU(dwconv(gLN1(h))), stats2
+        { StageTimer tm(CTN_ST_DW, st);
+          CTN_TRY(ctn_dw_fwd(ws->h, ws->u, p.norm1_g, p.norm1_b, p.dw_w, p.dw_b, p.prelu2, st1, st2, B, H, frames, pitch,
+                             c->sep_kernel, dilation, c->causal, c->eps_tcn, st)); }
+        // K_C: r = [Wo;Ws] diag(gamma2) u
+        memset(&a, 0, sizeof(a));
+        a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+        a.wimg = ws->wimg2[i];
+        { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
+      }
       // K_F: residual / skip with deferred gLN2
       { StageTimer tm(CTN_ST_FIN, st);
         CTN_TRY(ctn_finish_fwd(ws->outraw, ws->folds[i], st2, (double)H * (double)frames, c->eps_tcn, ws->x, ws->skip, B, Bc,

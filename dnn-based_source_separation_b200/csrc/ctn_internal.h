@@ -12,7 +12,7 @@ struct FoldedConv {
 };
 
 // epilogue / prologue selectors of the pointwise (1x1) contraction kernels
-enum { PRO_NONE = 0, PRO_PRELU = 1 };
+enum { PRO_NONE = 0, PRO_PRELU = 1, PRO_DW = 2 };
 enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3 };
 
 struct PwArgs {
@@ -21,7 +21,16 @@ struct PwArgs {
   float* D;            // (B, M, pitch)
   int B, M, K, frames, pitch;
   // prologue
-  const float* pro_slope;  // PRO_PRELU
+  const float* pro_slope;  // PRO_PRELU / PRO_DW: PReLU slope (1)
+  // PRO_DW (tcgen05 path): A is h (B,K,pitch); the producer computes u = PReLU(dwconv3(gLN1(h)) + bd) on the fly
+  const float* dw_norm_g;  // (K) gLN1 gamma
+  const float* dw_norm_b;  // (K) gLN1 beta
+  const float* dw_w;       // (K,3) depthwise taps
+  const float* dw_b;       // (K)
+  const double* dw_stats_in;   // (B,2) (sum, sumsq) of h
+  double* dw_stats_out;        // (B,2) += (sum, sumsq) of u
+  int dw_dilation, dw_pad_left;
+  float dw_eps;
   // epilogue
   const float* bias;       // EPI_H / EPI_MASK: (M)
   const float* slope;      // EPI_H: PReLU slope (1)

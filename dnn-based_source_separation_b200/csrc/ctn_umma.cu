@@ -20,6 +20,7 @@
 // Pipelines: smem ring (full/empty mbarriers, tcgen05.commit frees a stage) and a 2-deep TMEM accumulator ring.
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -29,7 +30,8 @@ constexpr int A_BYTES = TM * KS * 4;  // 16 KB per precision
 constexpr int MAX_STAGES = 6;
 constexpr int NUM_THREADS = 13 * 32;
 constexpr int PROD_WARPS = 8;
-constexpr int SMEM_HEADER = 1024;
+constexpr int SMEM_HEADER = 2048;   // barriers + tmem pointer, then the epilogue parameter row
+constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
 
 struct UmmaArgs {
   PwArgs a;
@@ -37,6 +39,7 @@ struct UmmaArgs {
   int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
   uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
   uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
+  uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
 
 struct __align__(8) SmemHeader {
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
     const int p = threadIdx.x - 160;  // 0..255
     const int pw = p >> 5;            // producer warp 0..7: rows pw*4 .. pw*4+3 of the slab
     float pslope = 0.f;
-    if (PRO == PRO_PRELU) pslope = a.pro_slope[0];
+    if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < items_per_cta; ++it) {
@@ -94,19 +97,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
       const int b = item / (g.n_tiles * g.t_tiles);
       const float* Ab = a.A + (size_t)b * a.K * a.pitch + (size_t)tt * TM + lane * 4;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(g.wimg) + (size_t)nt * g.k_slabs * NPREC * g.w_bytes;
+      // PRO_DW: per-sample gLN1 statistics of h (the A operand)
+      float2 mr1 = make_float2(0.f, 1.f);
+      float dls = 0.f, dlss = 0.f;
+      if (PRO == PRO_DW) mr1 = gln_mean_rstd(a.dw_stats_in + 2 * b, (double)a.K * (double)a.frames, a.dw_eps);
+      const int tbase = tt * TM + lane * 4;  // first of this thread's 4 time steps
       for (int ks = 0; ks < g.k_slabs; ++ks) {
         float4 v[4];
+        if (PRO != PRO_DW) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = ks * KS + pw * 4 + j;
-          v[j] = k < a.K ? __ldg(reinterpret_cast<const float4*>(Ab + (size_t)k * a.pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 4; ++j) {
+            const int k = ks * KS + pw * 4 + j;
+            v[j] = (k < a.K && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab + (size_t)k * a.pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside.
+          // All 12 128-bit loads of the slab (4 channels x 3 taps) are issued up front from clamped, always-valid
+          // addresses; validity is applied afterwards with selects (no control flow between the loads).
+          const int d = a.dw_dilation, pl = a.dw_pad_left;
+          const int step = d >= 4 ? d : 4;            // aligned load spacing; d in {1,2} uses the window [t-4, t+8)
+          const int first = d >= 4 ? tbase - pl : tbase - 4;
+          float4 q[4][3];
+          float pg[4], pb[4], pbd[4], pw0[4], pw1[4], pw2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = ks * KS + pw * 4 + j;
+            const int cc = c < a.K ? c : a.K - 1;
+            const float* hr = a.A + ((size_t)b * a.K + cc) * a.pitch;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              int ts = first + k * step;
+              ts = ts < 0 ? 0 : (ts > a.pitch - 4 ? a.pitch - 4 : ts);
+              q[j][k] = __ldg(reinterpret_cast<const float4*>(hr + ts));
+            }
+            pg[j] = __ldg(a.dw_norm_g + cc); pb[j] = __ldg(a.dw_norm_b + cc); pbd[j] = __ldg(a.dw_b + cc);
+            pw0[j] = __ldg(a.dw_w + cc * 3); pw1[j] = __ldg(a.dw_w + cc * 3 + 1); pw2[j] = __ldg(a.dw_w + cc * 3 + 2);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = ks * KS + pw * 4 + j;
+            const float gsc = pg[j] * mr1.y, gsh = pb[j] - mr1.x * mr1.y * pg[j];
+            float win[12];  // normalised (and zero-padded) samples at first + 0..11 (spacing 1) or 3 aligned quads
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int ts = first + k * step;
+              const float qv[4] = {q[j][k].x, q[j][k].y, q[j][k].z, q[j][k].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) win[k * 4 + e] = (ts + e >= 0 && ts + e < a.frames) ? fmaf(qv[e], gsc, gsh) : 0.f;
+            }
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t0, t1, t2;
+              if (d >= 4) { t0 = win[e]; t1 = win[4 + e]; t2 = win[8 + e]; }            // taps at t-d, t, t+d
+              else if (d == 2) { t0 = win[2 + e]; t1 = win[4 + e]; t2 = win[6 + e]; }   // window starts at t-4
+              else { t0 = win[3 + e]; t1 = win[4 + e]; t2 = win[5 + e]; }
+              float u = fmaf(pw2[j], t2, fmaf(pw1[j], t1, fmaf(pw0[j], t0, pbd[j])));
+              u = prelu_f(u, pslope);
+              if (tbase + e >= a.frames || c >= a.K) u = 0.f;
+              o[e] = u;
+              dls += u;
+              dlss = fmaf(u, u, dlss);
+            }
+            v[j] = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
         ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
         const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
         if (p == 0) {
           const uint32_t fb = ptx::smem_u32(&hdr->full[s]);
-          ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
-          ptx::bulk_g2s(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb);
+          if (g.dbg & 4u) {
+            ptx::mbar_arrive(fb);
+          } else {
+            ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
+            ptx::bulk_g2s(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -134,6 +199,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
         if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
+      if (PRO == PRO_DW && nt == 0) {
+        const double sd = warp_sum_d((double)dls), ssd = warp_sum_d((double)dlss);
+        if (lane == 0) { atomicAdd(&a.dw_stats_out[2 * b], sd); atomicAdd(&a.dw_stats_out[2 * b + 1], ssd); }
+      }
     }
   } else if (warp == 4) {
     // ===================================== MMA ISSUER =======================================================
@@ -152,7 +221,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
           const uint32_t a_hi = st_base, a_lo = st_base + A_BYTES;
           const uint32_t w_hi = st_base + NPREC * A_BYTES, w_lo = w_hi + g.w_bytes;
 #pragma unroll
-          for (int kk = 0; kk < KS / 8; ++kk) {
+          for (int kk = 0; kk < ((g.dbg & 8u) ? 0 : KS / 8); ++kk) {
             const uint64_t da_hi = ptx::make_smem_desc(a_hi + kk * 4096, g.lbo_a, g.sbo_a, 1);
             const uint64_t dw_hi = ptx::make_smem_desc(w_hi + kk * 32, g.lbo_w, g.sbo_w);
             ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
@@ -172,44 +241,118 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
     __syncwarp();
   } else {
     // ===================================== EPILOGUE =========================================================
+    // thread = one time step (TMEM lane); columns = output channels.  Per-channel parameters of the tile are staged
+    // in shared memory once per item; TMEM is read in 16-column chunks, double buffered so that the next tcgen05.ld is
+    // in flight while the current chunk is transformed and stored (one coalesced 128-byte row segment per warp-store).
     float eslope = 0.f;
     if (EPI == EPI_H) eslope = a.slope[0];
+    float* sp = reinterpret_cast<float*>(smem + SMEM_PARAMS);  // [256] per-channel epilogue parameter
+    const int te = threadIdx.x;                                // 0..127
     for (int it = 0; it < items_per_cta; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int nt = item % g.n_tiles;
       const int tt = (item / g.n_tiles) % g.t_tiles;
       const int b = item / (g.n_tiles * g.t_tiles);
       const int acc = it & 1;
-      const int t = tt * TM + warp * 32 + lane;
+      const int t = tt * TM + te;
       const bool tvalid = t < a.frames;
-      float2 mr = make_float2(0.f, 1.f);
-      if (EPI == EPI_HEAD) mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps);
+      const int n0 = nt * g.n_tile;
+      const int nvalid = min(g.n_tile, a.M - n0);
+      float mscale = 1.f;
+      {
+        // stage the per-channel parameter: EPI_HEAD: v1 - mean*rstd*v2 (deferred gLN shift); EPI_H / EPI_MASK: bias
+        float2 mr = make_float2(0.f, 1.f);
+        if (EPI == EPI_HEAD) { mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps); mscale = mr.y; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with sp
+        for (int i = te; i < g.n_tile; i += 128) {
+          float pv = 0.f;
+          if (i < nvalid) {
+            if (EPI == EPI_HEAD) pv = __ldg(a.v1 + n0 + i) - mr.x * mr.y * __ldg(a.v2 + n0 + i);
+            if (EPI == EPI_H || EPI == EPI_MASK) pv = __ldg(a.bias + n0 + i);
+          }
+          sp[i] = pv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       ptx::mbar_wait(ptx::smem_u32(&hdr->tfull[acc]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(warp * 32) << 16);
-      float* Db = a.D + (size_t)b * a.M * a.pitch + t;
+      float* Dp = a.D + ((size_t)b * a.M + n0) * a.pitch + t;
+      float* Mp = (EPI == EPI_MASK && a.mask_out) ? a.mask_out + ((size_t)b * a.M + n0) * a.pitch + t : nullptr;
+      const float* Wp = (EPI == EPI_MASK) ? a.wenc + (size_t)b * a.Nb * a.pitch + t : nullptr;
+      const int nb0 = (EPI == EPI_MASK) ? n0 % a.Nb : 0;
       float ls = 0.f, lss = 0.f;
-      for (int c0 = 0; c0 < g.n_tile; c0 += 16) {
-        uint32_t raw16[16];
-        ptx::tmem_ld16(taddr + (uint32_t)c0, raw16);
-        ptx::tmem_ld_wait();
+      const int ncols = (nvalid + 15) & ~15;
+
+      const bool do_store = !(g.dbg & 1u);
+      auto process = [&](const uint32_t (&buf)[16], int c0) {
+        float wv[16];
+        if (EPI == EPI_MASK) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            int nn = nb0 + c0 + j;
+            while (nn >= a.Nb) nn -= a.Nb;
+            wv[j] = (c0 + j < nvalid) ? __ldg(Wp + (size_t)nn * a.pitch) : 0.f;
+          }
+        }
+        float pv[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(sp + c0 + j4 * 4);
+          pv[j4 * 4] = p4.x; pv[j4 * 4 + 1] = p4.y; pv[j4 * 4 + 2] = p4.z; pv[j4 * 4 + 3] = p4.w;
+        }
+        float o[16], mk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int n = nt * g.n_tile + c0 + j;
-          if (n >= a.M) break;
-          float v = __uint_as_float(raw16[j]);
-          if (EPI == EPI_HEAD) v = mr.y * v + (__ldg(a.v1 + n) - mr.x * mr.y * __ldg(a.v2 + n));
-          if (EPI == EPI_H) v = prelu_f(v + __ldg(a.bias + n), eslope);
-          float mk = 0.f;
+          float v = __uint_as_float(buf[j]);
+          mk[j] = 0.f;
+          if (EPI == EPI_HEAD) v = fmaf(mscale, v, pv[j]);
+          if (EPI == EPI_H) v = prelu_f(v + pv[j], eslope);
           if (EPI == EPI_MASK) {
-            mk = 1.f / (1.f + expf(-(v + __ldg(a.bias + n))));
-            v = mk * __ldg(a.wenc + ((size_t)b * a.Nb + (n % a.Nb)) * a.pitch + t);
+            mk[j] = __fdividef(1.f, 1.f + __expf(-(v + pv[j])));
+            v = mk[j] * wv[j];
           }
-          if (!tvalid) { v = 0.f; mk = 0.f; }
-          Db[(size_t)n * a.pitch] = v;
-          if (EPI == EPI_MASK && a.mask_out) a.mask_out[((size_t)b * a.M + n) * a.pitch + t] = mk;
-          if (EPI == EPI_H) { ls += v; lss += v * v; }
+          if (!tvalid) { v = 0.f; mk[j] = 0.f; }
+          o[j] = v;
         }
+        float* q = Dp + (size_t)c0 * a.pitch;
+        float* qm = Mp ? Mp + (size_t)c0 * a.pitch : nullptr;
+        if (c0 + 16 <= nvalid) {  // full chunk (warp-uniform): no per-element predicates
+          if (do_store) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q[(size_t)j * a.pitch] = o[j];
+            if (EPI == EPI_MASK && qm) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) qm[(size_t)j * a.pitch] = mk[j];
+            }
+          }
+          if (EPI == EPI_H) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < nvalid) {
+              if (do_store) {
+                q[(size_t)j * a.pitch] = o[j];
+                if (EPI == EPI_MASK && qm) qm[(size_t)j * a.pitch] = mk[j];
+              }
+              if (EPI == EPI_H) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
+            }
+          }
+        }
+      };
+
+      uint32_t bufA[16], bufB[16];
+      ptx::tmem_ld16(taddr, bufA);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        ptx::tmem_ld_wait();
+        if (c0 + 16 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 16), bufB);
+        process(bufA, c0);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 32), bufA);
+        if (c0 + 16 < ncols) process(bufB, c0 + 16);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
@@ -245,6 +388,8 @@ __global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W,
 }
 
 int pick_n_tile(int M) {
+  static const char* env_nt = getenv("CTN_UMMA_NTILE");
+  if (env_nt && atoi(env_nt) >= 16 && atoi(env_nt) <= 256 && atoi(env_nt) % 16 == 0 && M >= atoi(env_nt)) return atoi(env_nt);
   if (M >= 256) return 256;
   return ((M + 15) / 16) * 16;
 }
@@ -313,7 +458,11 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   const size_t budget = 227 * 1024 - SMEM_HEADER - 1024;
   int stages = (int)(budget / g.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) return CTN_EUNSUPPORTED;
+  static const char* env_st = getenv("CTN_UMMA_STAGES");
+  if (env_st && atoi(env_st) >= 1 && atoi(env_st) < stages) stages = atoi(env_st);
+  static const char* env_dbg = getenv("CTN_UMMA_DBG");
+  g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
+  if (stages < 1) return CTN_EUNSUPPORTED;
   g.stages = stages;
   g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
   g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
@@ -322,11 +471,14 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : 1024u;  // between 8-row (output channel) groups
   const size_t smem = SMEM_HEADER + 1024 + (size_t)stages * g.stage_bytes;
   int grid = num_sms();
+  static const char* env_grid = getenv("CTN_UMMA_GRID");
+  if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
   if (grid > g.num_items) grid = g.num_items;
 #define UM_LAUNCH(P, E)                                                                   \
   if (pro == P && epi == E)                                                               \
     return nprec == 2 ? launch<P, E, 3>(g, smem, grid, st) : launch<P, E, 1>(g, smem, grid, st);
   UM_LAUNCH(PRO_NONE, EPI_RAW)
+  UM_LAUNCH(PRO_DW, EPI_RAW)
   UM_LAUNCH(PRO_NONE, EPI_HEAD)
   UM_LAUNCH(PRO_NONE, EPI_H)
   UM_LAUNCH(PRO_PRELU, EPI_MASK)
