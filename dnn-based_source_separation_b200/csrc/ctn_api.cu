@@ -149,17 +149,24 @@ static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t
 static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnWs* ws, int B, int frames, int pitch,
                    cudaStream_t st) {
   const int R = c->num_blocks, X = c->num_layers, Bc = c->bottleneck, H = c->hidden, Sc = c->skip;
-  // weight folding for all blocks (tiny kernels)
-  for (int i = 0; i < R * X; ++i) {
+  // weight preparation for all blocks: gLN2 folding, then (tcgen05 modes) the swizzled hi/lo operand images
+  {
     StageTimer tm(CTN_ST_PREP, st);
-    const ctn_block_params_t& p = blocks[i];
-    const bool has_out = p.out_w != nullptr;
-    if (has_out) CTN_TRY(ctn_fold_conv(p.out_w, p.out_b, p.norm2_g, p.norm2_b, Bc, H, ws->folds[i], 0, st));
-    CTN_TRY(ctn_fold_conv(p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, Sc, H, ws->folds[i], has_out ? Bc : 0, st));
-    if (c->math != CTN_MATH_FP32) {
-      CTN_TRY(ctn_umma_build_wimg(p.bottleneck_w, H, Bc, c->math, ws->wimg1[i], st));
-      CTN_TRY(ctn_umma_build_wimg(ws->folds[i].Wf, has_out ? Bc + Sc : Sc, H, c->math, ws->wimg2[i], st));
+    std::vector<FoldJob> fj;
+    std::vector<WimgJob> wj;
+    for (int i = 0; i < R * X; ++i) {
+      const ctn_block_params_t& p = blocks[i];
+      const bool has_out = p.out_w != nullptr;
+      const FoldedConv& f = ws->folds[i];
+      if (has_out) fj.push_back(FoldJob{p.out_w, p.out_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Bc, H, 0});
+      fj.push_back(FoldJob{p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Sc, H, has_out ? Bc : 0});
+      if (c->math != CTN_MATH_FP32) {
+        wj.push_back(WimgJob{p.bottleneck_w, ws->wimg1[i], H, Bc});
+        wj.push_back(WimgJob{f.Wf, ws->wimg2[i], has_out ? Bc + Sc : Sc, H});
+      }
     }
+    CTN_TRY(ctn_fold_batch(fj.data(), (int)fj.size(), st));
+    if (!wj.empty()) CTN_TRY(ctn_umma_build_wimg_batch(wj.data(), (int)wj.size(), c->math, st));
   }
   for (int r = 0; r < R; ++r) {
     for (int l = 0; l < X; ++l) {

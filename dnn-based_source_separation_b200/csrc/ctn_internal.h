@@ -58,6 +58,13 @@ int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cud
 int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
                   int row_offset, cudaStream_t st);
 
+// batched variants: all weight preparation of a forward in two launches (jobs travel in the kernel parameter block)
+struct FoldJob { const float *W, *bias, *gamma, *beta; float *Wf, *v1, *v2; int M, K, row_offset; };
+struct WimgJob { const float* W; float* wimg; int M, K; };
+#define CTN_MAX_JOBS 48
+int ctn_fold_batch(const FoldJob* jobs, int n, cudaStream_t st);
+int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t st);
+
 // depthwise stage: u = PReLU(dwconv(gLN1(h))) (+ stats2), all (B,H,pitch)
 int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_b, const float* dw_w, const float* dw_b,
                const float* slope, const double* stats_in, double* stats_out, int B, int H, int frames, int pitch, int P,

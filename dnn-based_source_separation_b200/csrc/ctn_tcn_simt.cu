@@ -41,6 +41,41 @@ int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const f
   return CTN_OK;
 }
 
+struct FoldJobs { FoldJob j[CTN_MAX_JOBS]; };
+__global__ void __launch_bounds__(128) k_fold_batch(const FoldJobs jobs) {
+  const FoldJob& jb = jobs.j[blockIdx.y];
+  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < jb.M; row += gridDim.x * 4) {
+    const int lane = threadIdx.x & 31;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < jb.K; k += 32) {
+      const float w = jb.W[(size_t)row * jb.K + k];
+      const float wf = w * jb.gamma[k];
+      jb.Wf[(size_t)(row + jb.row_offset) * jb.K + k] = wf;
+      s1 = fmaf(w, jb.beta[k], s1);
+      s2 += wf;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      jb.v1[row + jb.row_offset] = s1 + (jb.bias ? jb.bias[row] : 0.f);
+      jb.v2[row + jb.row_offset] = s2;
+    }
+  }
+}
+
+int ctn_fold_batch(const FoldJob* jobs, int n, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += CTN_MAX_JOBS) {
+    FoldJobs fj;
+    const int m = n - i0 < CTN_MAX_JOBS ? n - i0 : CTN_MAX_JOBS;
+    int maxM = 1;
+    for (int i = 0; i < m; ++i) { fj.j[i] = jobs[i0 + i]; if (jobs[i0 + i].M > maxM) maxM = jobs[i0 + i].M; }
+    k_fold_batch<<<dim3((maxM + 3) / 4, m), 128, 0, st>>>(fj);
+    CTN_COUNT_LAUNCH();
+  }
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // pointwise (1x1) contraction, fp32 FFMA:  D[b][m][t] = epi( sum_k W[m][k] * pro(A[b][k][t]) )
 // 64(m) x 64(t) x 16(k) tiles, 256 threads, 4x4 micro-tiles, 128-bit loads/stores along t.

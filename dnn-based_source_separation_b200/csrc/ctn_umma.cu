@@ -28,7 +28,8 @@ constexpr int TM = 128;       // time steps per tile (UMMA M)
 constexpr int KS = 32;        // input channels per smem slab (one 128-byte swizzle row of tf32)
 constexpr int A_BYTES = TM * KS * 4;  // 16 KB per precision
 constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 13 * 32;
+constexpr int NUM_THREADS = 13 * 32;      // PRO_DW kernels: 4 epilogue + 1 MMA + 8 producer warps
+constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: a second epilogue warpgroup (warps 13-16)
 constexpr int PROD_WARPS = 8;
 constexpr int SMEM_HEADER = 2048;   // barriers + tmem pointer, then the epilogue parameter row
 constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
@@ -50,9 +51,83 @@ struct __align__(8) SmemHeader {
   uint32_t tmem_base;
 };
 
+// ---- depthwise producer math (PRO_DW) -------------------------------------------------------------------------
+// One channel, 4 consecutive time steps.  q0,q1,q2: the three aligned 128-bit loads (d >= 4: taps t-d, t, t+d;
+// d < 4: the window [t-4, t+8)).  DCLS in {1, 2, 4(=d>=4)} selects the tap positions at compile time.
+// INTERIOR tiles (every tap of every element inside [0, frames)) fold gLN1 into the taps: 3 FMA per output.
+template <int DCLS, bool INTERIOR>
+__device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, const float4 q2, float gsc, float gsh, float w0,
+                                             float w1, float w2, float bd, float slope, int first, int step, int tbase,
+                                             int frames, bool cvalid, float& ls, float& lss) {
+  const float win[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+  constexpr int i0 = DCLS == 4 ? 0 : (DCLS == 2 ? 2 : 3);
+  constexpr int i1 = 4;
+  constexpr int i2 = DCLS == 4 ? 8 : (DCLS == 2 ? 6 : 5);
+  float o[4];
+  if (INTERIOR) {
+    const float a0 = gsc * w0, a1 = gsc * w1, a2 = gsc * w2;
+    const float cst = fmaf(gsh, (w0 + w1) + w2, bd);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = fmaf(a2, win[i2 + e], fmaf(a1, win[i1 + e], fmaf(a0, win[i0 + e], cst)));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // absolute time of the three taps of element e
+      const int t0 = DCLS == 4 ? first + e : first + i0 + e;
+      const int t1 = DCLS == 4 ? first + step + e : first + i1 + e;
+      const int t2 = DCLS == 4 ? first + 2 * step + e : first + i2 + e;
+      const float h0 = (t0 >= 0 && t0 < frames) ? fmaf(win[i0 + e], gsc, gsh) : 0.f;
+      const float h1 = (t1 >= 0 && t1 < frames) ? fmaf(win[i1 + e], gsc, gsh) : 0.f;
+      const float h2 = (t2 >= 0 && t2 < frames) ? fmaf(win[i2 + e], gsc, gsh) : 0.f;
+      o[e] = fmaf(w2, h2, fmaf(w1, h1, fmaf(w0, h0, bd)));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float u = prelu_f(o[e], slope);
+    if (!INTERIOR && (tbase + e >= frames || !cvalid)) u = 0.f;
+    o[e] = u;
+    ls += u;
+    lss = fmaf(u, u, lss);
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+template <int DCLS, bool INTERIOR>
+__device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, int tbase, float2 mr1, float pslope, bool skip_loads,
+                                        float4 (&v)[4], float& dls, float& dlss) {
+  const int d = a.dw_dilation, pl = a.dw_pad_left;
+  const int step = DCLS == 4 ? d : 4;
+  const int first = DCLS == 4 ? tbase - pl : tbase - 4;
+  float4 q[4][3];
+  float pg[4], pb[4], pbd[4], pw0[4], pw1[4], pw2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = ks * 32 + pw * 4 + j;
+    const int cc = INTERIOR ? c : (c < a.K ? c : a.K - 1);
+    const float* hr = a.A + ((size_t)b * a.K + cc) * a.pitch;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int ts = first + k * step;
+      if (!INTERIOR) ts = ts < 0 ? 0 : (ts > a.pitch - 4 ? a.pitch - 4 : ts);
+      q[j][k] = skip_loads ? make_float4(1.f, 2.f, 3.f, 4.f) : __ldg(reinterpret_cast<const float4*>(hr + ts));
+    }
+    pg[j] = __ldg(a.dw_norm_g + cc); pb[j] = __ldg(a.dw_norm_b + cc); pbd[j] = __ldg(a.dw_b + cc);
+    pw0[j] = __ldg(a.dw_w + cc * 3); pw1[j] = __ldg(a.dw_w + cc * 3 + 1); pw2[j] = __ldg(a.dw_w + cc * 3 + 2);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = ks * 32 + pw * 4 + j;
+    const float gsc = pg[j] * mr1.y, gsh = pb[j] - mr1.x * mr1.y * pg[j];
+    v[j] = dw_channel<DCLS, INTERIOR>(q[j][0], q[j][1], q[j][2], gsc, gsh, pw0[j], pw1[j], pw2[j], pbd[j], pslope, first, step,
+                                      tbase, a.frames, c < a.K, dls, dlss);
+  }
+}
+
 template <int PRO, int EPI, int NPASS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
+__global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
   constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
+  constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;  // epilogue warpgroups (each covers all 128 TMEM lanes)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -69,7 +144,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&hdr->tfull[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&hdr->tempty[i]), 128);
+      ptx::mbar_init(ptx::smem_u32(&hdr->tempty[i]), 128 * EGROUPS);
     }
     ptx::fence_mbar_init();
   }
@@ -82,7 +157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
   // item -> (b, tt, nt): nt fastest so that concurrently running CTAs share the activation tile in L2
   const int items_per_cta = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 5) {
+  if (warp >= 5 && warp < 13) {
     // ===================================== PRODUCERS ========================================================
     const int p = threadIdx.x - 160;  // 0..255
     const int pw = p >> 5;            // producer warp 0..7: rows pw*4 .. pw*4+3 of the slab
@@ -102,6 +177,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
       float dls = 0.f, dlss = 0.f;
       if (PRO == PRO_DW) mr1 = gln_mean_rstd(a.dw_stats_in + 2 * b, (double)a.K * (double)a.frames, a.dw_eps);
       const int tbase = tt * TM + lane * 4;  // first of this thread's 4 time steps
+      int dcls = 4;
+      bool dw_interior = false;
+      if (PRO == PRO_DW) {
+        const int d = a.dw_dilation;
+        dcls = d >= 4 ? 4 : d;
+        const int reach = d >= 4 ? d : 4;  // furthest sample touched on either side of the tile
+        dw_interior = (tt * TM - reach >= 0) && (tt * TM + TM - 1 + reach + 3 < a.frames) && (a.K % KS == 0) &&
+                      (a.dw_pad_left == d);
+      }
       for (int ks = 0; ks < g.k_slabs; ++ks) {
         float4 v[4];
         if (PRO != PRO_DW) {
@@ -112,54 +196,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
           }
         } else {
           // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside.
-          // All 12 128-bit loads of the slab (4 channels x 3 taps) are issued up front from clamped, always-valid
-          // addresses; validity is applied afterwards with selects (no control flow between the loads).
-          const int d = a.dw_dilation, pl = a.dw_pad_left;
-          const int step = d >= 4 ? d : 4;            // aligned load spacing; d in {1,2} uses the window [t-4, t+8)
-          const int first = d >= 4 ? tbase - pl : tbase - 4;
-          float4 q[4][3];
-          float pg[4], pb[4], pbd[4], pw0[4], pw1[4], pw2[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = ks * KS + pw * 4 + j;
-            const int cc = c < a.K ? c : a.K - 1;
-            const float* hr = a.A + ((size_t)b * a.K + cc) * a.pitch;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              int ts = first + k * step;
-              ts = ts < 0 ? 0 : (ts > a.pitch - 4 ? a.pitch - 4 : ts);
-              q[j][k] = __ldg(reinterpret_cast<const float4*>(hr + ts));
-            }
-            pg[j] = __ldg(a.dw_norm_g + cc); pb[j] = __ldg(a.dw_norm_b + cc); pbd[j] = __ldg(a.dw_b + cc);
-            pw0[j] = __ldg(a.dw_w + cc * 3); pw1[j] = __ldg(a.dw_w + cc * 3 + 1); pw2[j] = __ldg(a.dw_w + cc * 3 + 2);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = ks * KS + pw * 4 + j;
-            const float gsc = pg[j] * mr1.y, gsh = pb[j] - mr1.x * mr1.y * pg[j];
-            float win[12];  // normalised (and zero-padded) samples at first + 0..11 (spacing 1) or 3 aligned quads
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const int ts = first + k * step;
-              const float qv[4] = {q[j][k].x, q[j][k].y, q[j][k].z, q[j][k].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) win[k * 4 + e] = (ts + e >= 0 && ts + e < a.frames) ? fmaf(qv[e], gsc, gsh) : 0.f;
-            }
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t0, t1, t2;
-              if (d >= 4) { t0 = win[e]; t1 = win[4 + e]; t2 = win[8 + e]; }            // taps at t-d, t, t+d
-              else if (d == 2) { t0 = win[2 + e]; t1 = win[4 + e]; t2 = win[6 + e]; }   // window starts at t-4
-              else { t0 = win[3 + e]; t1 = win[4 + e]; t2 = win[5 + e]; }
-              float u = fmaf(pw2[j], t2, fmaf(pw1[j], t1, fmaf(pw0[j], t0, pbd[j])));
-              u = prelu_f(u, pslope);
-              if (tbase + e >= a.frames || c >= a.K) u = 0.f;
-              o[e] = u;
-              dls += u;
-              dlss = fmaf(u, u, dlss);
-            }
-            v[j] = make_float4(o[0], o[1], o[2], o[3]);
+          // All 12 128-bit loads of the slab (4 channels x 3 taps) are issued before any arithmetic.  The branch below is
+          // uniform over the CTA (depends on the item only).
+          const bool skipl = (g.dbg & 2u) != 0;
+          if (dw_interior) {
+            if (dcls == 4) dw_slab<4, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            else dw_slab<1, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+          } else {
+            if (dcls == 4) dw_slab<4, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            else dw_slab<1, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
           }
         }
         ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
@@ -247,7 +294,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
     float eslope = 0.f;
     if (EPI == EPI_H) eslope = a.slope[0];
     float* sp = reinterpret_cast<float*>(smem + SMEM_PARAMS);  // [256] per-channel epilogue parameter
-    const int te = threadIdx.x;                                // 0..127
+    const int egroup = warp >= 13 ? 1 : 0;                     // second warpgroup handles the upper half of the columns
+    const int te = (warp & 3) * 32 + lane;                     // time step within the tile == TMEM lane
+    const int tid_e = egroup * 128 + te;
     for (int it = 0; it < items_per_cta; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int nt = item % g.n_tiles;
@@ -263,8 +312,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
         // stage the per-channel parameter: EPI_HEAD: v1 - mean*rstd*v2 (deferred gLN shift); EPI_H / EPI_MASK: bias
         float2 mr = make_float2(0.f, 1.f);
         if (EPI == EPI_HEAD) { mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps); mscale = mr.y; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with sp
-        for (int i = te; i < g.n_tile; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");  // previous item's readers are done with sp
+        for (int i = tid_e; i < g.n_tile; i += 128 * EGROUPS) {
           float pv = 0.f;
           if (i < nvalid) {
             if (EPI == EPI_HEAD) pv = __ldg(a.v1 + n0 + i) - mr.x * mr.y * __ldg(a.v2 + n0 + i);
@@ -272,17 +321,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
           }
           sp[i] = pv;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");
       }
       ptx::mbar_wait(ptx::smem_u32(&hdr->tfull[acc]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)((warp & 3) * 32) << 16);
       float* Dp = a.D + ((size_t)b * a.M + n0) * a.pitch + t;
       float* Mp = (EPI == EPI_MASK && a.mask_out) ? a.mask_out + ((size_t)b * a.M + n0) * a.pitch + t : nullptr;
       const float* Wp = (EPI == EPI_MASK) ? a.wenc + (size_t)b * a.Nb * a.pitch + t : nullptr;
       const int nb0 = (EPI == EPI_MASK) ? n0 % a.Nb : 0;
       float ls = 0.f, lss = 0.f;
-      const int ncols = (nvalid + 15) & ~15;
+      const int ncols_all = (nvalid + 15) & ~15;
+      const int csplit = EGROUPS == 2 ? ((ncols_all / 2 + 15) & ~15) : ncols_all;  // group 0: [0,csplit), group 1: rest
+      const int cbeg = egroup == 0 ? 0 : csplit;
+      const int ncols = egroup == 0 ? csplit : ncols_all;
 
       const bool do_store = !(g.dbg & 1u);
       auto process = [&](const uint32_t (&buf)[16], int c0) {
@@ -345,8 +397,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_pw_umma(const UmmaArgs g) {
       };
 
       uint32_t bufA[16], bufB[16];
-      ptx::tmem_ld16(taddr, bufA);
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      if (cbeg < ncols) ptx::tmem_ld16(taddr + (uint32_t)cbeg, bufA);
+      for (int c0 = cbeg; c0 < ncols; c0 += 32) {
         ptx::tmem_ld_wait();
         if (c0 + 16 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 16), bufB);
         process(bufA, c0);
@@ -387,6 +439,28 @@ __global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W,
   }
 }
 
+struct WimgJobs { WimgJob j[CTN_MAX_JOBS]; };
+// grid (max k_slabs * max n_tiles, jobs): one block per (slab, n-tile) of one job
+__global__ void __launch_bounds__(256) k_build_wimg_batch(const WimgJobs jobs, int nprec) {
+  const WimgJob& jb = jobs.j[blockIdx.y];
+  const int n_tile = jb.M >= 256 ? 256 : ((jb.M + 15) / 16) * 16;
+  const int n_tiles = (jb.M + n_tile - 1) / n_tile, k_slabs = (jb.K + 31) / 32;
+  const size_t per = (size_t)n_tile * 32;
+  for (int blk = blockIdx.x; blk < n_tiles * k_slabs; blk += gridDim.x) {
+    const int nt = blk / k_slabs, ks = blk - nt * k_slabs;
+    float* dst = jb.wimg + ((size_t)nt * k_slabs + ks) * nprec * per;
+    for (int i = threadIdx.x; i < n_tile * 32; i += 256) {
+      const int nl = i >> 5, kl = i & 31;
+      const int n = nt * n_tile + nl, k = ks * 32 + kl;
+      const float x = (n < jb.M && k < jb.K) ? jb.W[(size_t)n * jb.K + k] : 0.f;
+      const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
+      const float hi = ptx::to_tf32(x);
+      dst[off] = hi;
+      if (nprec == 2) dst[per + off] = ptx::to_tf32(x - hi);
+    }
+  }
+}
+
 int pick_n_tile(int M) {
   static const char* env_nt = getenv("CTN_UMMA_NTILE");
   if (env_nt && atoi(env_nt) >= 16 && atoi(env_nt) <= 256 && atoi(env_nt) % 16 == 0 && M >= atoi(env_nt)) return atoi(env_nt);
@@ -407,13 +481,14 @@ int num_sms() {
 
 template <int PRO, int EPI, int NPASS>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
+  constexpr int NT = PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  k_pw_umma<PRO, EPI, NPASS><<<grid, NUM_THREADS, smem, st>>>(g);
+  k_pw_umma<PRO, EPI, NPASS><<<grid, NT, smem, st>>>(g);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
@@ -436,6 +511,29 @@ int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cud
   const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + 31) / 32;
   k_build_wimg<<<dim3(k_slabs, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, nprec, wimg);
   CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t st) {
+  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  if (getenv("CTN_UMMA_NTILE")) {  // debug override changes the tiling: fall back to per-job launches
+    for (int i = 0; i < n; ++i) CTN_TRY(ctn_umma_build_wimg(jobs[i].W, jobs[i].M, jobs[i].K, math, jobs[i].wimg, st));
+    return CTN_OK;
+  }
+  for (int i0 = 0; i0 < n; i0 += CTN_MAX_JOBS) {
+    WimgJobs wj;
+    const int m = n - i0 < CTN_MAX_JOBS ? n - i0 : CTN_MAX_JOBS;
+    int maxb = 1;
+    for (int i = 0; i < m; ++i) {
+      wj.j[i] = jobs[i0 + i];
+      const int n_tile = pick_n_tile(jobs[i0 + i].M);
+      const int blocks = ((jobs[i0 + i].M + n_tile - 1) / n_tile) * ((jobs[i0 + i].K + 31) / 32);
+      if (blocks > maxb) maxb = blocks;
+    }
+    k_build_wimg_batch<<<dim3(maxb, m), 256, 0, st>>>(wj, nprec);
+    CTN_COUNT_LAUNCH();
+  }
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
 }
