@@ -95,7 +95,7 @@ __device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, c
 
 template <int DCLS, bool INTERIOR>
 __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, int tbase, float2 mr1, float pslope, bool skip_loads,
-                                        float4 (&v)[4], float& dls, float& dlss) {
+                                        bool prefetch_next, float4 (&v)[4], float& dls, float& dlss) {
   const int d = a.dw_dilation, pl = a.dw_pad_left;
   const int step = DCLS == 4 ? d : 4;
   const int first = DCLS == 4 ? tbase - pl : tbase - 4;
@@ -114,6 +114,15 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
     }
     pg[j] = __ldg(a.dw_norm_g + cc); pb[j] = __ldg(a.dw_norm_b + cc); pbd[j] = __ldg(a.dw_b + cc);
     pw0[j] = __ldg(a.dw_w + cc * 3); pw1[j] = __ldg(a.dw_w + cc * 3 + 1); pw2[j] = __ldg(a.dw_w + cc * 3 + 2);
+  }
+  if (prefetch_next && INTERIOR) {
+    // pull the next slab's rows towards the SM while this slab is being computed (no register cost)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* hr = a.A + ((size_t)b * a.K + (ks + 1) * 32 + pw * 4 + j) * a.pitch;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + first + k * step));
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -165,12 +174,27 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
     if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
     int s = 0;
     uint32_t ph = 0;
+    // activation loads of slab (it2, ks2): issued ONE SLAB AHEAD of their use (register double buffer), across item
+    // boundaries, so that the global-load latency overlaps the split/store work and the barrier waits
+    auto load_A = [&](int it2, int ks2, float4 (&dst)[4]) {
+      const int item2 = blockIdx.x + it2 * gridDim.x;
+      const int tt2 = (item2 / g.n_tiles) % g.t_tiles;
+      const int b2 = item2 / (g.n_tiles * g.t_tiles);
+      const float* Ab2 = a.A + (size_t)b2 * a.K * a.pitch + (size_t)tt2 * TM + lane * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = ks2 * KS + pw * 4 + j;
+        dst[j] = (k < a.K && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab2 + (size_t)k * a.pitch))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 vnext[4];
+    if (PRO != PRO_DW && items_per_cta > 0) load_A(0, 0, vnext);
     for (int it = 0; it < items_per_cta; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int nt = item % g.n_tiles;
       const int tt = (item / g.n_tiles) % g.t_tiles;
       const int b = item / (g.n_tiles * g.t_tiles);
-      const float* Ab = a.A + (size_t)b * a.K * a.pitch + (size_t)tt * TM + lane * 4;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(g.wimg) + (size_t)nt * g.k_slabs * NPREC * g.w_bytes;
       // PRO_DW: per-sample gLN1 statistics of h (the A operand)
       float2 mr1 = make_float2(0.f, 1.f);
@@ -190,23 +214,24 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
         float4 v[4];
         if (PRO != PRO_DW) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = ks * KS + pw * 4 + j;
-            v[j] = (k < a.K && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab + (size_t)k * a.pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j = 0; j < 4; ++j) v[j] = vnext[j];
+          const int ks_n = ks + 1 < g.k_slabs ? ks + 1 : 0;
+          const int it_n = ks + 1 < g.k_slabs ? it : it + 1;
+          if (it_n < items_per_cta) load_A(it_n, ks_n, vnext);
         } else {
           // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside.
           // All 12 128-bit loads of the slab (4 channels x 3 taps) are issued before any arithmetic.  The branch below is
           // uniform over the CTA (depends on the item only).
           const bool skipl = (g.dbg & 2u) != 0;
+          const bool pfn = (ks + 1 < g.k_slabs) && !(g.dbg & 16u);
           if (dw_interior) {
-            if (dcls == 4) dw_slab<4, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
-            else if (dcls == 2) dw_slab<2, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
-            else dw_slab<1, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            if (dcls == 4) dw_slab<4, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else dw_slab<1, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
           } else {
-            if (dcls == 4) dw_slab<4, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
-            else if (dcls == 2) dw_slab<2, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
-            else dw_slab<1, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, v, dls, dlss);
+            if (dcls == 4) dw_slab<4, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else dw_slab<1, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
           }
         }
         ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < ((g.dbg & 64u) ? 0 : 4); ++j) {
           const int kl = pw * 4 + j;  // 0..31 within the slab
           const int kg = kl >> 2, r = kl & 3;
           // MN-major tf32 needs SWIZZLE_128B_BASE32B (the only MN-major layout the tensor core accepts for 32-bit
@@ -233,13 +258,11 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
           if (PRO == PRO_PRELU) {
             x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
           }
-          float4 hi = make_float4(ptx::to_tf32(x.x), ptx::to_tf32(x.y), ptx::to_tf32(x.z), ptx::to_tf32(x.w));
+          float4 hi, lo;
+          ptx::split_tf32(x.x, hi.x, lo.x); ptx::split_tf32(x.y, hi.y, lo.y);
+          ptx::split_tf32(x.z, hi.z, lo.z); ptx::split_tf32(x.w, hi.w, lo.w);
           *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + off) = hi;
-          if (NPASS == 3) {
-            float4 lo = make_float4(ptx::to_tf32(x.x - hi.x), ptx::to_tf32(x.y - hi.y), ptx::to_tf32(x.z - hi.z),
-                                    ptx::to_tf32(x.w - hi.w));
-            *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off) = lo;
-          }
+          if (NPASS == 3) *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off) = lo;
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -337,6 +360,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
       const int ncols = egroup == 0 ? csplit : ncols_all;
 
       const bool do_store = !(g.dbg & 1u);
+      const bool tile_full = tt * TM + TM <= a.frames;  // every time step of this tile is a real frame
       auto process = [&](const uint32_t (&buf)[16], int c0) {
         float wv[16];
         if (EPI == EPI_MASK) {
@@ -353,6 +377,9 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
           const float4 p4 = *reinterpret_cast<const float4*>(sp + c0 + j4 * 4);
           pv[j4 * 4] = p4.x; pv[j4 * 4 + 1] = p4.y; pv[j4 * 4 + 2] = p4.z; pv[j4 * 4 + 3] = p4.w;
         }
+        float* q = Dp + (size_t)c0 * a.pitch;
+        float* qm = Mp ? Mp + (size_t)c0 * a.pitch : nullptr;
+        const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
         float o[16], mk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -364,41 +391,37 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
             mk[j] = __fdividef(1.f, 1.f + __expf(-(v + pv[j])));
             v = mk[j] * wv[j];
           }
-          if (!tvalid) { v = 0.f; mk[j] = 0.f; }
           o[j] = v;
         }
-        float* q = Dp + (size_t)c0 * a.pitch;
-        float* qm = Mp ? Mp + (size_t)c0 * a.pitch : nullptr;
-        if (c0 + 16 <= nvalid) {  // full chunk (warp-uniform): no per-element predicates
-          if (do_store) {
+        if (full) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) q[(size_t)j * a.pitch] = o[j];
-            if (EPI == EPI_MASK && qm) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) qm[(size_t)j * a.pitch] = mk[j];
-            }
+          for (int j = 0; j < 16; ++j) {
+            *q = o[j];
+            q += a.pitch;
+            if (EPI == EPI_H) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
           }
-          if (EPI == EPI_H) {
+          if (EPI == EPI_MASK && qm) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
+            for (int j = 0; j < 16; ++j) { *qm = mk[j]; qm += a.pitch; }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            const float v = tvalid ? o[j] : 0.f;
             if (c0 + j < nvalid) {
               if (do_store) {
-                q[(size_t)j * a.pitch] = o[j];
-                if (EPI == EPI_MASK && qm) qm[(size_t)j * a.pitch] = mk[j];
+                q[(size_t)j * a.pitch] = v;
+                if (EPI == EPI_MASK && qm) qm[(size_t)j * a.pitch] = tvalid ? mk[j] : 0.f;
               }
-              if (EPI == EPI_H) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
+              if (EPI == EPI_H) { ls += v; lss = fmaf(v, v, lss); }
             }
           }
         }
       };
 
       uint32_t bufA[16], bufB[16];
-      if (cbeg < ncols) ptx::tmem_ld16(taddr + (uint32_t)cbeg, bufA);
-      for (int c0 = cbeg; c0 < ncols; c0 += 32) {
+      if (cbeg < ncols && !(g.dbg & 32u)) ptx::tmem_ld16(taddr + (uint32_t)cbeg, bufA);
+      for (int c0 = cbeg; c0 < ((g.dbg & 32u) ? 0 : ncols); c0 += 32) {
         ptx::tmem_ld_wait();
         if (c0 + 16 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 16), bufB);
         process(bufA, c0);

@@ -10,7 +10,10 @@ from ctn_b200 import _native as N
 dev = torch.device("cuda", 0)
 B, pitch, frames = 32, 4096, 3999
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CTN_UMMA"))
-for (name, M, K, epi) in (("pw1", 512, 128, 2), ("pw2", 256, 512, 0), ("head", 128, 512, 0), ("mask", 1024, 128, 0)):
+import sys as _s
+SHAPES = (("pw1", 512, 128, 2), ("pw2", 256, 512, 0), ("head", 128, 512, 0), ("mask", 1024, 128, 0))
+if len(_s.argv) > 1: SHAPES = tuple(x for x in SHAPES if x[0] in _s.argv[1:])
+for (name, M, K, epi) in SHAPES:
     A = torch.randn(B, K, pitch, device=dev)
     W = torch.randn(M, K, device=dev) / K ** 0.5
     D = torch.empty(B, M, pitch, device=dev)
