@@ -28,9 +28,8 @@ constexpr int TM = 128;       // time steps per tile (UMMA M)
 constexpr int KS = 32;        // input channels per smem slab (one 128-byte swizzle row of tf32)
 constexpr int A_BYTES = TM * KS * 4;  // 16 KB per precision
 constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 13 * 32;      // PRO_DW kernels: 4 epilogue + 1 MMA + 8 producer warps
-constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: a second epilogue warpgroup (warps 13-16)
-constexpr int PROD_WARPS = 8;
+constexpr int NUM_THREADS_DW = 21 * 32;   // PRO_DW kernels: 4 epilogue + 1 MMA + 16 producer warps (2 channels each)
+constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: 4 + 1 + 8 producer warps + a second epilogue warpgroup (13-16)
 constexpr int SMEM_HEADER = 2048;   // barriers + tmem pointer, then the epilogue parameter row
 constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
 
@@ -58,17 +57,25 @@ struct __align__(8) SmemHeader {
 template <int DCLS, bool INTERIOR>
 __device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, const float4 q2, float gsc, float gsh, float w0,
                                              float w1, float w2, float bd, float slope, int first, int step, int tbase,
-                                             int frames, bool cvalid, float& ls, float& lss) {
+                                             int frames, bool cvalid, float2& ls, float2& lss) {
   const float win[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
   constexpr int i0 = DCLS == 4 ? 0 : (DCLS == 2 ? 2 : 3);
   constexpr int i1 = 4;
   constexpr int i2 = DCLS == 4 ? 8 : (DCLS == 2 ? 6 : 5);
   float o[4];
   if (INTERIOR) {
+    // packed fp32 (FFMA2): two time steps per instruction
     const float a0 = gsc * w0, a1 = gsc * w1, a2 = gsc * w2;
     const float cst = fmaf(gsh, (w0 + w1) + w2, bd);
+    const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), C = make_float2(cst, cst);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = fmaf(a2, win[i2 + e], fmaf(a1, win[i1 + e], fmaf(a0, win[i0 + e], cst)));
+    for (int e = 0; e < 4; e += 2) {
+      float2 r = __ffma2_rn(A0, make_float2(win[i0 + e], win[i0 + e + 1]), C);
+      r = __ffma2_rn(A1, make_float2(win[i1 + e], win[i1 + e + 1]), r);
+      r = __ffma2_rn(A2, make_float2(win[i2 + e], win[i2 + e + 1]), r);
+      o[e] = r.x;
+      o[e + 1] = r.y;
+    }
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -87,23 +94,25 @@ __device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, c
     float u = prelu_f(o[e], slope);
     if (!INTERIOR && (tbase + e >= frames || !cvalid)) u = 0.f;
     o[e] = u;
-    ls += u;
-    lss = fmaf(u, u, lss);
   }
+  const float2 u01 = make_float2(o[0], o[1]), u23 = make_float2(o[2], o[3]);
+  ls = __fadd2_rn(ls, __fadd2_rn(u01, u23));
+  lss = __ffma2_rn(u01, u01, lss);
+  lss = __ffma2_rn(u23, u23, lss);
   return make_float4(o[0], o[1], o[2], o[3]);
 }
 
-template <int DCLS, bool INTERIOR>
+template <int DCLS, bool INTERIOR, int CPW>
 __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, int tbase, float2 mr1, float pslope, bool skip_loads,
-                                        bool prefetch_next, float4 (&v)[4], float& dls, float& dlss) {
+                                        bool prefetch_next, float4 (&v)[CPW], float2& dls, float2& dlss) {
   const int d = a.dw_dilation, pl = a.dw_pad_left;
   const int step = DCLS == 4 ? d : 4;
   const int first = DCLS == 4 ? tbase - pl : tbase - 4;
-  float4 q[4][3];
-  float pg[4], pb[4], pbd[4], pw0[4], pw1[4], pw2[4];
+  float4 q[CPW][3];
+  float pg[CPW], pb[CPW], pbd[CPW], pw0[CPW], pw1[CPW], pw2[CPW];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = ks * 32 + pw * 4 + j;
+  for (int j = 0; j < CPW; ++j) {
+    const int c = ks * 32 + pw * CPW + j;
     const int cc = INTERIOR ? c : (c < a.K ? c : a.K - 1);
     const float* hr = a.A + ((size_t)b * a.K + cc) * a.pitch;
 #pragma unroll
@@ -118,15 +127,15 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
   if (prefetch_next && INTERIOR) {
     // pull the next slab's rows towards the SM while this slab is being computed (no register cost)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float* hr = a.A + ((size_t)b * a.K + (ks + 1) * 32 + pw * 4 + j) * a.pitch;
+    for (int j = 0; j < CPW; ++j) {
+      const float* hr = a.A + ((size_t)b * a.K + (ks + 1) * 32 + pw * CPW + j) * a.pitch;
 #pragma unroll
       for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + first + k * step));
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = ks * 32 + pw * 4 + j;
+  for (int j = 0; j < CPW; ++j) {
+    const int c = ks * 32 + pw * CPW + j;
     const float gsc = pg[j] * mr1.y, gsh = pb[j] - mr1.x * mr1.y * pg[j];
     v[j] = dw_channel<DCLS, INTERIOR>(q[j][0], q[j][1], q[j][2], gsc, gsh, pw0[j], pw1[j], pw2[j], pbd[j], pslope, first, step,
                                       tbase, a.frames, c < a.K, dls, dlss);
@@ -134,9 +143,11 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
 }
 
 template <int PRO, int EPI, int NPASS>
-__global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
+__global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
   constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
   constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;  // epilogue warpgroups (each covers all 128 TMEM lanes)
+  constexpr int PROD_WARPS = PRO == PRO_DW ? 16 : 8;
+  constexpr int CPW = KS / PROD_WARPS;            // channels of a slab per producer warp (2 or 4)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -166,29 +177,29 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
   // item -> (b, tt, nt): nt fastest so that concurrently running CTAs share the activation tile in L2
   const int items_per_cta = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 5 && warp < 13) {
+  if (warp >= 5 && warp < 5 + PROD_WARPS) {
     // ===================================== PRODUCERS ========================================================
-    const int p = threadIdx.x - 160;  // 0..255
-    const int pw = p >> 5;            // producer warp 0..7: rows pw*4 .. pw*4+3 of the slab
+    const int p = threadIdx.x - 160;  // 0 .. 32*PROD_WARPS-1
+    const int pw = p >> 5;            // producer warp: rows pw*CPW .. pw*CPW+CPW-1 of the slab
     float pslope = 0.f;
     if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
     int s = 0;
     uint32_t ph = 0;
     // activation loads of slab (it2, ks2): issued ONE SLAB AHEAD of their use (register double buffer), across item
     // boundaries, so that the global-load latency overlaps the split/store work and the barrier waits
-    auto load_A = [&](int it2, int ks2, float4 (&dst)[4]) {
+    auto load_A = [&](int it2, int ks2, float4 (&dst)[CPW]) {
       const int item2 = blockIdx.x + it2 * gridDim.x;
       const int tt2 = (item2 / g.n_tiles) % g.t_tiles;
       const int b2 = item2 / (g.n_tiles * g.t_tiles);
       const float* Ab2 = a.A + (size_t)b2 * a.K * a.pitch + (size_t)tt2 * TM + lane * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = ks2 * KS + pw * 4 + j;
+      for (int j = 0; j < CPW; ++j) {
+        const int k = ks2 * KS + pw * CPW + j;
         dst[j] = (k < a.K && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab2 + (size_t)k * a.pitch))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 vnext[4];
+    float4 vnext[CPW];
     if (PRO != PRO_DW && items_per_cta > 0) load_A(0, 0, vnext);
     for (int it = 0; it < items_per_cta; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(g.wimg) + (size_t)nt * g.k_slabs * NPREC * g.w_bytes;
       // PRO_DW: per-sample gLN1 statistics of h (the A operand)
       float2 mr1 = make_float2(0.f, 1.f);
-      float dls = 0.f, dlss = 0.f;
+      float2 dls = make_float2(0.f, 0.f), dlss = make_float2(0.f, 0.f);
       if (PRO == PRO_DW) mr1 = gln_mean_rstd(a.dw_stats_in + 2 * b, (double)a.K * (double)a.frames, a.dw_eps);
       const int tbase = tt * TM + lane * 4;  // first of this thread's 4 time steps
       int dcls = 4;
@@ -211,10 +222,10 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
                       (a.dw_pad_left == d);
       }
       for (int ks = 0; ks < g.k_slabs; ++ks) {
-        float4 v[4];
+        float4 v[CPW];
         if (PRO != PRO_DW) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = vnext[j];
+          for (int j = 0; j < CPW; ++j) v[j] = vnext[j];
           const int ks_n = ks + 1 < g.k_slabs ? ks + 1 : 0;
           const int it_n = ks + 1 < g.k_slabs ? it : it + 1;
           if (it_n < items_per_cta) load_A(it_n, ks_n, vnext);
@@ -225,13 +236,13 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
           const bool skipl = (g.dbg & 2u) != 0;
           const bool pfn = (ks + 1 < g.k_slabs) && !(g.dbg & 16u);
           if (dw_interior) {
-            if (dcls == 4) dw_slab<4, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
-            else if (dcls == 2) dw_slab<2, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
-            else dw_slab<1, true>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            if (dcls == 4) dw_slab<4, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else dw_slab<1, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
           } else {
-            if (dcls == 4) dw_slab<4, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
-            else if (dcls == 2) dw_slab<2, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
-            else dw_slab<1, false>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            if (dcls == 4) dw_slab<4, false, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else if (dcls == 2) dw_slab<2, false, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
+            else dw_slab<1, false, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
           }
         }
         ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
@@ -246,8 +257,8 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
           }
         }
 #pragma unroll
-        for (int j = 0; j < ((g.dbg & 64u) ? 0 : 4); ++j) {
-          const int kl = pw * 4 + j;  // 0..31 within the slab
+        for (int j = 0; j < ((g.dbg & 64u) ? 0 : CPW); ++j) {
+          const int kl = pw * CPW + j;  // 0..31 within the slab
           const int kg = kl >> 2, r = kl & 3;
           // MN-major tf32 needs SWIZZLE_128B_BASE32B (the only MN-major layout the tensor core accepts for 32-bit
           // operands; pinned on hardware with tools/umma_unit.cu): atoms of 4 channel rows x 128 B (32 time steps),
@@ -259,8 +270,12 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
             x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
           }
           float4 hi, lo;
-          ptx::split_tf32(x.x, hi.x, lo.x); ptx::split_tf32(x.y, hi.y, lo.y);
-          ptx::split_tf32(x.z, hi.z, lo.z); ptx::split_tf32(x.w, hi.w, lo.w);
+          hi.x = ptx::hi_tf32(x.x); hi.y = ptx::hi_tf32(x.y); hi.z = ptx::hi_tf32(x.z); hi.w = ptx::hi_tf32(x.w);
+          {  // lo = x - hi (exact), two elements per FADD2
+            const float2 l01 = __fadd2_rn(make_float2(x.x, x.y), make_float2(-hi.x, -hi.y));
+            const float2 l23 = __fadd2_rn(make_float2(x.z, x.w), make_float2(-hi.z, -hi.w));
+            lo = make_float4(l01.x, l01.y, l23.x, l23.y);
+          }
           *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + off) = hi;
           if (NPASS == 3) *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off) = lo;
         }
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
         if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
       if (PRO == PRO_DW && nt == 0) {
-        const double sd = warp_sum_d((double)dls), ssd = warp_sum_d((double)dlss);
+        const double sd = warp_sum_d((double)dls.x + (double)dls.y), ssd = warp_sum_d((double)dlss.x + (double)dlss.y);
         if (lane == 0) { atomicAdd(&a.dw_stats_out[2 * b], sd); atomicAdd(&a.dw_stats_out[2 * b + 1], ssd); }
       }
     }
@@ -317,7 +332,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8, 
     float eslope = 0.f;
     if (EPI == EPI_H) eslope = a.slope[0];
     float* sp = reinterpret_cast<float*>(smem + SMEM_PARAMS);  // [256] per-channel epilogue parameter
-    const int egroup = warp >= 13 ? 1 : 0;                     // second warpgroup handles the upper half of the columns
+    const int egroup = (EGROUPS == 2 && warp >= 13) ? 1 : 0;                     // second warpgroup handles the upper half of the columns
     const int te = (warp & 3) * 32 + lane;                     // time step within the tile == TMEM lane
     const int tid_e = egroup * 128 + te;
     for (int it = 0; it < items_per_cta; ++it) {
@@ -504,7 +519,7 @@ int num_sms() {
 
 template <int PRO, int EPI, int NPASS>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
-  constexpr int NT = PRO == PRO_DW ? NUM_THREADS : NUM_THREADS_E8;
+  constexpr int NT = PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

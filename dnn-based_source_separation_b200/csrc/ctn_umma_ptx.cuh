@@ -107,6 +107,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+__device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 // ---- descriptors -------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B canonical layouts:
 //   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
