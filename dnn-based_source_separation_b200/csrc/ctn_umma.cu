@@ -21,6 +21,7 @@
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -39,6 +40,7 @@ struct UmmaArgs {
   int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
   uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
   uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
+  int cluster, tiles_total, cluster_items;  // CTAs per cluster sharing weight slabs by multicast; B*t_tiles; n_tiles*ceil(tiles/cluster)
   uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
 
@@ -47,6 +49,7 @@ struct __align__(8) SmemHeader {
   uint64_t empty[MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t wempty[MAX_STAGES];  // cluster mode: on the leader CTA, "every CTA of the cluster has consumed weight stage s"
   uint32_t tmem_base;
 };
 
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), PROD_WARPS + 1);
       ptx::mbar_init(ptx::smem_u32(&hdr->empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->wempty[s]), (uint32_t)g.cluster);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&hdr->tfull[i]), 1);
@@ -173,9 +177,24 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  if (g.cluster > 1) ptx::cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
 
-  // item -> (b, tt, nt): nt fastest so that concurrently running CTAs share the activation tile in L2
-  const int items_per_cta = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Work decomposition.  A cluster of C CTAs walks the same sequence of cluster items J = cidx + it * num_clusters;
+  // J -> (weight tile nt = J % n_tiles, tile group J / n_tiles); CTA rank r of the cluster takes time tile
+  // L = group * C + r -> (b, tt).  All CTAs of a cluster therefore need the SAME weight slabs at the same step, which
+  // the leader multicasts once; ranks whose L falls off the end run a dummy item (no loads, no stores).
+  const int crank = g.cluster > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int cidx = (int)blockIdx.x / g.cluster, num_clusters = (int)gridDim.x / g.cluster;
+  const int items_per_cta = (g.cluster_items - cidx + num_clusters - 1) / num_clusters;
+  auto decode = [&](int it2, int& nt2, int& tt2, int& b2) -> bool {
+    const int J = cidx + it2 * num_clusters;
+    nt2 = J % g.n_tiles;
+    const int L = (J / g.n_tiles) * g.cluster + crank;
+    tt2 = L % g.t_tiles;
+    b2 = L / g.t_tiles;
+    if (L >= g.tiles_total) { tt2 = 0; b2 = 0; return false; }
+    return true;
+  };
 
   if (warp >= 5 && warp < 5 + PROD_WARPS) {
     // ===================================== PRODUCERS ========================================================
@@ -188,24 +207,21 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     // activation loads of slab (it2, ks2): issued ONE SLAB AHEAD of their use (register double buffer), across item
     // boundaries, so that the global-load latency overlaps the split/store work and the barrier waits
     auto load_A = [&](int it2, int ks2, float4 (&dst)[CPW]) {
-      const int item2 = blockIdx.x + it2 * gridDim.x;
-      const int tt2 = (item2 / g.n_tiles) % g.t_tiles;
-      const int b2 = item2 / (g.n_tiles * g.t_tiles);
+      int nt2, tt2, b2;
+      const bool live2 = decode(it2, nt2, tt2, b2);
       const float* Ab2 = a.A + (size_t)b2 * a.K * a.pitch + (size_t)tt2 * TM + lane * 4;
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
         const int k = ks2 * KS + pw * CPW + j;
-        dst[j] = (k < a.K && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab2 + (size_t)k * a.pitch))
+        dst[j] = (k < a.K && live2 && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab2 + (size_t)k * a.pitch))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     float4 vnext[CPW];
     if (PRO != PRO_DW && items_per_cta > 0) load_A(0, 0, vnext);
     for (int it = 0; it < items_per_cta; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int nt = item % g.n_tiles;
-      const int tt = (item / g.n_tiles) % g.t_tiles;
-      const int b = item / (g.n_tiles * g.t_tiles);
+      int nt, tt, b;
+      const bool live = decode(it, nt, tt, b);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(g.wimg) + (size_t)nt * g.k_slabs * NPREC * g.w_bytes;
       // PRO_DW: per-sample gLN1 statistics of h (the A operand)
       float2 mr1 = make_float2(0.f, 1.f);
@@ -235,7 +251,10 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           // uniform over the CTA (depends on the item only).
           const bool skipl = (g.dbg & 2u) != 0;
           const bool pfn = (ks + 1 < g.k_slabs) && !(g.dbg & 16u);
-          if (dw_interior) {
+          if (!live) {
+#pragma unroll
+            for (int j = 0; j < CPW; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (dw_interior) {
             if (dcls == 4) dw_slab<4, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
             else if (dcls == 2) dw_slab<2, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
             else dw_slab<1, true, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
@@ -251,9 +270,18 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           const uint32_t fb = ptx::smem_u32(&hdr->full[s]);
           if (g.dbg & 4u) {
             ptx::mbar_arrive(fb);
-          } else {
+          } else if (g.cluster == 1) {
             ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
             ptx::bulk_g2s(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb);
+          } else {
+            // every CTA expects the slab on its own barrier; the leader waits until ALL CTAs of the cluster have consumed
+            // stage s, then one L2 read feeds every CTA (multicast bulk copy, same CTA-relative offsets)
+            ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
+            if (crank == 0) {
+              ptx::mbar_wait(ptx::smem_u32(&hdr->wempty[s]), ph ^ 1u);
+              ptx::bulk_g2s_multicast(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb,
+                                      (uint16_t)((1u << g.cluster) - 1u));
+            }
           }
         }
 #pragma unroll
@@ -284,7 +312,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
         if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
-      if (PRO == PRO_DW && nt == 0) {
+      if (PRO == PRO_DW && nt == 0 && live) {
         const double sd = warp_sum_d((double)dls.x + (double)dls.y), ssd = warp_sum_d((double)dlss.x + (double)dlss.y);
         if (lane == 0) { atomicAdd(&a.dw_stats_out[2 * b], sd); atomicAdd(&a.dw_stats_out[2 * b + 1], ssd); }
       }
@@ -318,6 +346,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
             }
           }
           ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // frees the smem stage when these MMAs have retired
+          if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[s]), (uint16_t)1u);  // -> leader CTA
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
         ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
@@ -336,15 +365,13 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     const int te = (warp & 3) * 32 + lane;                     // time step within the tile == TMEM lane
     const int tid_e = egroup * 128 + te;
     for (int it = 0; it < items_per_cta; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int nt = item % g.n_tiles;
-      const int tt = (item / g.n_tiles) % g.t_tiles;
-      const int b = item / (g.n_tiles * g.t_tiles);
+      int nt, tt, b;
+      const bool live = decode(it, nt, tt, b);
       const int acc = it & 1;
       const int t = tt * TM + te;
       const bool tvalid = t < a.frames;
       const int n0 = nt * g.n_tile;
-      const int nvalid = min(g.n_tile, a.M - n0);
+      const int nvalid = live ? min(g.n_tile, a.M - n0) : 0;  // dummy item: nothing to read, store or count
       float mscale = 1.f;
       {
         // stage the per-channel parameter: EPI_HEAD: v1 - mean*rstd*v2 (deferred gLN shift); EPI_H / EPI_MASK: bias
@@ -455,6 +482,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (g.cluster > 1) ptx::cluster_sync_all();  // nobody exits while a peer may still multicast into it / arrive on it
   if (warp == 4) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -526,7 +554,25 @@ int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  k_pw_umma<PRO, EPI, NPASS><<<grid, NT, smem, st>>>(g);
+  if (g.cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_pw_umma<PRO, EPI, NPASS>, g);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    k_pw_umma<PRO, EPI, NPASS><<<grid, NT, smem, st>>>(g);
+  }
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
@@ -609,7 +655,15 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   int grid = num_sms();
   static const char* env_grid = getenv("CTN_UMMA_GRID");
   if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
-  if (grid > g.num_items) grid = g.num_items;
+  static const char* env_cl = getenv("CTN_UMMA_CLUSTER");
+  int cluster = env_cl ? atoi(env_cl) : 2;
+  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+  g.tiles_total = a.B * g.t_tiles;
+  while (cluster > 1 && (grid % cluster != 0 || g.tiles_total < cluster)) cluster >>= 1;
+  g.cluster = cluster;
+  g.cluster_items = g.n_tiles * ((g.tiles_total + cluster - 1) / cluster);
+  const int max_grid = g.cluster_items * cluster;
+  if (grid > max_grid) grid = max_grid;
 #define UM_LAUNCH(P, E)                                                                   \
   if (pro == P && epi == E)                                                               \
     return nprec == 2 ? launch<P, E, 3>(g, smem, grid, st) : launch<P, E, 1>(g, smem, grid, st);
