@@ -26,9 +26,15 @@
 namespace {
 
 constexpr int TM = 128;       // time steps per tile (UMMA M)
-constexpr int KS = 32;        // input channels per smem slab (one 128-byte swizzle row of tf32)
-constexpr int A_BYTES = TM * KS * 4;  // 16 KB per precision
-constexpr int MAX_STAGES = 6;
+#ifndef CTN_KS
+#define CTN_KS 32
+#endif
+constexpr int KS = CTN_KS;    // input channels per smem slab.  32: 128-byte weight rows (SWIZZLE_128B), 2-3 stages;
+                              // 16: 64-byte rows (SWIZZLE_64B), 4-6 stages -- measured SLOWER (per-slab handshakes dominate)
+constexpr int A_BYTES = TM * KS * 4;  // 8 KB per precision
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t W_LAYOUT = KS == 32 ? 2u : 4u;    // UMMA layout type of the weight operand (SWIZZLE_128B / SWIZZLE_64B)
+constexpr uint32_t W_SBO = KS == 32 ? 1024u : 512u;  // bytes between 8-row groups of the weight image
 constexpr int NUM_THREADS_DW = 21 * 32;   // PRO_DW kernels: 4 epilogue + 1 MMA + 16 producer warps (2 channels each)
 constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: 4 + 1 + 8 producer warps + a second epilogue warpgroup (13-16)
 constexpr int SMEM_HEADER = 2048;   // barriers + tmem pointer, then the epilogue parameter row
@@ -40,9 +46,17 @@ struct UmmaArgs {
   int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
   uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
   uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
-  int cluster, tiles_total, cluster_items;  // CTAs per cluster sharing weight slabs by multicast; B*t_tiles; n_tiles*ceil(tiles/cluster)
+  int cluster, tiles_total, cluster_items, wsplit;  // CTAs per cluster sharing weight slabs by multicast; B*t_tiles; n_tiles*ceil(tiles/cluster)
   uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
+
+// debug timeline (CTN_UMMA_DBG bit 128): CTA 0 records globaltimer stamps per role and slab
+__device__ unsigned long long g_timeline[3 * 4096];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct __align__(8) SmemHeader {
   uint64_t full[MAX_STAGES];
@@ -115,7 +129,7 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
   float pg[CPW], pb[CPW], pbd[CPW], pw0[CPW], pw1[CPW], pw2[CPW];
 #pragma unroll
   for (int j = 0; j < CPW; ++j) {
-    const int c = ks * 32 + pw * CPW + j;
+    const int c = ks * KS + pw * CPW + j;
     const int cc = INTERIOR ? c : (c < a.K ? c : a.K - 1);
     const float* hr = a.A + ((size_t)b * a.K + cc) * a.pitch;
 #pragma unroll
@@ -131,14 +145,14 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
     // pull the next slab's rows towards the SM while this slab is being computed (no register cost)
 #pragma unroll
     for (int j = 0; j < CPW; ++j) {
-      const float* hr = a.A + ((size_t)b * a.K + (ks + 1) * 32 + pw * CPW + j) * a.pitch;
+      const float* hr = a.A + ((size_t)b * a.K + (ks + 1) * KS + pw * CPW + j) * a.pitch;
 #pragma unroll
       for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + first + k * step));
     }
   }
 #pragma unroll
   for (int j = 0; j < CPW; ++j) {
-    const int c = ks * 32 + pw * CPW + j;
+    const int c = ks * KS + pw * CPW + j;
     const float gsc = pg[j] * mr1.y, gsh = pb[j] - mr1.x * mr1.y * pg[j];
     v[j] = dw_channel<DCLS, INTERIOR>(q[j][0], q[j][1], q[j][2], gsc, gsh, pw0[j], pw1[j], pw2[j], pbd[j], pslope, first, step,
                                       tbase, a.frames, c < a.K, dls, dlss);
@@ -264,7 +278,10 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
             else dw_slab<1, false, CPW>(a, b, ks, pw, tbase, mr1, pslope, skipl, pfn, v, dls, dlss);
           }
         }
+        const bool tl = (g.dbg & 128u) && blockIdx.x == 0 && p == 0 && (it * g.k_slabs + ks) < 1024;
+        if (tl) g_timeline[(it * g.k_slabs + ks) * 4 + 0] = gtime();
         ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
+        if (tl) g_timeline[(it * g.k_slabs + ks) * 4 + 1] = gtime();
         const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
         if (p == 0) {
           const uint32_t fb = ptx::smem_u32(&hdr->full[s]);
@@ -272,7 +289,9 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
             ptx::mbar_arrive(fb);
           } else if (g.cluster == 1) {
             ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
-            ptx::bulk_g2s(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb);
+            const uint32_t chunk = NPREC * g.w_bytes / (uint32_t)g.wsplit;  // several requests in flight per slab
+            for (int c = 0; c < g.wsplit; ++c)
+              ptx::bulk_g2s(st_base + NPREC * A_BYTES + c * chunk, wsrc + (size_t)ks * NPREC * g.w_bytes + (size_t)c * chunk, chunk, fb);
           } else {
             // every CTA expects the slab on its own barrier; the leader waits until ALL CTAs of the cluster have consumed
             // stage s, then one L2 read feeds every CTA (multicast bulk copy, same CTA-relative offsets)
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         }
 #pragma unroll
         for (int j = 0; j < ((g.dbg & 64u) ? 0 : CPW); ++j) {
-          const int kl = pw * CPW + j;  // 0..31 within the slab
+          const int kl = pw * CPW + j;  // 0..KS-1 within the slab
           const int kg = kl >> 2, r = kl & 3;
           // MN-major tf32 needs SWIZZLE_128B_BASE32B (the only MN-major layout the tensor core accepts for 32-bit
           // operands; pinned on hardware with tools/umma_unit.cu): atoms of 4 channel rows x 128 B (32 time steps),
@@ -310,6 +329,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
+        if (tl) g_timeline[(it * g.k_slabs + ks) * 4 + 2] = gtime();
         if (++s == g.stages) { s = 0; ph ^= 1u; }
       }
       if (PRO == PRO_DW && nt == 0 && live) {
@@ -319,37 +339,62 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     }
   } else if (warp == 4) {
     // ===================================== MMA ISSUER =======================================================
-    if (lane == 0) {
+    // The whole warp walks the loop converged; one elected lane issues.  The stage-free commit of slab q is issued
+    // AFTER the first MMA of slab q+1 (same item), so the tensor pipe always has work queued while the thread is busy
+    // with the commit / barrier bookkeeping.
+    {
       int s = 0;
       uint32_t ph = 0;
+      const bool leader = ptx::elect_one();
+      // descriptor templates: only the 14-bit start-address field changes
+      const uint64_t da_t = ptx::make_smem_desc(0, g.lbo_a, g.sbo_a, 1);
+      const uint64_t dw_t = ptx::make_smem_desc(0, g.lbo_w, g.sbo_w, W_LAYOUT);
       for (int it = 0; it < items_per_cta; ++it) {
         const int acc = it & 1;
         ptx::mbar_wait(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        int prev_s = -1;
         for (int ks = 0; ks < g.k_slabs; ++ks) {
+          const bool tl = (g.dbg & 128u) && blockIdx.x == 0 && lane == 0 && (it * g.k_slabs + ks) < 1024;
+          if (tl) g_timeline[4096 + (it * g.k_slabs + ks) * 4 + 0] = gtime();
           ptx::mbar_wait(ptx::smem_u32(&hdr->full[s]), ph);
+          if (tl) g_timeline[4096 + (it * g.k_slabs + ks) * 4 + 1] = gtime();
           ptx::tc_fence_after();
           const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
-          const uint32_t a_hi = st_base, a_lo = st_base + A_BYTES;
-          const uint32_t w_hi = st_base + NPREC * A_BYTES, w_lo = w_hi + g.w_bytes;
+          const uint32_t a_hi = st_base >> 4, a_lo = (st_base + A_BYTES) >> 4;
+          const uint32_t w_hi = (st_base + NPREC * A_BYTES) >> 4, w_lo = w_hi + (g.w_bytes >> 4);
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < ((g.dbg & 8u) ? 0 : KS / 8); ++kk) {
-            const uint64_t da_hi = ptx::make_smem_desc(a_hi + kk * 4096, g.lbo_a, g.sbo_a, 1);
-            const uint64_t dw_hi = ptx::make_smem_desc(w_hi + kk * 32, g.lbo_w, g.sbo_w);
-            ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
-            if (NPASS == 3) {
-              const uint64_t da_lo = ptx::make_smem_desc(a_lo + kk * 4096, g.lbo_a, g.sbo_a, 1);
-              const uint64_t dw_lo = ptx::make_smem_desc(w_lo + kk * 32, g.lbo_w, g.sbo_w);
-              ptx::mma_tf32(d_tmem, da_lo, dw_hi, g.idesc, 1u);
-              ptx::mma_tf32(d_tmem, da_hi, dw_lo, g.idesc, 1u);
+            for (int kk = 0; kk < KS / 8; ++kk) {
+              if (g.dbg & 8u) break;
+              const uint64_t da_hi = da_t | (uint64_t)(a_hi + kk * 256), dw_hi = dw_t | (uint64_t)(w_hi + kk * 2);
+              ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
+              if (kk == 0 && prev_s >= 0) {
+                ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));  // previous slab's stage (its MMAs are queued ahead)
+                if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
+              }
+              if (NPASS == 3) {
+                const uint64_t da_lo = da_t | (uint64_t)(a_lo + kk * 256), dw_lo = dw_t | (uint64_t)(w_lo + kk * 2);
+                ptx::mma_tf32(d_tmem, da_lo, dw_hi, g.idesc, 1u);
+                ptx::mma_tf32(d_tmem, da_hi, dw_lo, g.idesc, 1u);
+              }
+            }
+            if ((g.dbg & 8u) && prev_s >= 0) {
+              ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));
+              if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
+            }
+            if (ks == g.k_slabs - 1) {
+              ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // last slab of the item: free its stage right away
+              if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[s]), (uint16_t)1u);
+              ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
             }
           }
-          ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // frees the smem stage when these MMAs have retired
-          if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[s]), (uint16_t)1u);  // -> leader CTA
+          __syncwarp();
+          if (tl) g_timeline[4096 + (it * g.k_slabs + ks) * 4 + 2] = gtime();
+          prev_s = s;
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
       }
     }
     __syncwarp();
@@ -388,7 +433,10 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");
       }
+      const bool tle = (g.dbg & 128u) && blockIdx.x == 0 && threadIdx.x == 0 && it < 1024;
+      if (tle) g_timeline[8192 + it * 4 + 0] = gtime();
       ptx::mbar_wait(ptx::smem_u32(&hdr->tfull[acc]), (uint32_t)(it >> 1) & 1u);
+      if (tle) g_timeline[8192 + it * 4 + 1] = gtime();
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)((warp & 3) * 32) << 16);
       float* Dp = a.D + ((size_t)b * a.M + n0) * a.pitch + t;
@@ -473,6 +521,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+      if (tle) g_timeline[8192 + it * 4 + 2] = gtime();
       if (EPI == EPI_H) {
         double s = warp_sum_d((double)ls), ss = warp_sum_d((double)lss);
         if (lane == 0) { atomicAdd(&a.stats_out[2 * b], s); atomicAdd(&a.stats_out[2 * b + 1], ss); }
@@ -487,18 +536,25 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
 }
 
 // ---- weight images ---------------------------------------------------------------------------------------------
-// grid (k_slabs, n_tiles), block 256: builds the K-major SWIZZLE_128B image(s) of one (n_tile x 32) weight slab.
+// K-major SWIZZLE_64B image of an (n_tile x KS=16) weight slab: rows of 64 B (16 k), 8-row groups of 512 B (SBO),
+// 16-byte chunk index XOR ((row >> 1) & 3).  Float offset of element (row nl, k kl):
+__host__ __device__ __forceinline__ int wimg_offset(int nl, int kl) {
+  if (KS == 32)  // SWIZZLE_128B: rows of 128 B, 8-row groups of 1024 B, chunk index XOR (row & 7)
+    return (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
+  return (nl >> 3) * 128 + (nl & 7) * 16 + ((((kl >> 2) ^ ((nl >> 1) & 3)) << 2) | (kl & 3));
+}
+
+// grid (k_slabs, n_tiles), block 256: builds the image(s) of one weight slab.
 __global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs,
                                                     int nprec, float* __restrict__ wimg) {
   const int ks = blockIdx.x, nt = blockIdx.y;
-  const size_t per = (size_t)n_tile * 32;  // floats per precision
+  const size_t per = (size_t)n_tile * KS;  // floats per precision
   float* dst = wimg + ((size_t)nt * k_slabs + ks) * nprec * per;
-  for (int i = threadIdx.x; i < n_tile * 32; i += 256) {
-    const int nl = i >> 5, kl = i & 31;
-    const int n = nt * n_tile + nl, k = ks * 32 + kl;
+  for (int i = threadIdx.x; i < n_tile * KS; i += 256) {
+    const int nl = i / KS, kl = i % KS;
+    const int n = nt * n_tile + nl, k = ks * KS + kl;
     const float x = (n < M && k < K) ? W[(size_t)n * K + k] : 0.f;
-    // K-major SW128: 8-row groups of 1024 B, row = 128 B (32 k), 16-byte chunk index XOR (row & 7)
-    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
+    const int off = wimg_offset(nl, kl);
     const float hi = ptx::to_tf32(x);
     dst[off] = hi;
     if (nprec == 2) dst[per + off] = ptx::to_tf32(x - hi);
@@ -510,16 +566,16 @@ struct WimgJobs { WimgJob j[CTN_MAX_JOBS]; };
 __global__ void __launch_bounds__(256) k_build_wimg_batch(const WimgJobs jobs, int nprec) {
   const WimgJob& jb = jobs.j[blockIdx.y];
   const int n_tile = jb.M >= 256 ? 256 : ((jb.M + 15) / 16) * 16;
-  const int n_tiles = (jb.M + n_tile - 1) / n_tile, k_slabs = (jb.K + 31) / 32;
-  const size_t per = (size_t)n_tile * 32;
+  const int n_tiles = (jb.M + n_tile - 1) / n_tile, k_slabs = (jb.K + KS - 1) / KS;
+  const size_t per = (size_t)n_tile * KS;
   for (int blk = blockIdx.x; blk < n_tiles * k_slabs; blk += gridDim.x) {
     const int nt = blk / k_slabs, ks = blk - nt * k_slabs;
     float* dst = jb.wimg + ((size_t)nt * k_slabs + ks) * nprec * per;
-    for (int i = threadIdx.x; i < n_tile * 32; i += 256) {
-      const int nl = i >> 5, kl = i & 31;
-      const int n = nt * n_tile + nl, k = ks * 32 + kl;
+    for (int i = threadIdx.x; i < n_tile * KS; i += 256) {
+      const int nl = i / KS, kl = i % KS;
+      const int n = nt * n_tile + nl, k = ks * KS + kl;
       const float x = (n < jb.M && k < jb.K) ? jb.W[(size_t)n * jb.K + k] : 0.f;
-      const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
+      const int off = wimg_offset(nl, kl);
       const float hi = ptx::to_tf32(x);
       dst[off] = hi;
       if (nprec == 2) dst[per + off] = ptx::to_tf32(x - hi);
@@ -582,17 +638,24 @@ int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
 
 extern "C" int ctn_has_tcgen05(void) { return 1; }
 
+// debug: copy the timeline of the last CTN_UMMA_DBG&128 launch (3 regions x 4096 stamps) to the host
+extern "C" int ctn_debug_timeline(unsigned long long* host, int n) {
+  if (!host || n <= 0 || n > 3 * 4096) return CTN_EINVAL;
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_timeline, sizeof(unsigned long long) * n);
+  return e == cudaSuccess ? CTN_OK : (int)e;
+}
+
 size_t ctn_umma_wimg_bytes(int M, int K, int math) {
   const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
   const int n_tile = pick_n_tile(M);
-  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + 31) / 32;
-  return (size_t)n_tiles * k_slabs * nprec * n_tile * 32 * sizeof(float);
+  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
+  return (size_t)n_tiles * k_slabs * nprec * n_tile * KS * sizeof(float);
 }
 
 int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st) {
   const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;  // hi [, lo]
   const int n_tile = pick_n_tile(M);
-  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + 31) / 32;
+  const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
   k_build_wimg<<<dim3(k_slabs, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, nprec, wimg);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
@@ -612,7 +675,7 @@ int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t
     for (int i = 0; i < m; ++i) {
       wj.j[i] = jobs[i0 + i];
       const int n_tile = pick_n_tile(jobs[i0 + i].M);
-      const int blocks = ((jobs[i0 + i].M + n_tile - 1) / n_tile) * ((jobs[i0 + i].K + 31) / 32);
+      const int blocks = ((jobs[i0 + i].M + n_tile - 1) / n_tile) * ((jobs[i0 + i].K + KS - 1) / KS);
       if (blocks > maxb) maxb = blocks;
     }
     k_build_wimg_batch<<<dim3(maxb, m), 256, 0, st>>>(wj, nprec);
@@ -622,6 +685,7 @@ int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t
   return CTN_OK;
 }
 
+#define NPREC_HOST(m) ((m) == CTN_MATH_TF32X3 ? 2u : 1u)
 int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (!a.wimg) return CTN_EINVAL;
   if (a.pitch % TM != 0) return CTN_EALIGN;
@@ -635,7 +699,7 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   g.t_tiles = a.pitch / TM;
   g.num_items = a.B * g.t_tiles * g.n_tiles;
   const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
-  g.w_bytes = (uint32_t)g.n_tile * 128u;
+  g.w_bytes = (uint32_t)g.n_tile * (uint32_t)(KS * 4);
   g.stage_bytes = (uint32_t)nprec * (A_BYTES + g.w_bytes);
   const size_t budget = 227 * 1024 - SMEM_HEADER - 1024;
   int stages = (int)(budget / g.stage_bytes);
@@ -650,14 +714,20 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
   g.sbo_a = a.dbg_sbo_a ? a.dbg_sbo_a : 2048u;  // between 4-channel groups
   g.lbo_w = 16u;                                 // unused for swizzled K-major
-  g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : 1024u;  // between 8-row (output channel) groups
+  g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : W_SBO;  // between 8-row (output channel) groups
   const size_t smem = SMEM_HEADER + 1024 + (size_t)stages * g.stage_bytes;
   int grid = num_sms();
   static const char* env_grid = getenv("CTN_UMMA_GRID");
   if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
+  static const char* env_ws = getenv("CTN_UMMA_WSPLIT");
+  g.wsplit = env_ws ? atoi(env_ws) : 1;
+  if (g.wsplit < 1 || g.wsplit > 16 || ((NPREC_HOST(math) * g.w_bytes / g.wsplit) % 16) != 0) g.wsplit = 1;
   static const char* env_cl = getenv("CTN_UMMA_CLUSTER");
-  int cluster = env_cl ? atoi(env_cl) : 2;
-  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+  // cluster multicast of the weight slabs is EXPERIMENTAL (opt-in): it halves the L2 reads of the weights but measured no
+  // speed-up (the stage recycle latency, not L2 bandwidth, bounds the kernel) and the combination with the deferred
+  // stage commit currently fails parity; default is 1 CTA per cluster.
+  int cluster = env_cl ? atoi(env_cl) : 1;
+  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
   g.tiles_total = a.B * g.t_tiles;
   while (cluster > 1 && (grid % cluster != 0 || g.tiles_total < cluster)) cluster >>= 1;
   g.cluster = cluster;

@@ -50,6 +50,21 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void
       : "memory");
 }
 
+// one lane of a converged warp (elect.sync): code under this predicate is known single-threaded to the compiler, so
+// uniform-datapath instructions (tcgen05.mma / commit) are emitted without per-instruction election loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---- clusters ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -79,6 +79,7 @@ ctn_convtasnet_loss_host = _sig("ctn_convtasnet_loss_host", _i, C.POINTER(Config
 ctn_last_launch_count = _sig("ctn_last_launch_count", _i)
 ctn_debug_pointwise = _sig("ctn_debug_pointwise", _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _i,
                            C.POINTER(C.c_uint32), _fp, _sz, _fp)
+ctn_debug_timeline = _sig("ctn_debug_timeline", _i, C.POINTER(C.c_ulonglong), _i)
 ctn_profile_enable = _sig("ctn_profile_enable", _i, _i)
 ctn_profile_read = _sig("ctn_profile_read", _i, C.POINTER(C.c_double), C.POINTER(_i))
 STAGES = ("prep", "enc", "head", "pw1", "dw", "pw2", "fin", "mask", "dec", "loss")
@@ -88,7 +89,7 @@ EXPORTED = [
     "ctn_decoder_fwd", "ctn_gln_fwd", "ctn_cln_fwd", "ctn_tcn_workspace_bytes", "ctn_tcn_fwd", "ctn_convtasnet_fwd",
     "ctn_separator_fwd", "ctn_sisdr_fwd", "ctn_sisdr_pit_fwd", "ctn_sisdr_pit_scratch_bytes", "ctn_host_io_bytes",
     "ctn_convtasnet_loss_host", "ctn_last_launch_count", "ctn_profile_enable", "ctn_profile_read",
-    "ctn_debug_pointwise",
+    "ctn_debug_pointwise", "ctn_debug_timeline",
 ]
 
 

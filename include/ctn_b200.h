@@ -178,6 +178,10 @@ int ctn_debug_pointwise(const float* A, const float* W, float* D, int B, int M, 
                         const float* bias, const float* slope, double* stats_out, int epi, int math,
                         const uint32_t* dbg, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
 
+/* Test hook: globaltimer stamps recorded by CTA 0 of the last tcgen05 pointwise launch when the environment variable
+ * CTN_UMMA_DBG has bit 128 set: [0,4096) producer, [4096,8192) MMA issuer, [8192,12288) epilogue (4 words per step). */
+int ctn_debug_timeline(unsigned long long* host, int n);
+
 /* number of kernel launches the last ctn_* call on this thread enqueued (for bench.py's gpu_launches) */
 int ctn_last_launch_count(void);
 

@@ -17,6 +17,7 @@ struct Case {
   int consumer_fence;  // 1: issuing thread also executes fence.proxy.async before the MMA
   int swz;          // 1: XOR swizzle applied when staging, 0: plain (to see what the HW expects)
   int a_layout;     // 2: SWIZZLE_128B, 1: SWIZZLE_128B_BASE32B (MN-major tf32)
+  int b_layout;     // 2: SWIZZLE_128B (128-byte rows = 32 k), 4: SWIZZLE_64B (64-byte rows = 16 k)
   const char* name;
 };
 
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
   if (!c.b_bulk) {
     for (int i = tid; i < c.N * c.K; i += 128) {
       const int n = i / c.K, k = i % c.K;
-      const int off = (n >> 3) * 256 + (n & 7) * 32 + ((((k >> 2) ^ (n & 7))) << 2) + (k & 3);
+      int off = (n >> 3) * 256 + (n & 7) * 32 + ((((k >> 2) ^ (n & 7))) << 2) + (k & 3);
+      if (c.b_layout == 4) off = (n >> 3) * 128 + (n & 7) * 16 + ((((k >> 2) ^ ((n >> 1) & 3))) << 2) + (k & 3);
       sB[off] = Bm[n * c.K + k];
     }
   } else if (tid == 0) {
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(128) k_probe(const float* __restrict__ A, cons
     for (int kk = 0; kk < c.K / 8; ++kk) {
       const uint32_t a_addr = ptx::smem_u32(sA) + (c.a_mn_major ? (c.a_layout == 1 ? kk * 2 * c.sbo_a : kk * 4096) : kk * 32);
       const uint64_t da = ptx::make_smem_desc(a_addr, c.lbo_a, c.sbo_a, c.a_layout);
-      const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(sB) + kk * 32, 16, c.sbo_b);
+      const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(sB) + kk * 32, 16, c.sbo_b, c.b_layout);
       ptx::mma_tf32(tmem, da, db, idesc, kk ? 1u : 0u);
     }
     ptx::mma_commit(ptx::smem_u32(&bars[0]));
@@ -144,17 +146,21 @@ static bool run_case(const Case& c) {
 int main() {
   std::vector<Case> cases = {
       // K-major A: the best documented configuration (sanity of idesc / descriptors / fences / tmem)
-      {0, 32, 32, 16, 1024, 1024, 0, 0, 1, 2, "Kmajor A, K=32 (sanity)"},
-      {0, 256, 32, 16, 1024, 1024, 1, 0, 1, 2, "Kmajor A, N=256, B via bulk copy (sanity)"},
+      {0, 32, 32, 16, 1024, 1024, 0, 0, 1, 2, 2, "Kmajor A, K=32 (sanity)"},
+      {0, 256, 32, 16, 1024, 1024, 1, 0, 1, 2, 2, "Kmajor A, N=256, B via bulk copy (sanity)"},
       // MN-major tf32 A: SWIZZLE_128B_BASE32B candidates.  atoms 512 B; time-atoms adjacent (lbo 512), k-groups 2048
-      {1, 32, 8, 512, 2048, 1024, 0, 0, 1, 1, "MN A 32B-base, K=8, lbo=512 sbo=2048"},
-      {1, 32, 32, 512, 2048, 1024, 0, 0, 1, 1, "MN A 32B-base, K=32, lbo=512 sbo=2048"},
-      {1, 256, 32, 512, 2048, 1024, 1, 0, 1, 1, "MN A 32B-base, N=256 K=32 bulk B"},
+      {1, 32, 8, 512, 2048, 1024, 0, 0, 1, 1, 2, "MN A 32B-base, K=8, lbo=512 sbo=2048"},
+      {1, 32, 32, 512, 2048, 1024, 0, 0, 1, 1, 2, "MN A 32B-base, K=32, lbo=512 sbo=2048"},
+      {1, 256, 32, 512, 2048, 1024, 1, 0, 1, 1, 2, "MN A 32B-base, N=256 K=32 bulk B"},
       // same data layout but descriptor fields swapped (expected to fail if the reading above is right)
-      {1, 32, 8, 2048, 512, 1024, 0, 0, 1, 1, "MN A 32B-base, K=8, fields swapped"},
+      {1, 32, 8, 2048, 512, 1024, 0, 0, 1, 1, 2, "MN A 32B-base, K=8, fields swapped"},
       // alternative placement: k-groups adjacent (sbo 512), time atoms 4096 apart
-      {1, 32, 32, 4096, 512, 1024, 0, 0, 1, 1, "MN A 32B-base, K=32, lbo=4096 sbo=512"},
-      {1, 32, 8, 512, 2048, 1024, 0, 0, 0, 1, "MN A 32B-base, K=8, no swizzle staged"},
+      {1, 32, 32, 4096, 512, 1024, 0, 0, 1, 1, 2, "MN A 32B-base, K=32, lbo=4096 sbo=512"},
+      {1, 32, 8, 512, 2048, 1024, 0, 0, 0, 1, 2, "MN A 32B-base, K=8, no swizzle staged"},
+      // K-major B in SWIZZLE_64B (rows of 16 k = 64 B, 8-row groups of 512 B)
+      {1, 32, 16, 512, 2048, 512, 0, 0, 1, 1, 4, "MN A + B SW64, K=16, sbo_b=512"},
+      {1, 256, 16, 512, 2048, 512, 0, 0, 1, 1, 4, "MN A + B SW64, N=256 K=16"},
+      {0, 32, 16, 16, 1024, 512, 0, 0, 1, 2, 4, "K-major A SW128 + B SW64, K=16"},
   };
   int ok = 0;
   for (const Case& c : cases) ok += run_case(c);
