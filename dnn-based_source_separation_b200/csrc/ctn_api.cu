@@ -101,6 +101,8 @@ struct TcnWs {
   double* stats;  // [2*RX][B][2]
   std::vector<FoldedConv> folds;  // per block, (Bc+Sc) rows
   std::vector<float*> wimg1, wimg2;  // per block: tcgen05 weight images of the two pointwise convs (math != fp32)
+  std::vector<float*> rblk;          // per block: raw [out;skip] contraction output r_i (B, Bc+Sc, pitch), kept for the
+                                     // deferred skip reduction (the skip accumulator is written once, at the end)
   float *x, *skip, *h, *u, *outraw;
   size_t stats_bytes;
 };
@@ -109,7 +111,7 @@ static int check_tcn_cfg(const ctn_config_t* c) {
   if (!c) return CTN_EINVAL;
   if (c->bottleneck <= 0 || c->hidden <= 0 || c->skip <= 0 || c->sep_kernel <= 0 || c->num_blocks <= 0 || c->num_layers <= 0)
     return CTN_EINVAL;
-  if (c->num_layers > 20) return CTN_EUNSUPPORTED;
+  if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
   if (c->causal) return CTN_EUNSUPPORTED;  // cLN inside the fused path: not built yet (module-level ctn_cln_fwd exists)
   if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
   return CTN_OK;
@@ -137,7 +139,9 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
   ws->skip = cv.take<float>(bp * c->skip);
   ws->h = cv.take<float>(bp * c->hidden);
   ws->u = cv.take<float>(bp * c->hidden);
-  ws->outraw = cv.take<float>(bp * Mt);
+  ws->outraw = nullptr;
+  ws->rblk.assign(RX, nullptr);
+  for (int i = 0; i < RX; ++i) ws->rblk[i] = cv.take<float>(bp * Mt);
 }
 
 static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
@@ -190,7 +194,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
         // it straight to the tensor core; u never touches HBM.  r = [Wo;Ws] diag(gamma2) u
         StageTimer tm(CTN_ST_PW2, st);
         memset(&a, 0, sizeof(a));
-        a.A = ws->h; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+        a.A = ws->h; a.W = ws->folds[i].Wf; a.D = ws->rblk[i]; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
         a.wimg = ws->wimg2[i];
         a.pro_slope = p.prelu2; a.dw_norm_g = p.norm1_g; a.dw_norm_b = p.norm1_b; a.dw_w = p.dw_w; a.dw_b = p.dw_b;
         a.dw_stats_in = st1; a.dw_stats_out = st2; a.dw_dilation = dilation; a.dw_pad_left = pad_left; a.dw_eps = c->eps_tcn;
@@ -202,15 +206,28 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
                              c->sep_kernel, dilation, c->causal, c->eps_tcn, st)); }
         // K_C: r = [Wo;Ws] diag(gamma2) u
         memset(&a, 0, sizeof(a));
-        a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->outraw; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
+        a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->rblk[i]; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
         a.wimg = ws->wimg2[i];
         { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
       }
-      // K_F: residual / skip with deferred gLN2
-      { StageTimer tm(CTN_ST_FIN, st);
-        CTN_TRY(ctn_finish_fwd(ws->outraw, ws->folds[i], st2, (double)H * (double)frames, c->eps_tcn, ws->x, ws->skip, B, Bc,
-                               Sc, has_out ? 1 : 0, i == 0 ? 1 : 0, frames, pitch, st)); }
+      // K_F: residual update with the deferred gLN2 (x += rstd2*r[:Bc] + c); the skip rows are reduced once at the end
+      if (has_out) {
+        StageTimer tm(CTN_ST_FIN, st);
+        CTN_TRY(ctn_finish_fwd(ws->rblk[i], ws->folds[i], st2, (double)H * (double)frames, c->eps_tcn, ws->x, ws->skip, B, Bc,
+                               Sc, 1, 2 /* x rows only */, frames, pitch, st));
+      }
     }
+  }
+  {
+    StageTimer tm(CTN_ST_FIN, st);
+    SkipJobs sj;
+    sj.n = R * X;
+    for (int i = 0; i < R * X; ++i) {
+      const bool has_out = blocks[i].out_w != nullptr;
+      sj.j[i] = SkipJob{ws->rblk[i], ws->folds[i].v1, ws->folds[i].v2, ws->stats + (size_t)(2 * i + 1) * B * 2, has_out ? Bc : 0,
+                        has_out ? Bc + Sc : Sc};
+    }
+    CTN_TRY(ctn_skip_reduce(sj, (double)H * (double)frames, c->eps_tcn, ws->skip, B, Sc, frames, pitch, st));
   }
   return CTN_OK;
 }

@@ -74,5 +74,12 @@ int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_
 int ctn_finish_fwd(const float* outraw, const FoldedConv f, const double* stats2, double n2, float eps, float* x,
                    float* skip, int B, int Bc, int Sc, int has_out, int skip_init, int frames, int pitch, cudaStream_t st);
 
+// deferred skip reduction: skip[b][m][t] = sum_i ( rstd2_i[b] * r_i[b][off_i + m][t] + (v1_i[off_i+m] - mean_i rstd_i v2_i[off_i+m]) )
+// over all residual blocks i -- reads every block's skip rows ONCE instead of read-modify-writing the accumulator per block
+#define CTN_MAX_BLOCKS 64
+struct SkipJob { const float* r; const float* v1; const float* v2; const double* stats2; int off; int Mt; };
+struct SkipJobs { SkipJob j[CTN_MAX_BLOCKS]; int n; };
+int ctn_skip_reduce(const SkipJobs& jobs, double n2, float eps, float* skip, int B, int Sc, int frames, int pitch, cudaStream_t st);
+
 int ctn_copy_to_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);
 int ctn_copy_from_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);

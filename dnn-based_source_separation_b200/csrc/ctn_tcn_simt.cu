@@ -294,8 +294,39 @@ __global__ void __launch_bounds__(128) k_finish(const float* __restrict__ outraw
 int ctn_finish_fwd(const float* outraw, const FoldedConv f, const double* stats2, double n2, float eps, float* x,
                    float* skip, int B, int Bc, int Sc, int has_out, int skip_init, int frames, int pitch, cudaStream_t st) {
   const int Mtot = has_out ? Bc + Sc : Sc;
-  dim3 grid((pitch + 511) / 512, Mtot, B);
+  // skip_init == 2: residual rows only (the skip rows are handled by ctn_skip_reduce)
+  dim3 grid((pitch + 511) / 512, skip_init == 2 ? Bc : Mtot, B);
   k_finish<<<grid, 128, 0, st>>>(outraw, f.v1, f.v2, stats2, n2, eps, x, skip, Bc, Sc, has_out, skip_init, frames, pitch);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+// grid (pitch/512, Sc, B), block 128: thread = 4 consecutive frames of one skip channel, loops over the blocks
+__global__ void __launch_bounds__(128) k_skip_reduce(const SkipJobs jobs, double n2, float eps, float* __restrict__ skip, int Sc,
+                                                     int frames, int pitch) {
+  const int b = blockIdx.z, m = blockIdx.y;
+  const int t = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (t >= pitch) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int i = 0; i < jobs.n; ++i) {
+    const SkipJob& jb = jobs.j[i];
+    const float2 mr = gln_mean_rstd(jb.stats2 + 2 * b, n2, eps);
+    const float c = __ldg(jb.v1 + jb.off + m) - mr.x * mr.y * __ldg(jb.v2 + jb.off + m);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(jb.r + ((size_t)b * jb.Mt + jb.off + m) * pitch + t));
+    acc.x += fmaf(mr.y, r.x, c); acc.y += fmaf(mr.y, r.y, c); acc.z += fmaf(mr.y, r.z, c); acc.w += fmaf(mr.y, r.w, c);
+  }
+  if (t + 0 >= frames) acc.x = 0.f;
+  if (t + 1 >= frames) acc.y = 0.f;
+  if (t + 2 >= frames) acc.z = 0.f;
+  if (t + 3 >= frames) acc.w = 0.f;
+  *reinterpret_cast<float4*>(skip + ((size_t)b * Sc + m) * pitch + t) = acc;
+}
+
+int ctn_skip_reduce(const SkipJobs& jobs, double n2, float eps, float* skip, int B, int Sc, int frames, int pitch, cudaStream_t st) {
+  dim3 grid((pitch + 511) / 512, Sc, B);
+  k_skip_reduce<<<grid, 128, 0, st>>>(jobs, n2, eps, skip, Sc, frames, pitch);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;

@@ -70,9 +70,9 @@ def test_workspace_bytes_and_envelope():
     assert N.ctn_workspace_bytes(C.byref(c), 32, 32000, C.byref(need)) == 0
     b32 = need.value
     assert N.ctn_workspace_bytes(C.byref(c), 16, 32000, C.byref(need)) == 0
-    assert 0 < need.value < b32 < 4 << 30
-    # per-sample activations at pitch 4096: w(512)+what(1024)+x(128)+skip(128)+h(512)+u(512)+outraw(256) rows
-    rows = 512 + 1024 + 128 + 128 + 512 + 512 + 256
+    assert 0 < need.value < b32 < 8 << 30
+    # per-sample activations at pitch 4096: w(512)+what(1024)+x(128)+skip(128)+h(512)+u(512) rows + 24 blocks x r(256)
+    rows = 512 + 1024 + 128 + 128 + 512 + 512 + 24 * 256
     assert b32 >= 32 * rows * 4096 * 4
     for bad in (dict(causal=1), dict(mask_softmax=1)):
         cb = _cfg(**bad)
