@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
               if (g.dbg & 8u) break;
               const uint64_t da_hi = da_t | (uint64_t)(a_hi + kk * 256), dw_hi = dw_t | (uint64_t)(w_hi + kk * 2);
               ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
-              if (kk == 0 && prev_s >= 0) {
+              if (kk == 0 && prev_s >= 0 && g.cluster == 1) {
                 ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));  // previous slab's stage (its MMAs are queued ahead)
                 if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
               }
@@ -384,10 +384,10 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
               ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));
               if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
             }
-            if (ks == g.k_slabs - 1) {
-              ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // last slab of the item: free its stage right away
+            if (ks == g.k_slabs - 1 || g.cluster > 1) {
+              ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // last slab of the item (or cluster mode): free its stage right away
               if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[s]), (uint16_t)1u);
-              ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
+              if (ks == g.k_slabs - 1) ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
             }
           }
           __syncwarp();
