@@ -104,6 +104,7 @@ struct TcnWs {
   std::vector<float*> rblk;          // per block: raw [out;skip] contraction output r_i (B, Bc+Sc, pitch), kept for the
                                      // deferred skip reduction (the skip accumulator is written once, at the end)
   float *x, *skip, *h, *u, *outraw;
+  float* xalt;  // second residual-stream buffer (tcgen05 modes ping-pong x between blocks: the update is fused into pw1)
   size_t stats_bytes;
 };
 
@@ -136,6 +137,7 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
   }
   const size_t bp = (size_t)B * pitch;
   ws->x = cv.take<float>(bp * c->bottleneck);
+  ws->xalt = cv.take<float>(bp * c->bottleneck);
   ws->skip = cv.take<float>(bp * c->skip);
   ws->h = cv.take<float>(bp * c->hidden);
   ws->u = cv.take<float>(bp * c->hidden);
@@ -184,9 +186,25 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       // K_A: h = PReLU(W1 x + b1), stats1
       PwArgs a;
       memset(&a, 0, sizeof(a));
-      a.A = ws->x; a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
+      // tcgen05 modes: the residual stream ping-pongs between ws->x and ws->xalt; block i >= 1 applies block i-1's
+      // update x += rstd2*r[:Bc] + c inside its own producer (PRO_RES) -- no separate finishing pass over x
+      const bool fuse_res = c->math != CTN_MATH_FP32;
+      float* xbuf[2] = {ws->x, ws->xalt};
+      a.A = fuse_res ? xbuf[(i + 1) & 1] : ws->x;
+      if (fuse_res && i == 0) a.A = ws->x;
+      a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
       a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1; a.wimg = ws->wimg1[i];
-      { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_H, c->math, st)); }
+      int pro1 = PRO_NONE;
+      if (fuse_res && i > 0) {
+        // x_{i} = x_{i-1} + deferred gLN2 of block i-1;  x_{i-1} lives in xbuf[(i-1)&1], x_i goes to xbuf[i&1]
+        pro1 = PRO_RES;
+        a.A = xbuf[(i - 1) & 1];
+        a.res_r = ws->rblk[i - 1]; a.res_Mt = Bc + Sc;  // block i-1 always has the out head (only the last block lacks it)
+        a.res_v1 = ws->folds[i - 1].v1; a.res_v2 = ws->folds[i - 1].v2;
+        a.res_stats = ws->stats + (size_t)(2 * (i - 1) + 1) * B * 2; a.res_n = (double)H * (double)frames; a.res_eps = c->eps_tcn;
+        a.res_x_out = xbuf[i & 1];
+      }
+      { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, pro1, EPI_H, c->math, st)); }
       const int Mt = has_out ? Bc + Sc : Sc;
       const int pad_left = c->causal ? (c->sep_kernel - 1) * dilation : ((c->sep_kernel - 1) * dilation) / 2;
       if (c->math != CTN_MATH_FP32 && c->sep_kernel == 3) {
@@ -211,7 +229,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
         { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
       }
       // K_F: residual update with the deferred gLN2 (x += rstd2*r[:Bc] + c); the skip rows are reduced once at the end
-      if (has_out) {
+      if (has_out && c->math == CTN_MATH_FP32) {
         StageTimer tm(CTN_ST_FIN, st);
         CTN_TRY(ctn_finish_fwd(ws->rblk[i], ws->folds[i], st2, (double)H * (double)frames, c->eps_tcn, ws->x, ws->skip, B, Bc,
                                Sc, 1, 2 /* x rows only */, frames, pitch, st));

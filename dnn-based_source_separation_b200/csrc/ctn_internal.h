@@ -12,7 +12,7 @@ struct FoldedConv {
 };
 
 // epilogue / prologue selectors of the pointwise (1x1) contraction kernels
-enum { PRO_NONE = 0, PRO_PRELU = 1, PRO_DW = 2 };
+enum { PRO_NONE = 0, PRO_PRELU = 1, PRO_DW = 2, PRO_RES = 3 };
 enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3 };
 
 struct PwArgs {
@@ -43,6 +43,16 @@ struct PwArgs {
   const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
   int Nb;                  // EPI_MASK: n_basis
   float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)
+  // PRO_RES (tcgen05 path): the operand is the UPDATED residual stream  x_new = A + rstd*res_r[:K] + (v1 - mean*rstd*v2)
+  // (the deferred gLN2 of the previous block); CTAs with n-tile 0 also store x_new to res_x_out (ping-pong buffer).
+  const float* res_r;       // (B, res_Mt, pitch) raw [out;skip] contraction of the previous block; rows [0,K) are used
+  int res_Mt;
+  const float* res_v1;      // (>=K) folded bias vectors of the previous block
+  const float* res_v2;
+  const double* res_stats;  // (B,2) stats2 of the previous block
+  double res_n;
+  float res_eps;
+  float* res_x_out;         // (B, K, pitch)
   // tcgen05 path only
   const float* wimg;       // pre-swizzled hi/lo weight images (ctn_umma_build_wimg)
   uint32_t dbg_idesc, dbg_lbo_a, dbg_sbo_a, dbg_sbo_w;  // 0 = defaults (descriptor probing from the debug entry)

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     uint32_t ph = 0;
     // activation loads of slab (it2, ks2): issued ONE SLAB AHEAD of their use (register double buffer), across item
     // boundaries, so that the global-load latency overlaps the split/store work and the barrier waits
-    auto load_A = [&](int it2, int ks2, float4 (&dst)[CPW]) {
+    auto load_A = [&](int it2, int ks2, float4 (&dst)[CPW], float4 (&dstr)[CPW]) {
       int nt2, tt2, b2;
       const bool live2 = decode(it2, nt2, tt2, b2);
       const float* Ab2 = a.A + (size_t)b2 * a.K * a.pitch + (size_t)tt2 * TM + lane * 4;
@@ -230,9 +230,17 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         dst[j] = (k < a.K && live2 && !(g.dbg & 2u)) ? __ldg(reinterpret_cast<const float4*>(Ab2 + (size_t)k * a.pitch))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (PRO == PRO_RES) {
+        const float* Rb2 = a.res_r + (size_t)b2 * a.res_Mt * a.pitch + (size_t)tt2 * TM + lane * 4;
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          const int k = ks2 * KS + pw * CPW + j;
+          dstr[j] = (k < a.K && live2) ? __ldg(reinterpret_cast<const float4*>(Rb2 + (size_t)k * a.pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     };
-    float4 vnext[CPW];
-    if (PRO != PRO_DW && items_per_cta > 0) load_A(0, 0, vnext);
+    float4 vnext[CPW], rnext[CPW];
+    if (PRO != PRO_DW && items_per_cta > 0) load_A(0, 0, vnext, rnext);
     for (int it = 0; it < items_per_cta; ++it) {
       int nt, tt, b;
       const bool live = decode(it, nt, tt, b);
@@ -241,6 +249,8 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
       float2 mr1 = make_float2(0.f, 1.f);
       float2 dls = make_float2(0.f, 0.f), dlss = make_float2(0.f, 0.f);
       if (PRO == PRO_DW) mr1 = gln_mean_rstd(a.dw_stats_in + 2 * b, (double)a.K * (double)a.frames, a.dw_eps);
+      float2 mr_res = make_float2(0.f, 1.f);
+      if (PRO == PRO_RES) mr_res = gln_mean_rstd(a.res_stats + 2 * b, a.res_n, a.res_eps);
       const int tbase = tt * TM + lane * 4;  // first of this thread's 4 time steps
       int dcls = 4;
       bool dw_interior = false;
@@ -256,9 +266,30 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         if (PRO != PRO_DW) {
 #pragma unroll
           for (int j = 0; j < CPW; ++j) v[j] = vnext[j];
+          if (PRO == PRO_RES) {
+            // x_new = x + rstd2*r + (v1 - mean2*rstd2*v2): the previous block's residual update, applied on the fly;
+            // the n-tile-0 CTA of each time tile also writes x_new for the block after next
+#pragma unroll
+            for (int j = 0; j < CPW; ++j) {
+              const int k = ks * KS + pw * CPW + j;
+              const int kc = k < a.K ? k : a.K - 1;
+              const float cst = __ldg(a.res_v1 + kc) - mr_res.x * mr_res.y * __ldg(a.res_v2 + kc);
+              float4 xn;
+              xn.x = fmaf(mr_res.y, rnext[j].x, v[j].x + cst); xn.y = fmaf(mr_res.y, rnext[j].y, v[j].y + cst);
+              xn.z = fmaf(mr_res.y, rnext[j].z, v[j].z + cst); xn.w = fmaf(mr_res.y, rnext[j].w, v[j].w + cst);
+              if (tbase + 0 >= a.frames) xn.x = 0.f;
+              if (tbase + 1 >= a.frames) xn.y = 0.f;
+              if (tbase + 2 >= a.frames) xn.z = 0.f;
+              if (tbase + 3 >= a.frames) xn.w = 0.f;
+              if (k >= a.K || !live) xn = make_float4(0.f, 0.f, 0.f, 0.f);
+              v[j] = xn;
+              if (nt == 0 && live && k < a.K)
+                *reinterpret_cast<float4*>(a.res_x_out + ((size_t)b * a.K + k) * a.pitch + tbase) = xn;
+            }
+          }
           const int ks_n = ks + 1 < g.k_slabs ? ks + 1 : 0;
           const int it_n = ks + 1 < g.k_slabs ? it : it + 1;
-          if (it_n < items_per_cta) load_A(it_n, ks_n, vnext);
+          if (it_n < items_per_cta) load_A(it_n, ks_n, vnext, rnext);
         } else {
           // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside.
           // All 12 128-bit loads of the slab (4 channels x 3 taps) are issued before any arithmetic.  The branch below is
@@ -741,6 +772,7 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   UM_LAUNCH(PRO_DW, EPI_RAW)
   UM_LAUNCH(PRO_NONE, EPI_HEAD)
   UM_LAUNCH(PRO_NONE, EPI_H)
+  UM_LAUNCH(PRO_RES, EPI_H)
   UM_LAUNCH(PRO_PRELU, EPI_MASK)
 #undef UM_LAUNCH
   return CTN_EUNSUPPORTED;
