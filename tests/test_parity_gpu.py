@@ -189,6 +189,33 @@ def test_model_ragged_lengths_vs_oracle(mode, T):
 
 
 @pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape", [
+    dict(n_basis=24, kernel_size=8, sep_hidden_channels=40, sep_bottleneck_channels=20, sep_skip_channels=12,
+         sep_num_blocks=2, sep_num_layers=3, n_sources=2),                       # nothing is a multiple of 16/32
+    dict(n_basis=32, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=16, sep_skip_channels=16,
+         sep_kernel_size=5, sep_num_blocks=1, sep_num_layers=4, n_sources=2),     # P=5: un-fused depthwise stage
+    dict(n_basis=48, kernel_size=4, sep_hidden_channels=288, sep_bottleneck_channels=272, sep_skip_channels=24,
+         sep_num_blocks=1, sep_num_layers=2, n_sources=3),                       # > 256 output channels: several n-tiles
+    dict(n_basis=16, kernel_size=2, stride=1, sep_hidden_channels=32, sep_bottleneck_channels=16, sep_skip_channels=16,
+         sep_num_blocks=2, sep_num_layers=9, n_sources=2),                       # dilation 256 > 2 tiles; L=2, stride 1
+])
+def test_model_odd_shapes_vs_oracle(mode, shape):
+    cfg = O.OracleConfig(causal=False, **shape)
+    sd = O.synth_state_dict(cfg, seed=31)
+    model = build_model(cfg, sd, math=mode)
+    mixture, sources = O.synth_batch(2, cfg.n_sources, 777, seed=32)
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        ref_out, ref_lat = O.conv_tasnet_fwd(mixture, sd, cfg)
+        loss_b, perm = PIT1d(NegSISDR(), cfg.n_sources)(out, sources.cuda(), batch_mean=False)
+    torch.testing.assert_close(out.cpu(), ref_out, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), ref_lat, rtol=RTOL, atol=ATOL)
+    ref_l, ref_p = O.pit_neg_sisdr(ref_out, sources, batch_mean=False)
+    assert torch.equal(perm.cpu(), ref_p)
+    torch.testing.assert_close(loss_b.cpu(), ref_l, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_separator_vs_oracle(mode):
     cfg = O.OracleConfig(n_basis=40, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=24, sep_skip_channels=16,
                          sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=3)
