@@ -46,7 +46,7 @@ struct UmmaArgs {
   int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
   uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
   uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
-  int cluster, tiles_total, cluster_items, wsplit;  // CTAs per cluster sharing weight slabs by multicast; B*t_tiles; n_tiles*ceil(tiles/cluster)
+  int cluster, tiles_total, cluster_items, wsplit;  // 2 = CTA pair (cta_group::2 MMA, each CTA stages half of the weight slab); B*t_tiles; n_tiles*ceil(tiles/cluster)
   uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
 
@@ -63,7 +63,6 @@ struct __align__(8) SmemHeader {
   uint64_t empty[MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
-  uint64_t wempty[MAX_STAGES];  // cluster mode: on the leader CTA, "every CTA of the cluster has consumed weight stage s"
   uint32_t tmem_base;
 };
 
@@ -159,7 +158,9 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
   }
 }
 
-template <int PRO, int EPI, int NPASS>
+// PAIR: the kernel runs as clusters of 2 CTAs driving cta_group::2 MMAs.  It is a template parameter (not a run-time
+// flag) because a kernel that contains cta_group::2 instructions can only be launched with an even cluster size.
+template <int PRO, int EPI, int NPASS, bool PAIR>
 __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
   constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
   constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;  // epilogue warpgroups (each covers all 128 TMEM lanes)
@@ -173,31 +174,35 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
   const uint32_t stage0 = base + SMEM_HEADER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const PwArgs& a = g.a;
+  constexpr bool pair = PAIR;  // CTA pair: cta_group::2 MMA (M = 256), each CTA stages its time tile and HALF of the weights
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), PROD_WARPS + 1);
+      // pair mode: the peer's producers fill the PEER's full[s]; its relay warp forwards one arrival to the leader's
+      ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), PROD_WARPS + 1 + ((pair && ptx::cluster_ctarank() == 0) ? 1 : 0));
       ptx::mbar_init(ptx::smem_u32(&hdr->empty[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&hdr->wempty[s]), (uint32_t)g.cluster);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&hdr->tfull[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&hdr->tempty[i]), 128 * EGROUPS);
+      ptx::mbar_init(ptx::smem_u32(&hdr->tempty[i]), pair ? 2 * 4 * EGROUPS : 128 * EGROUPS);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 4) ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  if (warp == 4) {
+    if constexpr (pair) ptx::tmem_alloc2(ptx::smem_u32(&hdr->tmem_base), 512);
+    else ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
-  if (g.cluster > 1) ptx::cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
+  if (pair) ptx::cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
 
   // Work decomposition.  A cluster of C CTAs walks the same sequence of cluster items J = cidx + it * num_clusters;
   // J -> (weight tile nt = J % n_tiles, tile group J / n_tiles); CTA rank r of the cluster takes time tile
-  // L = group * C + r -> (b, tt).  All CTAs of a cluster therefore need the SAME weight slabs at the same step, which
-  // the leader multicasts once; ranks whose L falls off the end run a dummy item (no loads, no stores).
-  const int crank = g.cluster > 1 ? (int)ptx::cluster_ctarank() : 0;
+  // L = group * C + r -> (b, tt).  All CTAs of a cluster therefore need the SAME weight slabs at the same step, of which
+  // each CTA of a pair stages one half; ranks whose L falls off the end run a dummy item (no loads, no stores).
+  const int crank = pair ? (int)ptx::cluster_ctarank() : 0;
   const int cidx = (int)blockIdx.x / g.cluster, num_clusters = (int)gridDim.x / g.cluster;
   const int items_per_cta = (g.cluster_items - cidx + num_clusters - 1) / num_clusters;
   auto decode = [&](int it2, int& nt2, int& tt2, int& b2) -> bool {
@@ -318,20 +323,21 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           const uint32_t fb = ptx::smem_u32(&hdr->full[s]);
           if (g.dbg & 4u) {
             ptx::mbar_arrive(fb);
-          } else if (g.cluster == 1) {
+          } else if (!pair) {
             ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
             const uint32_t chunk = NPREC * g.w_bytes / (uint32_t)g.wsplit;  // several requests in flight per slab
             for (int c = 0; c < g.wsplit; ++c)
               ptx::bulk_g2s(st_base + NPREC * A_BYTES + c * chunk, wsrc + (size_t)ks * NPREC * g.w_bytes + (size_t)c * chunk, chunk, fb);
           } else {
-            // every CTA expects the slab on its own barrier; the leader waits until ALL CTAs of the cluster have consumed
-            // stage s, then one L2 read feeds every CTA (multicast bulk copy, same CTA-relative offsets)
-            ptx::mbar_arrive_expect_tx(fb, NPREC * g.w_bytes);
-            if (crank == 0) {
-              ptx::mbar_wait(ptx::smem_u32(&hdr->wempty[s]), ph ^ 1u);
-              ptx::bulk_g2s_multicast(st_base + NPREC * A_BYTES, wsrc + (size_t)ks * NPREC * g.w_bytes, NPREC * g.w_bytes, fb,
-                                      (uint16_t)((1u << g.cluster) - 1u));
-            }
+            // pair mode: this CTA stages rows [crank*n_tile/2, +n_tile/2) of the slab (a contiguous half of the hi image and
+            // of the lo image); the copy completes on this CTA's own full[s].
+            const uint32_t half = g.w_bytes / 2;
+            const uint32_t lb = fb;
+            ptx::mbar_arrive_expect_tx(lb, NPREC * half);
+            const uint8_t* src = wsrc + (size_t)ks * NPREC * g.w_bytes + (size_t)crank * half;
+#pragma unroll
+            for (int pr = 0; pr < NPREC; ++pr)
+              ptx::bulk_g2s(st_base + NPREC * A_BYTES + pr * half, src + (size_t)pr * g.w_bytes, half, lb);
           }
         }
 #pragma unroll
@@ -373,52 +379,56 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     // The whole warp walks the loop converged; one elected lane issues.  The stage-free commit of slab q is issued
     // AFTER the first MMA of slab q+1 (same item), so the tensor pipe always has work queued while the thread is busy
     // with the commit / barrier bookkeeping.
-    {
+    if (!pair || crank == 0) {  // pair mode: only the leader CTA issues (its MMAs span both CTAs' TMEM and smem)
       int s = 0;
       uint32_t ph = 0;
       const bool leader = ptx::elect_one();
+      const uint32_t w_lo_off = (pair ? g.w_bytes / 2 : g.w_bytes) >> 4;
       // descriptor templates: only the 14-bit start-address field changes
       const uint64_t da_t = ptx::make_smem_desc(0, g.lbo_a, g.sbo_a, 1);
       const uint64_t dw_t = ptx::make_smem_desc(0, g.lbo_w, g.sbo_w, W_LAYOUT);
       for (int it = 0; it < items_per_cta; ++it) {
         const int acc = it & 1;
-        ptx::mbar_wait(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        if (pair) ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        else ptx::mbar_wait(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         int prev_s = -1;
         for (int ks = 0; ks < g.k_slabs; ++ks) {
           const bool tl = (g.dbg & 128u) && blockIdx.x == 0 && lane == 0 && (it * g.k_slabs + ks) < 1024;
           if (tl) g_timeline[4096 + (it * g.k_slabs + ks) * 4 + 0] = gtime();
-          ptx::mbar_wait(ptx::smem_u32(&hdr->full[s]), ph);
+          if (pair) ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->full[s]), ph);
+          else ptx::mbar_wait(ptx::smem_u32(&hdr->full[s]), ph);
           if (tl) g_timeline[4096 + (it * g.k_slabs + ks) * 4 + 1] = gtime();
           ptx::tc_fence_after();
           const uint32_t st_base = stage0 + (uint32_t)s * g.stage_bytes;
           const uint32_t a_hi = st_base >> 4, a_lo = (st_base + A_BYTES) >> 4;
-          const uint32_t w_hi = (st_base + NPREC * A_BYTES) >> 4, w_lo = w_hi + (g.w_bytes >> 4);
+          const uint32_t w_hi = (st_base + NPREC * A_BYTES) >> 4, w_lo = w_hi + w_lo_off;
           if (leader) {
+            auto commit = [&](uint64_t* bar) {
+              if constexpr (pair) ptx::mma2_commit_multicast(ptx::smem_u32(bar), (uint16_t)3u);  // same barrier in both CTAs
+              else ptx::mma_commit(ptx::smem_u32(bar));
+            };
+            auto mma = [&](uint64_t da, uint64_t dw, uint32_t accum) {
+              if constexpr (pair) ptx::mma2_tf32(d_tmem, da, dw, g.idesc, accum);
+              else ptx::mma_tf32(d_tmem, da, dw, g.idesc, accum);
+            };
 #pragma unroll
             for (int kk = 0; kk < KS / 8; ++kk) {
               if (g.dbg & 8u) break;
               const uint64_t da_hi = da_t | (uint64_t)(a_hi + kk * 256), dw_hi = dw_t | (uint64_t)(w_hi + kk * 2);
-              ptx::mma_tf32(d_tmem, da_hi, dw_hi, g.idesc, (ks | kk) ? 1u : 0u);
-              if (kk == 0 && prev_s >= 0 && g.cluster == 1) {
-                ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));  // previous slab's stage (its MMAs are queued ahead)
-                if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
-              }
+              mma(da_hi, dw_hi, (ks | kk) ? 1u : 0u);
+              if (kk == 0 && prev_s >= 0) commit(&hdr->empty[prev_s]);  // previous slab's stage (its MMAs are queued ahead)
               if (NPASS == 3) {
                 const uint64_t da_lo = da_t | (uint64_t)(a_lo + kk * 256), dw_lo = dw_t | (uint64_t)(w_lo + kk * 2);
-                ptx::mma_tf32(d_tmem, da_lo, dw_hi, g.idesc, 1u);
-                ptx::mma_tf32(d_tmem, da_hi, dw_lo, g.idesc, 1u);
+                mma(da_lo, dw_hi, 1u);
+                mma(da_hi, dw_lo, 1u);
               }
             }
-            if ((g.dbg & 8u) && prev_s >= 0) {
-              ptx::mma_commit(ptx::smem_u32(&hdr->empty[prev_s]));
-              if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[prev_s]), (uint16_t)1u);
-            }
-            if (ks == g.k_slabs - 1 || g.cluster > 1) {
-              ptx::mma_commit(ptx::smem_u32(&hdr->empty[s]));  // last slab of the item (or cluster mode): free its stage right away
-              if (g.cluster > 1) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->wempty[s]), (uint16_t)1u);
-              if (ks == g.k_slabs - 1) ptx::mma_commit(ptx::smem_u32(&hdr->tfull[acc]));  // accumulator ready for the epilogue
+            if ((g.dbg & 8u) && prev_s >= 0) commit(&hdr->empty[prev_s]);
+            if (ks == g.k_slabs - 1) {
+              commit(&hdr->empty[s]);     // last slab of the item: free its stage right away
+              commit(&hdr->tfull[acc]);   // accumulator ready for the epilogue
             }
           }
           __syncwarp();
@@ -427,6 +437,20 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
       }
+    }
+    else {
+      // peer CTA of a pair: this warp has no MMAs to issue; it forwards "my stage s is full" (the peer's local full[s]:
+      // its producer warps + its half of the weight slab) to the leader's full[s] with ONE cluster-scope arrival per
+      // slab, which keeps remote arrivals and cluster-scope releases off the producers' path
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < items_per_cta; ++it)
+        for (int ks = 0; ks < g.k_slabs; ++ks) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->full[s]), ph);
+          if (lane == 0) ptx::mbar_arrive_remote(ptx::smem_u32(&hdr->full[s]), 0);
+          __syncwarp();
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
+        }
     }
     __syncwarp();
   } else {
@@ -551,7 +575,15 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         if (c0 + 16 < ncols) process(bufB, c0 + 16);
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+      if (pair) {  // one arrival per warp, on the LEADER's barrier (its MMA warp overwrites both CTAs' accumulators)
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+          else ptx::mbar_arrive_remote(ptx::smem_u32(&hdr->tempty[acc]), 0);
+        }
+      } else {
+        ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+      }
       if (tle) g_timeline[8192 + it * 4 + 2] = gtime();
       if (EPI == EPI_H) {
         double s = warp_sum_d((double)ls), ss = warp_sum_d((double)lss);
@@ -562,8 +594,11 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (g.cluster > 1) ptx::cluster_sync_all();  // nobody exits while a peer may still multicast into it / arrive on it
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, 512);
+  if (pair) ptx::cluster_sync_all();  // nobody exits while a peer may still multicast into it / arrive on it
+  if (warp == 4) {
+    if constexpr (pair) ptx::tmem_dealloc2(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---- weight images ---------------------------------------------------------------------------------------------
@@ -632,16 +667,16 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int PRO, int EPI, int NPASS>
+template <int PRO, int EPI, int NPASS, bool PAIR>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
   constexpr int NT = PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  if (g.cluster > 1) {
+  if (PAIR) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -650,15 +685,15 @@ int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = g.cluster;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_pw_umma<PRO, EPI, NPASS>, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_pw_umma<PRO, EPI, NPASS, PAIR>, g);
     if (e != cudaSuccess) return (int)e;
   } else {
-    k_pw_umma<PRO, EPI, NPASS><<<grid, NT, smem, st>>>(g);
+    k_pw_umma<PRO, EPI, NPASS, PAIR><<<grid, NT, smem, st>>>(g);
   }
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
@@ -731,43 +766,49 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   g.num_items = a.B * g.t_tiles * g.n_tiles;
   const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
   g.w_bytes = (uint32_t)g.n_tile * (uint32_t)(KS * 4);
-  g.stage_bytes = (uint32_t)nprec * (A_BYTES + g.w_bytes);
+  static const char* env_dbg = getenv("CTN_UMMA_DBG");
+  g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
+  int grid = num_sms();
+  static const char* env_grid = getenv("CTN_UMMA_GRID");
+  if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
+  // CTA pairs (cluster of 2, tcgen05 cta_group::2; opt-in with CTN_UMMA_CLUSTER=2): one MMA covers two time tiles
+  // (M = 256) and each CTA stages only HALF of the weight slab, so a stage shrinks from 96 KB to 64 KB (3xTF32, n_tile
+  // 256) and the ring gets 3 stages instead of 2.  Parity-green on B200, but measured perf-neutral on cfg2 (10.59 vs
+  // 10.56 ms/step): with MMA-only (3.9 ms) and producer-only (4.2 ms) floors this close, the third stage does not buy
+  // overlap yet, so the simpler 1-CTA kernel stays the default.
+  static const char* env_cl = getenv("CTN_UMMA_CLUSTER");
+  int cluster = env_cl ? atoi(env_cl) : 1;
+  if (cluster != 1 && cluster != 2) cluster = 1;
+  g.tiles_total = a.B * g.t_tiles;
+  static const char* env_pm = getenv("CTN_UMMA_PAIR_MIN_N");
+  const int pair_min_n = env_pm ? atoi(env_pm) : 64;  // N = 64 / 256 are the pair shapes pinned by tools/umma_unit2.cu
+  if (cluster == 2 && (grid % 2 != 0 || g.tiles_total < 2 || g.n_tile % 32 != 0 || g.n_tile < pair_min_n)) cluster = 1;
+  g.cluster = cluster;
+  const uint32_t w_stage = cluster == 2 ? g.w_bytes / 2 : g.w_bytes;
+  g.stage_bytes = (uint32_t)nprec * (A_BYTES + w_stage);
   const size_t budget = 227 * 1024 - SMEM_HEADER - 1024;
   int stages = (int)(budget / g.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   static const char* env_st = getenv("CTN_UMMA_STAGES");
   if (env_st && atoi(env_st) >= 1 && atoi(env_st) < stages) stages = atoi(env_st);
-  static const char* env_dbg = getenv("CTN_UMMA_DBG");
-  g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
   if (stages < 1) return CTN_EUNSUPPORTED;
   g.stages = stages;
-  g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
+  g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(cluster == 2 ? 2 * TM : TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
   g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
   g.sbo_a = a.dbg_sbo_a ? a.dbg_sbo_a : 2048u;  // between 4-channel groups
   g.lbo_w = 16u;                                 // unused for swizzled K-major
   g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : W_SBO;  // between 8-row (output channel) groups
   const size_t smem = SMEM_HEADER + 1024 + (size_t)stages * g.stage_bytes;
-  int grid = num_sms();
-  static const char* env_grid = getenv("CTN_UMMA_GRID");
-  if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
   static const char* env_ws = getenv("CTN_UMMA_WSPLIT");
   g.wsplit = env_ws ? atoi(env_ws) : 1;
   if (g.wsplit < 1 || g.wsplit > 16 || ((NPREC_HOST(math) * g.w_bytes / g.wsplit) % 16) != 0) g.wsplit = 1;
-  static const char* env_cl = getenv("CTN_UMMA_CLUSTER");
-  // cluster multicast of the weight slabs is EXPERIMENTAL (opt-in): it halves the L2 reads of the weights but measured no
-  // speed-up (the stage recycle latency, not L2 bandwidth, bounds the kernel) and the combination with the deferred
-  // stage commit currently fails parity; default is 1 CTA per cluster.
-  int cluster = env_cl ? atoi(env_cl) : 1;
-  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
-  g.tiles_total = a.B * g.t_tiles;
-  while (cluster > 1 && (grid % cluster != 0 || g.tiles_total < cluster)) cluster >>= 1;
-  g.cluster = cluster;
   g.cluster_items = g.n_tiles * ((g.tiles_total + cluster - 1) / cluster);
   const int max_grid = g.cluster_items * cluster;
   if (grid > max_grid) grid = max_grid;
 #define UM_LAUNCH(P, E)                                                                   \
   if (pro == P && epi == E)                                                               \
-    return nprec == 2 ? launch<P, E, 3>(g, smem, grid, st) : launch<P, E, 1>(g, smem, grid, st);
+    return nprec == 2 ? (cluster == 2 ? launch<P, E, 3, true>(g, smem, grid, st) : launch<P, E, 3, false>(g, smem, grid, st)) \
+                      : (cluster == 2 ? launch<P, E, 1, true>(g, smem, grid, st) : launch<P, E, 1, false>(g, smem, grid, st));
   UM_LAUNCH(PRO_NONE, EPI_RAW)
   UM_LAUNCH(PRO_DW, EPI_RAW)
   UM_LAUNCH(PRO_NONE, EPI_HEAD)
