@@ -276,3 +276,44 @@ extern "C" int ctn_sisdr_fwd(const float* est, const float* tgt, int rows, int T
   return CTN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward of PIT(NegSISDR) through the SELECTED permutation (pit.py:36-44: the indices carry no gradient).
+//   SI-SDR = k (ln P - ln Q),  P = alpha^2 |t|^2 + eps,  Q = |alpha t - x|^2 + eps,  alpha = <x,t> / (|t|^2 + eps)
+//   dSI-SDR/dx = k { [2 alpha tt / ((tt+eps) P)] t  -  [ (2 (alpha tt - xt)/(tt+eps) - 2 alpha) t + 2 x ] / Q }
+// The pair statistics <x,t>, |alpha t - x|^2, |t|^2 are the ones the forward left in its scratch (explicit residual,
+// double), so the backward is one streaming pass.  grid (chunks, B*S), block 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sisdr_pit_bwd(const float* __restrict__ est, const float* __restrict__ tgt,
+                                                       const int64_t* __restrict__ perm, const double* __restrict__ scratch,
+                                                       const float* __restrict__ gl, float coef, int S, int T, float eps,
+                                                       float* __restrict__ d_est) {
+  const int row = blockIdx.y, b = row / S, i = row % S;
+  const int j = (int)perm[(size_t)b * S + i];
+  const double* sc = scratch + (size_t)b * pit_scratch_per_sample(S);
+  const double xt = sc[i * S + j], den = sc[S * S + i * S + j], tt = sc[2 * S * S + j];
+  const double e = (double)eps;
+  const double alpha = xt / (tt + e), P = alpha * alpha * tt + e, Q = den + e;
+  const double k10 = 4.342944819032518;  // 10 / ln 10
+  const double g = (gl ? (double)gl[b] : 1.0) * (double)coef;
+  const float ct = (float)(g * k10 * (2.0 * alpha * tt / ((tt + e) * P) - (2.0 * (alpha * tt - xt) / (tt + e) - 2.0 * alpha) / Q));
+  const float cx = (float)(g * k10 * (-2.0 / Q));
+  const float* x = est + (size_t)row * T;
+  const float* t = tgt + ((size_t)b * S + j) * T;
+  float* d = d_est + (size_t)row * T;
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < T; k += gridDim.x * 256) d[k] = fmaf(ct, t[k], cx * x[k]);
+}
+
+extern "C" int ctn_sisdr_pit_bwd(const float* est, const float* tgt, const int64_t* perm, int B, int S, int T, float eps,
+                                 const double* fwd_scratch, const float* grad_loss_b, float coef, float* d_est,
+                                 ctn_stream_t stream) {
+  LaunchScope scope;
+  if (!est || !tgt || !perm || !fwd_scratch || !d_est || B <= 0 || T <= 0) return CTN_EINVAL;
+  if (S < 1 || S > CTN_MAX_S) return CTN_EUNSUPPORTED;
+  int gx = (T + 1023) / 1024;
+  if (gx > 64) gx = 64;
+  k_sisdr_pit_bwd<<<dim3(gx, B * S), 256, 0, (cudaStream_t)stream>>>(est, tgt, perm, fwd_scratch, grad_loss_b, coef, S, T, eps, d_est);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}

@@ -1,0 +1,853 @@
+// Training path of the Conv-TasNet hot path: a forward that keeps what the backward needs, and the backward itself
+// (gradients of all 343 parameter tensors), i.e. what `loss.backward()` does in the reference trainer
+// (egs/wsj0-mix/common/src/driver.py:146-150) for the modules of src/models/conv_tasnet.py, src/models/tdcn.py,
+// src/models/filterbank.py and src/modules/norm.py.
+//
+// Structure (first cut: correctness and full coverage; the dense contractions already run on the tcgen05 kernels):
+//   * every 1x1 convolution, forward or data-gradient (W^T dY), is ONE call of the pointwise contraction kernels of the
+//     inference path (ctn_pw_umma / ctn_pw_simt, raw epilogue) -- 3xTF32 on the tensor cores by default;
+//   * weight gradients dW = sum_{b,t} dY X^T reduce over B*frames (128 k at cfg2): a split-K FFMA kernel (k_wgrad,
+//     64x64 register-tiled, fp32 atomics across the splits);
+//   * everything between the contractions (bias, PReLU, gLN and their backward, dilated depthwise conv and its
+//     backward, residual / skip bookkeeping) are streaming kernels over the (B, C, pitch) layout, HBM-bound, with the
+//     per-sample gLN reductions accumulated in double.
+// Saved per residual block: its input x_i, the pre-activations h_pre = W1 x + b1 and u_pre = dwconv(gLN1(PReLU h_pre)) + bd,
+// and the two (sum, sumsq) statistics; normalised tensors are recomputed in the backward.
+#include <string.h>
+#include <vector>
+#include "ctn_internal.h"
+
+namespace {
+
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* b) : base((char*)b), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// ================================================================================================================
+// streaming kernels.  Layout (B, C, pitch); only columns t < frames carry data, pad columns are written as zero.
+// Unless noted: grid (min(C, 1024), B), block 256, a block walks channels c = blockIdx.x, += gridDim.x.
+// ================================================================================================================
+
+// y = y + bias[c] (in place) ; stats[b] += (sum, sumsq) of PReLU(y)          (tdcn.py:116-119 before the norm)
+__global__ void __launch_bounds__(256) k_bias_prelu_stats(float* __restrict__ y, const float* __restrict__ bias,
+                                                          const float* __restrict__ slope, double* __restrict__ stats, int C,
+                                                          int frames, int pitch) {
+  __shared__ double red[64];
+  const int b = blockIdx.y;
+  const float a = slope[0];
+  double s = 0.0, ss = 0.0;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    float* r = y + ((size_t)b * C + c) * pitch;
+    const float bc = bias[c];
+    float ls = 0.f, lss = 0.f;
+    for (int t = threadIdx.x; t < pitch; t += 256) {
+      float v = 0.f;
+      if (t < frames) {
+        v = r[t] + bc;
+        const float p = prelu_f(v, a);
+        ls += p;
+        lss = fmaf(p, p, lss);
+      }
+      r[t] = v;
+    }
+    s += ls;
+    ss += lss;
+  }
+  block_sum2_d(s, ss, red);
+  if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+}
+
+// u_pre[c][t] = sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c],  hn = gLN1(PReLU(h_pre)) inside [0,frames), 0 outside
+// (tdcn.py:120-130,181); stats2[b] += (sum, sumsq) of PReLU(u_pre; a2)
+__global__ void __launch_bounds__(256) k_dw_train_fwd(const float* __restrict__ hpre, float* __restrict__ upre,
+                                                      const float* __restrict__ g1, const float* __restrict__ b1,
+                                                      const float* __restrict__ wd, const float* __restrict__ bd,
+                                                      const float* __restrict__ slope1, const float* __restrict__ slope2,
+                                                      const double* __restrict__ stats1, double* __restrict__ stats2, int C,
+                                                      int frames, int pitch, int P, int dil, int pad_left, double n1, float eps) {
+  __shared__ double red[64];
+  const int b = blockIdx.y;
+  const float a1 = slope1[0], a2 = slope2[0];
+  const float2 mr = gln_mean_rstd(stats1 + 2 * b, n1, eps);
+  double s = 0.0, ss = 0.0;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const float* h = hpre + ((size_t)b * C + c) * pitch;
+    float* u = upre + ((size_t)b * C + c) * pitch;
+    const float gsc = g1[c] * mr.y, gsh = b1[c] - mr.x * mr.y * g1[c];
+    const float bc = bd[c];
+    float ls = 0.f, lss = 0.f;
+    for (int t = threadIdx.x; t < pitch; t += 256) {
+      float v = 0.f;
+      if (t < frames) {
+        float acc = bc;
+        for (int k = 0; k < P; ++k) {
+          const int tt = t + k * dil - pad_left;
+          if (tt >= 0 && tt < frames) acc = fmaf(wd[c * P + k], fmaf(gsc, prelu_f(h[tt], a1), gsh), acc);
+        }
+        v = acc;
+        const float p = prelu_f(v, a2);
+        ls += p;
+        lss = fmaf(p, p, lss);
+      }
+      u[t] = v;
+    }
+    s += ls;
+    ss += lss;
+  }
+  block_sum2_d(s, ss, red);
+  if (threadIdx.x == 0) { atomicAdd(&stats2[2 * b], s); atomicAdd(&stats2[2 * b + 1], ss); }
+}
+
+// y = gLN(act(pre)) : act = PReLU(slope) or identity (slope == nullptr)
+__global__ void __launch_bounds__(256) k_act_norm(const float* __restrict__ pre, float* __restrict__ y,
+                                                  const float* __restrict__ slope, const float* __restrict__ g,
+                                                  const float* __restrict__ bt, const double* __restrict__ stats, double n,
+                                                  float eps, int C, int frames, int pitch) {
+  const int b = blockIdx.y;
+  const float2 mr = gln_mean_rstd(stats + 2 * b, n, eps);
+  const bool act = slope != nullptr;
+  const float a = act ? slope[0] : 1.f;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const float* p = pre + ((size_t)b * C + c) * pitch;
+    float* o = y + ((size_t)b * C + c) * pitch;
+    const float gsc = g[c] * mr.y, gsh = bt[c] - mr.x * mr.y * g[c];
+    for (int t = threadIdx.x; t < pitch; t += 256) {
+      float v = 0.f;
+      if (t < frames) {
+        const float x = act ? prelu_f(p[t], a) : p[t];
+        v = fmaf(gsc, x, gsh);
+      }
+      o[t] = v;
+    }
+  }
+}
+
+// rows of r (B, Mt, pitch): m < Bc (has_out): x_out = x_in + r + bo[m] ; else skip (+)= r + bs[j]      (tdcn.py:144-145, :39)
+__global__ void __launch_bounds__(256) k_res_skip(const float* __restrict__ r, int Mt, const float* __restrict__ xin,
+                                                  float* __restrict__ xout, float* __restrict__ skip,
+                                                  const float* __restrict__ bo, const float* __restrict__ bs, int Bc, int Sc,
+                                                  int has_out, int skip_init, int frames, int pitch) {
+  const int b = blockIdx.y;
+  for (int m = blockIdx.x; m < Mt; m += gridDim.x) {
+    const float* rr = r + ((size_t)b * Mt + m) * pitch;
+    if (has_out && m < Bc) {
+      const float* xi = xin + ((size_t)b * Bc + m) * pitch;
+      float* xo = xout + ((size_t)b * Bc + m) * pitch;
+      const float bb = bo[m];
+      for (int t = threadIdx.x; t < pitch; t += 256) xo[t] = t < frames ? xi[t] + rr[t] + bb : 0.f;
+    } else {
+      const int j = m - (has_out ? Bc : 0);
+      float* sk = skip + ((size_t)b * Sc + j) * pitch;
+      const float bb = bs[j];
+      for (int t = threadIdx.x; t < pitch; t += 256) {
+        const float base = skip_init ? 0.f : sk[t];
+        sk[t] = t < frames ? base + rr[t] + bb : 0.f;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_transpose(const float* __restrict__ W, float* __restrict__ Wt, int M, int K) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < M * K) {
+    const int m = i / K, k = i - m * K;
+    Wt[(size_t)k * M + m] = W[i];
+  }
+}
+
+// dst[b][c][:] (+)= src[b][c][:] for c < C, with independent batch strides (row blocks of wider tensors)
+__global__ void __launch_bounds__(256) k_rows(float* __restrict__ dst, size_t dst_bs, const float* __restrict__ src,
+                                              size_t src_bs, int C, int accumulate, int frames, int pitch) {
+  const int b = blockIdx.y;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    float* d = dst + (size_t)b * dst_bs + (size_t)c * pitch;
+    const float* s = src + (size_t)b * src_bs + (size_t)c * pitch;
+    for (int t = threadIdx.x; t < pitch; t += 256) d[t] = t < frames ? (accumulate ? d[t] + s[t] : s[t]) : 0.f;
+  }
+}
+
+// out[c] += sum_{b,t} dy[b][c][t]   (bias gradients).  grid (C), block 256
+__global__ void __launch_bounds__(256) k_rowsum(const float* __restrict__ dy, size_t batch_stride, int B, int frames, int pitch,
+                                                float* __restrict__ out) {
+  __shared__ double red[64];
+  const int c = blockIdx.x;
+  double s = 0.0, z = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* r = dy + (size_t)b * batch_stride + (size_t)c * pitch;
+    float ls = 0.f;
+    for (int t = threadIdx.x; t < frames; t += 256) ls += r[t];
+    s += ls;
+  }
+  block_sum2_d(s, z, red);
+  if (threadIdx.x == 0) atomicAdd(&out[c], (float)s);
+}
+
+// ---- gLN backward, phase 1.  xhat = (act(pre) - mean) * rstd, g = gamma_c * dy:
+//   sums[b] += (sum g, sum g*xhat) ; dgamma[c] += sum dy*xhat ; dbeta[c] += sum dy         grid (C, B)
+__global__ void __launch_bounds__(256) k_gln_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ pre,
+                                                        const float* __restrict__ slope, const float* __restrict__ g,
+                                                        const double* __restrict__ stats, double n, float eps,
+                                                        double* __restrict__ sums, float* __restrict__ dgamma,
+                                                        float* __restrict__ dbeta, int C, int frames, int pitch) {
+  __shared__ double red[64];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float2 mr = gln_mean_rstd(stats + 2 * b, n, eps);
+  const bool act = slope != nullptr;
+  const float a = act ? slope[0] : 1.f;
+  const float* d = dy + ((size_t)b * C + c) * pitch;
+  const float* p = pre + ((size_t)b * C + c) * pitch;
+  float s0 = 0.f, s1 = 0.f;
+  for (int t = threadIdx.x; t < frames; t += 256) {
+    const float x = act ? prelu_f(p[t], a) : p[t];
+    const float xh = (x - mr.x) * mr.y;
+    s0 += d[t];
+    s1 = fmaf(d[t], xh, s1);
+  }
+  double ds0 = s0, ds1 = s1;
+  block_sum2_d(ds0, ds1, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&dbeta[c], (float)ds0);
+    atomicAdd(&dgamma[c], (float)ds1);
+    const double gc = (double)g[c];
+    atomicAdd(&sums[2 * b], gc * ds0);
+    atomicAdd(&sums[2 * b + 1], gc * ds1);
+  }
+}
+
+// ---- gLN backward, phase 2 (+ the PReLU in front of the norm, + the bias of the conv that produced `pre`):
+//   d_act = rstd * (g - mean(g) - xhat * mean(g*xhat))                       (GroupNorm(1,C) backward)
+//   d_pre = d_act * (pre > 0 ? 1 : a) ; dslope += sum_{pre<=0} d_act * pre   (PReLU backward, single shared slope)
+//   dbias[c] += sum d_pre.   dpre may alias dy.                               grid (C, B)
+__global__ void __launch_bounds__(256) k_gln_prelu_bwd_apply(const float* dy, const float* __restrict__ pre, float* dpre,
+                                                             const float* __restrict__ slope, const float* __restrict__ g,
+                                                             const double* __restrict__ stats, double n, float eps,
+                                                             const double* __restrict__ sums, float* __restrict__ dslope,
+                                                             float* __restrict__ dbias, int C, int frames, int pitch) {
+  __shared__ double red[64];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float2 mr = gln_mean_rstd(stats + 2 * b, n, eps);
+  const float mg = (float)(sums[2 * b] / n), mgx = (float)(sums[2 * b + 1] / n);
+  const bool act = slope != nullptr;
+  const float a = act ? slope[0] : 1.f;
+  const float gc = g[c];
+  const float* d = dy + ((size_t)b * C + c) * pitch;
+  const float* p = pre + ((size_t)b * C + c) * pitch;
+  float* o = dpre + ((size_t)b * C + c) * pitch;
+  float sa = 0.f, sb = 0.f;
+  for (int t = threadIdx.x; t < pitch; t += 256) {
+    float v = 0.f;
+    if (t < frames) {
+      const float pv = p[t];
+      const float x = act ? prelu_f(pv, a) : pv;
+      const float xh = (x - mr.x) * mr.y;
+      const float da = mr.y * (gc * d[t] - mg - xh * mgx);
+      if (act) {
+        v = pv > 0.f ? da : a * da;
+        if (!(pv > 0.f)) sa = fmaf(da, pv, sa);
+      } else {
+        v = da;
+      }
+      sb += v;
+    }
+    o[t] = v;
+  }
+  double dsa = sa, dsb = sb;
+  block_sum2_d(dsa, dsb, red);
+  if (threadIdx.x == 0) {
+    if (act && dslope) atomicAdd(dslope, (float)dsa);
+    if (dbias) atomicAdd(&dbias[c], (float)dsb);
+  }
+}
+
+// ---- depthwise conv backward (tdcn.py:181 with the padding of :123-130).  dU = d_u_pre (zero outside [0,frames)):
+//   d_hn[c][t] = sum_k wd[c][k] * dU[c][t - k*d + pl]
+//   dwd[c][k] += sum_{b,t} dU[c][t] * hn[c][t + k*d - pl],   hn = gLN1(PReLU(h_pre)) inside [0,frames), 0 outside
+// grid (C, B)
+#define CTN_MAX_P 8
+__global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre, const float* __restrict__ hpre,
+                                                float* __restrict__ dhn, const float* __restrict__ slope1,
+                                                const float* __restrict__ g1, const float* __restrict__ b1,
+                                                const double* __restrict__ stats1, double n1, float eps,
+                                                const float* __restrict__ wd, float* __restrict__ dwd, int C, int frames,
+                                                int pitch, int P, int dil, int pad_left) {
+  __shared__ double red[64];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float a1 = slope1[0];
+  const float2 mr = gln_mean_rstd(stats1 + 2 * b, n1, eps);
+  const float gsc = g1[c] * mr.y, gsh = b1[c] - mr.x * mr.y * g1[c];
+  const float* du = dupre + ((size_t)b * C + c) * pitch;
+  const float* h = hpre + ((size_t)b * C + c) * pitch;
+  float* o = dhn + ((size_t)b * C + c) * pitch;
+  float w[CTN_MAX_P], acc[CTN_MAX_P];
+#pragma unroll
+  for (int k = 0; k < CTN_MAX_P; ++k) { w[k] = k < P ? wd[c * P + k] : 0.f; acc[k] = 0.f; }
+  for (int t = threadIdx.x; t < pitch; t += 256) {
+    float v = 0.f;
+    if (t < frames) {
+      const float dut = du[t];
+#pragma unroll
+      for (int k = 0; k < CTN_MAX_P; ++k) {
+        if (k < P) {
+          const int ts = t - k * dil + pad_left;  // u[ts] read hn[t] through tap k
+          if (ts >= 0 && ts < frames) v = fmaf(w[k], du[ts], v);
+          const int th = t + k * dil - pad_left;  // u[t] read hn[th] through tap k
+          if (th >= 0 && th < frames) acc[k] = fmaf(dut, fmaf(gsc, prelu_f(h[th], a1), gsh), acc[k]);
+        }
+      }
+    }
+    o[t] = v;
+  }
+  for (int k = 0; k < P; k += 2) {
+    double x0 = acc[k], x1 = (k + 1 < P) ? acc[k + 1] : 0.0;
+    block_sum2_d(x0, x1, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&dwd[c * P + k], (float)x0);
+      if (k + 1 < P) atomicAdd(&dwd[c * P + k + 1], (float)x1);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- mask head backward (conv_tasnet.py:158-160 and the sigmoid of :375):  w_hat[s] = w * mask[s]
+//   d_wprod[b][n][t] = sum_s d_what[b][s][n][t] * mask[b][s][n][t]
+//   d_mpre = d_what * w * mask * (1 - mask)      (in place over d_what)                      grid (N, B)
+__global__ void __launch_bounds__(256) k_mask_bwd(float* __restrict__ dwhat, const float* __restrict__ w,
+                                                  const float* __restrict__ mask, float* __restrict__ dwprod, int S, int N,
+                                                  int frames, int pitch) {
+  const int b = blockIdx.y;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const float* wr = w + ((size_t)b * N + n) * pitch;
+    float* dp = dwprod + ((size_t)b * N + n) * pitch;
+    for (int t = threadIdx.x; t < pitch; t += 256) {
+      float acc = 0.f;
+      const float wv = t < frames ? wr[t] : 0.f;
+      for (int s = 0; s < S; ++s) {
+        const size_t idx = (((size_t)b * S + s) * N + n) * pitch + t;
+        float v = 0.f;
+        if (t < frames) {
+          const float d = dwhat[idx], m = mask[idx];
+          acc = fmaf(d, m, acc);
+          v = d * wv * m * (1.f - m);
+        }
+        dwhat[idx] = v;
+      }
+      dp[t] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_prelu_apply(const float* __restrict__ x, float* __restrict__ y,
+                                                     const float* __restrict__ slope, int C, int frames, int pitch) {
+  const int b = blockIdx.y;
+  const float a = slope[0];
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const float* p = x + ((size_t)b * C + c) * pitch;
+    float* o = y + ((size_t)b * C + c) * pitch;
+    for (int t = threadIdx.x; t < pitch; t += 256) o[t] = t < frames ? prelu_f(p[t], a) : 0.f;
+  }
+}
+
+// d_pre = dy * (pre > 0 ? 1 : a) ; dslope += sum_{pre<=0} dy*pre.  dpre may alias dy.  grid (C, B)
+__global__ void __launch_bounds__(256) k_prelu_bwd(const float* dy, const float* __restrict__ pre, float* dpre,
+                                                   const float* __restrict__ slope, float* __restrict__ dslope, int C,
+                                                   int frames, int pitch) {
+  __shared__ double red[64];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float a = slope[0];
+  const float* d = dy + ((size_t)b * C + c) * pitch;
+  const float* p = pre + ((size_t)b * C + c) * pitch;
+  float* o = dpre + ((size_t)b * C + c) * pitch;
+  float sa = 0.f;
+  for (int t = threadIdx.x; t < pitch; t += 256) {
+    float v = 0.f;
+    if (t < frames) {
+      const float pv = p[t], dv = d[t];
+      v = pv > 0.f ? dv : a * dv;
+      if (!(pv > 0.f)) sa = fmaf(dv, pv, sa);
+    }
+    o[t] = v;
+  }
+  double dsa = sa, z = 0.0;
+  block_sum2_d(dsa, z, red);
+  if (threadIdx.x == 0) atomicAdd(dslope, (float)dsa);
+}
+
+// d_w = d_wnorm + d_wprod, times (w > 0) when the encoder has a ReLU (filterbank.py:225-226)
+__global__ void __launch_bounds__(256) k_dw_combine(float* __restrict__ dw, const float* __restrict__ dwprod,
+                                                    const float* __restrict__ w, int relu, int C, int frames, int pitch) {
+  const int b = blockIdx.y;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const size_t base = ((size_t)b * C + c) * pitch;
+    for (int t = threadIdx.x; t < pitch; t += 256) {
+      float v = 0.f;
+      if (t < frames) {
+        v = dw[base + t] + dwprod[base + t];
+        if (relu && !(w[base + t] > 0.f)) v = 0.f;
+      }
+      dw[base + t] = v;
+    }
+  }
+}
+
+// ---- filter-bank weight gradients: dW[n][k] += sum_{r,f} act[r][n][f] * sig[r][f*stride + k - pl]
+// (encoder: act = d_w, sig = mixture, filterbank.py:212,222; decoder: act = w_hat, sig = d_out, filterbank.py:243).
+// grid (L, N), block 256
+__global__ void __launch_bounds__(256) k_encdec_wgrad(const float* __restrict__ act, const float* __restrict__ sig,
+                                                      float* __restrict__ dW, int R, int N, int frames, int pitch, int T, int L,
+                                                      int stride, int pad_left) {
+  __shared__ double red[64];
+  const int k = blockIdx.x, n = blockIdx.y;
+  double s = 0.0, z = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const float* a = act + ((size_t)r * N + n) * pitch;
+    const float* sg = sig + (size_t)r * T;
+    float ls = 0.f;
+    for (int f = threadIdx.x; f < frames; f += 256) {
+      const int t = f * stride + k - pad_left;
+      if (t >= 0 && t < T) ls = fmaf(a[f], sg[t], ls);
+    }
+    s += ls;
+  }
+  block_sum2_d(s, z, red);
+  if (threadIdx.x == 0) atomicAdd(&dW[n * L + k], (float)s);
+}
+
+// ---- weight gradient of a 1x1 conv: dW[m][k] += sum_{b, t<frames} dY[b][m][t] * X[b][k][t]
+// 64x64 output tile per CTA, 256 threads x (4x4) accumulators, time in chunks of 32 staged TRANSPOSED in shared memory so
+// that the inner product reads two conflict-free 128-bit vectors per step; grid (tiles_m*tiles_k, splits): each CTA
+// reduces its share of the B*ceil(frames/32) chunks and adds its partial tile with fp32 atomics.
+#define WG_T 32
+__global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ dy, size_t dy_bs, const float* __restrict__ x,
+                                               size_t x_bs, float* __restrict__ dW, int M, int K, int B, int frames, int pitch,
+                                               int units_per_cta) {
+  __shared__ __align__(16) float sdy[WG_T][68];
+  __shared__ __align__(16) float sx[WG_T][68];
+  const int tiles_k = (K + 63) / 64;
+  const int m0 = ((int)blockIdx.x / tiles_k) * 64, k0 = ((int)blockIdx.x % tiles_k) * 64;
+  const int chunks = (frames + WG_T - 1) / WG_T;
+  const long long total = (long long)B * chunks;
+  const long long u0 = (long long)blockIdx.y * units_per_cta;
+  const long long u1 = u0 + units_per_cta < total ? u0 + units_per_cta : total;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lrow = threadIdx.x >> 2, lt = (threadIdx.x & 3) * 8;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long u = u0; u < u1; ++u) {
+    const int b = (int)(u / chunks), t0 = (int)(u % chunks) * WG_T;
+    float vy[8], vx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { vy[j] = 0.f; vx[j] = 0.f; }
+    if (m0 + lrow < M) {
+      const float4* p = reinterpret_cast<const float4*>(dy + (size_t)b * dy_bs + (size_t)(m0 + lrow) * pitch + t0 + lt);
+      const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+      vy[0] = q0.x; vy[1] = q0.y; vy[2] = q0.z; vy[3] = q0.w; vy[4] = q1.x; vy[5] = q1.y; vy[6] = q1.z; vy[7] = q1.w;
+    }
+    if (k0 + lrow < K) {
+      const float4* p = reinterpret_cast<const float4*>(x + (size_t)b * x_bs + (size_t)(k0 + lrow) * pitch + t0 + lt);
+      const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+      vx[0] = q0.x; vx[1] = q0.y; vx[2] = q0.z; vx[3] = q0.w; vx[4] = q1.x; vx[5] = q1.y; vx[6] = q1.z; vx[7] = q1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = t0 + lt + j < frames;  // pad columns never contribute
+      sdy[lt + j][lrow] = ok ? vy[j] : 0.f;
+      sx[lt + j][lrow] = ok ? vx[j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int tt = 0; tt < WG_T; ++tt) {
+      const float4 a = *reinterpret_cast<const float4*>(&sdy[tt][ty * 4]);
+      const float4 c = *reinterpret_cast<const float4*>(&sx[tt][tx * 4]);
+      acc[0][0] = fmaf(a.x, c.x, acc[0][0]); acc[0][1] = fmaf(a.x, c.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, c.z, acc[0][2]); acc[0][3] = fmaf(a.x, c.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, c.x, acc[1][0]); acc[1][1] = fmaf(a.y, c.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, c.z, acc[1][2]); acc[1][3] = fmaf(a.y, c.w, acc[1][3]);
+      acc[2][0] = fmaf(a.z, c.x, acc[2][0]); acc[2][1] = fmaf(a.z, c.y, acc[2][1]);
+      acc[2][2] = fmaf(a.z, c.z, acc[2][2]); acc[2][3] = fmaf(a.z, c.w, acc[2][3]);
+      acc[3][0] = fmaf(a.w, c.x, acc[3][0]); acc[3][1] = fmaf(a.w, c.y, acc[3][1]);
+      acc[3][2] = fmaf(a.w, c.z, acc[3][2]); acc[3][3] = fmaf(a.w, c.w, acc[3][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, k = k0 + tx * 4 + j;
+      if (m < M && k < K) atomicAdd(&dW[(size_t)m * K + k], acc[i][j]);
+    }
+}
+
+// ================================================================================================================
+// host side
+// ================================================================================================================
+inline dim3 grid_cb(int C, int B) { return dim3(C < 1024 ? C : 1024, B); }
+
+#define LAUNCH_CHECK()      \
+  do {                      \
+    CTN_COUNT_LAUNCH();     \
+    CTN_RETURN_IF_CUDA_ERR(); \
+  } while (0)
+
+struct TrainWs {
+  // ---- saved by the forward
+  float *w, *mask, *what, *skip;
+  double *stats0, *stats;  // stats: [2*RX][B][2]
+  std::vector<float*> x, hpre, upre;
+  // ---- scratch (forward and backward)
+  FoldedConv head;
+  float *wimg, *Wcat, *Wt;
+  float *T1, *G1, *G2;      // (B, H, pitch)
+  float *r;                 // (B, Bc+Sc, pitch)
+  float *dcat, *dS, *dxtmp; // (B, Bc+Sc, pitch), (B, Sc, pitch), (B, Bc, pitch)
+  float *dwhat;             // (B, S*N, pitch)
+  float *nA, *nB, *nC;      // (B, N, pitch): wn, d_wn, d_wprod
+  float *sp, *dsp;          // (B, Sc, pitch)
+  double* sums;             // (B, 2)
+  size_t stats_bytes;
+};
+
+size_t max_wimg_bytes(const ctn_config_t* c) {
+  if (c->math == CTN_MATH_FP32) return 256;
+  const int N = c->n_basis, Bc = c->bottleneck, H = c->hidden, Sc = c->skip, SN = c->n_sources * c->n_basis;
+  const int shapes[][2] = {{H, Bc}, {Bc + Sc, H}, {H, Bc + Sc}, {Bc, H}, {Bc, N}, {N, Bc}, {SN, Sc}, {Sc, SN}};
+  size_t mx = 0;
+  for (auto& s : shapes) {
+    const size_t b = ctn_umma_wimg_bytes(s[0], s[1], c->math);
+    if (b > mx) mx = b;
+  }
+  return mx;
+}
+
+void carve_train(Carver& cv, const ctn_config_t* c, int B, int pitch, TrainWs* ws) {
+  const int RX = c->num_blocks * c->num_layers;
+  const int N = c->n_basis, Bc = c->bottleneck, H = c->hidden, Sc = c->skip, S = c->n_sources;
+  const size_t bp = (size_t)B * pitch;
+  ws->stats0 = cv.take<double>((size_t)B * 2);
+  ws->stats_bytes = sizeof(double) * 2 * RX * B * 2;
+  ws->stats = cv.take<double>((size_t)2 * RX * B * 2);
+  ws->sums = cv.take<double>((size_t)B * 2);
+  ws->w = cv.take<float>(bp * N);
+  ws->mask = cv.take<float>(bp * N * S);
+  ws->what = cv.take<float>(bp * N * S);
+  ws->skip = cv.take<float>(bp * Sc);
+  ws->x.assign(RX, nullptr);
+  ws->hpre.assign(RX, nullptr);
+  ws->upre.assign(RX, nullptr);
+  for (int i = 0; i < RX; ++i) {
+    ws->x[i] = cv.take<float>(bp * Bc);
+    ws->hpre[i] = cv.take<float>(bp * H);
+    ws->upre[i] = cv.take<float>(bp * H);
+  }
+  ws->head.Wf = cv.take<float>((size_t)Bc * N);
+  ws->head.v1 = cv.take<float>(Bc);
+  ws->head.v2 = cv.take<float>(Bc);
+  ws->wimg = cv.take<float>(max_wimg_bytes(c) / sizeof(float));
+  size_t wmax = (size_t)(Bc + Sc) * H;
+  if ((size_t)S * N * Sc > wmax) wmax = (size_t)S * N * Sc;
+  if ((size_t)Bc * N > wmax) wmax = (size_t)Bc * N;
+  ws->Wcat = cv.take<float>(wmax);
+  ws->Wt = cv.take<float>(wmax);
+  ws->T1 = cv.take<float>(bp * H);
+  ws->G1 = cv.take<float>(bp * H);
+  ws->G2 = cv.take<float>(bp * H);
+  ws->r = cv.take<float>(bp * (Bc + Sc));
+  ws->dcat = cv.take<float>(bp * (Bc + Sc));
+  ws->dS = cv.take<float>(bp * Sc);
+  ws->dxtmp = cv.take<float>(bp * Bc);
+  ws->dwhat = cv.take<float>(bp * N * S);
+  ws->nA = cv.take<float>(bp * N);
+  ws->nB = cv.take<float>(bp * N);
+  ws->nC = cv.take<float>(bp * N);
+  ws->sp = cv.take<float>(bp * Sc);
+  ws->dsp = cv.take<float>(bp * Sc);
+}
+
+int check_train_cfg(const ctn_config_t* c) {
+  if (!c) return CTN_EINVAL;
+  if (c->n_basis <= 0 || c->kernel_size <= 0 || c->stride <= 0 || c->n_sources <= 0 || c->bottleneck <= 0 || c->hidden <= 0 ||
+      c->skip <= 0 || c->sep_kernel <= 0 || c->num_blocks <= 0 || c->num_layers <= 0)
+    return CTN_EINVAL;
+  if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
+  if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
+  if (c->causal || c->mask_softmax || c->sep_kernel > CTN_MAX_P) return CTN_EUNSUPPORTED;
+  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
+  return CTN_OK;
+}
+
+// D (B, M, pitch) = W (M, K) . A (B, K, pitch), raw epilogue, in the configured numeric mode
+int gemm_raw(const ctn_config_t* c, TrainWs& ws, const float* W, int M, int K, const float* A, float* D, int B, int frames,
+             int pitch, cudaStream_t st) {
+  PwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.W = W; a.D = D; a.B = B; a.M = M; a.K = K; a.frames = frames; a.pitch = pitch;
+  if (c->math == CTN_MATH_FP32) return ctn_pw_simt(a, PRO_NONE, EPI_RAW, st);
+  CTN_TRY(ctn_umma_build_wimg(W, M, K, c->math, ws.wimg, st));
+  a.wimg = ws.wimg;
+  return ctn_pw_umma(a, PRO_NONE, EPI_RAW, c->math, st);
+}
+
+int transpose(const float* W, float* Wt, int M, int K, cudaStream_t st) {
+  k_transpose<<<(M * K + 255) / 256, 256, 0, st>>>(W, Wt, M, K);
+  LAUNCH_CHECK();
+  return CTN_OK;
+}
+
+int wgrad(const float* dy, size_t dy_bs, const float* x, size_t x_bs, float* dW, int M, int K, int B, int frames, int pitch,
+          cudaStream_t st) {
+  const int tiles = ((M + 63) / 64) * ((K + 63) / 64);
+  const long long total = (long long)B * ((frames + WG_T - 1) / WG_T);
+  long long splits = (4 * 148 + tiles - 1) / tiles;
+  if (splits > total) splits = total;
+  if (splits < 1) splits = 1;
+  const int upc = (int)((total + splits - 1) / splits);
+  splits = (total + upc - 1) / upc;
+  k_wgrad<<<dim3(tiles, (unsigned)splits), 256, 0, st>>>(dy, dy_bs, x, x_bs, dW, M, K, B, frames, pitch, upc);
+  LAUNCH_CHECK();
+  return CTN_OK;
+}
+
+int rowsum(const float* dy, size_t bs, int C, int B, int frames, int pitch, float* out, cudaStream_t st) {
+  k_rowsum<<<C, 256, 0, st>>>(dy, bs, B, frames, pitch, out);
+  LAUNCH_CHECK();
+  return CTN_OK;
+}
+
+// gLN (+ optional PReLU in front) backward: dy (B,C,pitch) -> dpre (may alias dy); accumulates dgamma, dbeta, dslope, dbias
+int gln_prelu_bwd(const float* dy, const float* pre, float* dpre, const float* slope, const float* g, const double* stats,
+                  double n, float eps, double* sums, float* dgamma, float* dbeta, float* dslope, float* dbias, int B, int C,
+                  int frames, int pitch, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  k_gln_bwd_reduce<<<dim3(C, B), 256, 0, st>>>(dy, pre, slope, g, stats, n, eps, sums, dgamma, dbeta, C, frames, pitch);
+  LAUNCH_CHECK();
+  k_gln_prelu_bwd_apply<<<dim3(C, B), 256, 0, st>>>(dy, pre, dpre, slope, g, stats, n, eps, sums, dslope, dbias, C, frames, pitch);
+  LAUNCH_CHECK();
+  return CTN_OK;
+}
+
+}  // namespace
+
+extern "C" int ctn_train_workspace_bytes(const ctn_config_t* cfg, int batch, int T, size_t* bytes) {
+  CTN_TRY(check_train_cfg(cfg));
+  if (batch <= 0 || !bytes) return CTN_EINVAL;
+  const int frames = ctn_frames(T, cfg->kernel_size, cfg->stride, nullptr, nullptr);
+  if (frames <= 0) return CTN_EINVAL;
+  Carver cv(nullptr);
+  TrainWs ws;
+  carve_train(cv, cfg, batch, ctn_pitch(frames), &ws);
+  *bytes = cv.off + 256;
+  return CTN_OK;
+}
+
+extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_t* p, const float* x, int B, int T, float* out,
+                                        void* train_ws, size_t train_ws_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  CTN_TRY(check_train_cfg(c));
+  if (!p || !p->blocks || !x || !out || !train_ws || B <= 0 || T <= 0) return CTN_EINVAL;
+  if (((uintptr_t)train_ws) & 255) return CTN_EALIGN;
+  size_t need = 0;
+  CTN_TRY(ctn_train_workspace_bytes(c, B, T, &need));
+  if (train_ws_bytes < need) return CTN_EWORKSPACE;
+  int pl = 0, pr = 0;
+  const int frames = ctn_frames(T, c->kernel_size, c->stride, &pl, &pr);
+  const int pitch = ctn_pitch(frames);
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(train_ws);
+  TrainWs ws;
+  carve_train(cv, c, B, pitch, &ws);
+  const int N = c->n_basis, Bc = c->bottleneck, H = c->hidden, Sc = c->skip, S = c->n_sources, R = c->num_blocks, X = c->num_layers;
+  cudaError_t e = cudaMemsetAsync(ws.stats0, 0, sizeof(double) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(ws.stats, 0, ws.stats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  // encoder + gLN0 statistics (filterbank.py:222-229)
+  CTN_TRY(ctn_encoder_fwd(x, p->enc_w, ws.w, B, T, pl, pr, N, c->kernel_size, c->stride, c->enc_relu, pitch, ws.stats0, stream));
+  // head: x_0 = Wb gLN0(w) + bb (conv_tasnet.py:370-371), gLN0 folded into the contraction like the inference path
+  {
+    CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws.head, 0, st));
+    PwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws.w; a.W = ws.head.Wf; a.D = ws.x[0]; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
+    a.v1 = ws.head.v1; a.v2 = ws.head.v2; a.stats_in = ws.stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
+    if (c->math == CTN_MATH_FP32) {
+      CTN_TRY(ctn_pw_simt(a, PRO_NONE, EPI_HEAD, st));
+    } else {
+      CTN_TRY(ctn_umma_build_wimg(ws.head.Wf, Bc, N, c->math, ws.wimg, st));
+      a.wimg = ws.wimg;
+      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_HEAD, c->math, st));
+    }
+  }
+  const double nH = (double)H * (double)frames;
+  for (int i = 0; i < R * X; ++i) {
+    const ctn_block_params_t& q = p->blocks[i];
+    const bool has_out = q.out_w != nullptr;
+    if (!has_out && i != R * X - 1) return CTN_EINVAL;
+    const int dil = 1 << (i % X);
+    const int pad_left = ((c->sep_kernel - 1) * dil) / 2;
+    double* st1 = ws.stats + (size_t)(2 * i) * B * 2;
+    double* st2 = ws.stats + (size_t)(2 * i + 1) * B * 2;
+    // h_pre = W1 x + b1 ; stats1 of PReLU(h_pre)
+    CTN_TRY(gemm_raw(c, ws, q.bottleneck_w, H, Bc, ws.x[i], ws.hpre[i], B, frames, pitch, st));
+    k_bias_prelu_stats<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], q.bottleneck_b, q.prelu1, st1, H, frames, pitch);
+    LAUNCH_CHECK();
+    // u_pre = dwconv(gLN1(PReLU(h_pre))) + bd ; stats2 of PReLU(u_pre)
+    k_dw_train_fwd<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], ws.upre[i], q.norm1_g, q.norm1_b, q.dw_w, q.dw_b, q.prelu1, q.prelu2,
+                                                  st1, st2, H, frames, pitch, c->sep_kernel, dil, pad_left, nH, c->eps_tcn);
+    LAUNCH_CHECK();
+    // un = gLN2(PReLU(u_pre)) ; r = [Wo; Ws] un
+    k_act_norm<<<grid_cb(H, B), 256, 0, st>>>(ws.upre[i], ws.T1, q.prelu2, q.norm2_g, q.norm2_b, st2, nH, c->eps_tcn, H, frames, pitch);
+    LAUNCH_CHECK();
+    const int Mt = has_out ? Bc + Sc : Sc;
+    if (has_out) {
+      if ((e = cudaMemcpyAsync(ws.Wcat, q.out_w, sizeof(float) * (size_t)Bc * H, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return (int)e;
+    }
+    if ((e = cudaMemcpyAsync(ws.Wcat + (has_out ? (size_t)Bc * H : 0), q.skip_w, sizeof(float) * (size_t)Sc * H, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return (int)e;
+    CTN_TRY(gemm_raw(c, ws, ws.Wcat, Mt, H, ws.T1, ws.r, B, frames, pitch, st));
+    // x_{i+1} = x_i + out + bo ; skip += skip_i + bs
+    k_res_skip<<<grid_cb(Mt, B), 256, 0, st>>>(ws.r, Mt, ws.x[i], has_out ? ws.x[i + 1] : nullptr, ws.skip, q.out_b, q.skip_b, Bc, Sc,
+                                               has_out ? 1 : 0, i == 0 ? 1 : 0, frames, pitch);
+    LAUNCH_CHECK();
+  }
+  // tail: PReLU -> mask 1x1 -> sigmoid -> * w (conv_tasnet.py:373-376, 158-160); keeps the mask
+  {
+    PwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws.skip; a.W = p->mask_w; a.D = ws.what; a.B = B; a.M = S * N; a.K = Sc; a.frames = frames; a.pitch = pitch;
+    a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws.w; a.Nb = N; a.mask_out = ws.mask;
+    if (c->math == CTN_MATH_FP32) {
+      CTN_TRY(ctn_pw_simt(a, PRO_PRELU, EPI_MASK, st));
+    } else {
+      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws.wimg, st));
+      a.wimg = ws.wimg;
+      CTN_TRY(ctn_pw_umma(a, PRO_PRELU, EPI_MASK, c->math, st));
+    }
+  }
+  CTN_TRY(ctn_decoder_fwd(ws.what, p->dec_w, out, B * S, N, frames, pitch, c->kernel_size, c->stride, pl, T, stream));
+  return CTN_OK;
+}
+
+// grads: same layout as params; every tensor must be ZERO on entry (the kernels accumulate with atomics)
+extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, const ctn_params_t* grads, const float* x,
+                                  const float* d_out, int B, int T, void* train_ws, size_t train_ws_bytes, ctn_stream_t stream) {
+  LaunchScope scope;
+  CTN_TRY(check_train_cfg(c));
+  if (!p || !p->blocks || !grads || !grads->blocks || !x || !d_out || !train_ws || B <= 0 || T <= 0) return CTN_EINVAL;
+  if (((uintptr_t)train_ws) & 255) return CTN_EALIGN;
+  size_t need = 0;
+  CTN_TRY(ctn_train_workspace_bytes(c, B, T, &need));
+  if (train_ws_bytes < need) return CTN_EWORKSPACE;
+  int pl = 0, pr = 0;
+  const int frames = ctn_frames(T, c->kernel_size, c->stride, &pl, &pr);
+  const int pitch = ctn_pitch(frames);
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(train_ws);
+  TrainWs ws;
+  carve_train(cv, c, B, pitch, &ws);
+  const int N = c->n_basis, Bc = c->bottleneck, H = c->hidden, Sc = c->skip, S = c->n_sources, RX = c->num_blocks * c->num_layers,
+            X = c->num_layers, L = c->kernel_size;
+  const size_t bsN = (size_t)N * pitch, bsH = (size_t)H * pitch, bsBc = (size_t)Bc * pitch, bsSc = (size_t)Sc * pitch,
+               bsCat = (size_t)(Bc + Sc) * pitch, bsSN = (size_t)S * N * pitch;
+  const double nH = (double)H * (double)frames;
+  auto G = [](const float* q) { return const_cast<float*>(q); };
+
+  // ---- decoder (filterbank.py:243-249): d_what = conv1d(d_out; Wd) (the transposed conv's adjoint), dWd
+  CTN_TRY(ctn_encoder_fwd(d_out, p->dec_w, ws.dwhat, B * S, T, pl, pr, N, L, c->stride, 0, pitch, nullptr, stream));
+  k_encdec_wgrad<<<dim3(L, N), 256, 0, st>>>(ws.what, d_out, G(grads->dec_w), B * S, N, frames, pitch, T, L, c->stride, pl);
+  LAUNCH_CHECK();
+  // ---- w_hat = w * sigmoid(m_pre): d_mpre (in place), d_wprod
+  k_mask_bwd<<<grid_cb(N, B), 256, 0, st>>>(ws.dwhat, ws.w, ws.mask, ws.nC, S, N, frames, pitch);
+  LAUNCH_CHECK();
+  // ---- mask conv (conv_tasnet.py:341,374): dWm, dbm, d_sp = Wm^T d_mpre
+  k_prelu_apply<<<grid_cb(Sc, B), 256, 0, st>>>(ws.skip, ws.sp, p->prelu_out, Sc, frames, pitch);
+  LAUNCH_CHECK();
+  CTN_TRY(wgrad(ws.dwhat, bsSN, ws.sp, bsSc, G(grads->mask_w), S * N, Sc, B, frames, pitch, st));
+  CTN_TRY(rowsum(ws.dwhat, bsSN, S * N, B, frames, pitch, G(grads->mask_b), st));
+  CTN_TRY(transpose(p->mask_w, ws.Wt, S * N, Sc, st));
+  CTN_TRY(gemm_raw(c, ws, ws.Wt, Sc, S * N, ws.dwhat, ws.dsp, B, frames, pitch, st));
+  // ---- PReLU on the skip sum (conv_tasnet.py:340,373): dS (the gradient of EVERY block's skip output)
+  k_prelu_bwd<<<dim3(Sc, B), 256, 0, st>>>(ws.dsp, ws.skip, ws.dS, p->prelu_out, G(grads->prelu_out), Sc, frames, pitch);
+  LAUNCH_CHECK();
+  // dcat rows [Bc, Bc+Sc) = dS for all blocks with an output head; rows [0,Bc) = gradient of the block's residual output
+  k_rows<<<grid_cb(Sc, B), 256, 0, st>>>(ws.dcat + bsBc, bsCat, ws.dS, bsSc, Sc, 0, frames, pitch);
+  LAUNCH_CHECK();
+  // ---- residual blocks, last to first
+  for (int i = RX - 1; i >= 0; --i) {
+    const ctn_block_params_t& q = p->blocks[i];
+    const ctn_block_params_t& gq = grads->blocks[i];
+    const bool has_out = q.out_w != nullptr;
+    const int dil = 1 << (i % X);
+    const int pad_left = ((c->sep_kernel - 1) * dil) / 2;
+    const double* st1 = ws.stats + (size_t)(2 * i) * B * 2;
+    const double* st2 = ws.stats + (size_t)(2 * i + 1) * B * 2;
+    const int Mt = has_out ? Bc + Sc : Sc;
+    const float* dY = has_out ? ws.dcat : ws.dS;  // (B, Mt, pitch)
+    const size_t dY_bs = has_out ? bsCat : bsSc;
+    // un = gLN2(PReLU(u_pre)) recomputed for the weight gradients of the two heads
+    k_act_norm<<<grid_cb(H, B), 256, 0, st>>>(ws.upre[i], ws.T1, q.prelu2, q.norm2_g, q.norm2_b, st2, nH, c->eps_tcn, H, frames, pitch);
+    LAUNCH_CHECK();
+    if (has_out) {
+      CTN_TRY(wgrad(dY, dY_bs, ws.T1, bsH, G(gq.out_w), Bc, H, B, frames, pitch, st));
+      CTN_TRY(rowsum(dY, dY_bs, Bc, B, frames, pitch, G(gq.out_b), st));
+    }
+    const float* dYs = dY + (has_out ? bsBc : 0);
+    CTN_TRY(wgrad(dYs, dY_bs, ws.T1, bsH, G(gq.skip_w), Sc, H, B, frames, pitch, st));
+    CTN_TRY(rowsum(dYs, dY_bs, Sc, B, frames, pitch, G(gq.skip_b), st));
+    // d_un = [Wo; Ws]^T dY
+    {
+      cudaError_t e;
+      if (has_out && (e = cudaMemcpyAsync(ws.Wcat, q.out_w, sizeof(float) * (size_t)Bc * H, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return (int)e;
+      if ((e = cudaMemcpyAsync(ws.Wcat + (has_out ? (size_t)Bc * H : 0), q.skip_w, sizeof(float) * (size_t)Sc * H, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return (int)e;
+    }
+    CTN_TRY(transpose(ws.Wcat, ws.Wt, Mt, H, st));
+    CTN_TRY(gemm_raw(c, ws, ws.Wt, H, Mt, dY, ws.G1, B, frames, pitch, st));
+    // gLN2 + PReLU2 backward -> d_u_pre (G1 in place); dgamma2, dbeta2, da2, d(bd)
+    CTN_TRY(gln_prelu_bwd(ws.G1, ws.upre[i], ws.G1, q.prelu2, q.norm2_g, st2, nH, c->eps_tcn, ws.sums, G(gq.norm2_g), G(gq.norm2_b),
+                          G(gq.prelu2), G(gq.dw_b), B, H, frames, pitch, st));
+    // depthwise conv backward -> d_hn (G2), d(wd)
+    k_dw_bwd<<<dim3(H, B), 256, 0, st>>>(ws.G1, ws.hpre[i], ws.G2, q.prelu1, q.norm1_g, q.norm1_b, st1, nH, c->eps_tcn, q.dw_w,
+                                         G(gq.dw_w), H, frames, pitch, c->sep_kernel, dil, pad_left);
+    LAUNCH_CHECK();
+    // gLN1 + PReLU1 backward -> d_h_pre (G2 in place); dgamma1, dbeta1, da1, db1
+    CTN_TRY(gln_prelu_bwd(ws.G2, ws.hpre[i], ws.G2, q.prelu1, q.norm1_g, st1, nH, c->eps_tcn, ws.sums, G(gq.norm1_g), G(gq.norm1_b),
+                          G(gq.prelu1), G(gq.bottleneck_b), B, H, frames, pitch, st));
+    // bottleneck 1x1: dW1 = d_h_pre x_i^T ; d_x_i = W1^T d_h_pre (+ residual path)
+    CTN_TRY(wgrad(ws.G2, bsH, ws.x[i], bsBc, G(gq.bottleneck_w), H, Bc, B, frames, pitch, st));
+    CTN_TRY(transpose(q.bottleneck_w, ws.Wt, H, Bc, st));
+    CTN_TRY(gemm_raw(c, ws, ws.Wt, Bc, H, ws.G2, ws.dxtmp, B, frames, pitch, st));
+    k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dcat, bsCat, ws.dxtmp, bsBc, Bc, has_out ? 1 : 0, frames, pitch);
+    LAUNCH_CHECK();
+  }
+  // ---- head (conv_tasnet.py:333-335,370-371): x_0 = Wb gLN0(w) + bb.   d_x0 = dcat rows [0,Bc)
+  k_act_norm<<<grid_cb(N, B), 256, 0, st>>>(ws.w, ws.nA, nullptr, p->norm0_g, p->norm0_b, ws.stats0, (double)N * frames, c->eps, N,
+                                            frames, pitch);
+  LAUNCH_CHECK();
+  CTN_TRY(wgrad(ws.dcat, bsCat, ws.nA, bsN, G(grads->bn_w), Bc, N, B, frames, pitch, st));
+  CTN_TRY(rowsum(ws.dcat, bsCat, Bc, B, frames, pitch, G(grads->bn_b), st));
+  // d_wn = Wb^T d_x0 (the operand of the contraction must be dense (B, K, pitch): copy the rows out of dcat)
+  k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dxtmp, bsBc, ws.dcat, bsCat, Bc, 0, frames, pitch);
+  LAUNCH_CHECK();
+  CTN_TRY(transpose(p->bn_w, ws.Wt, Bc, N, st));
+  CTN_TRY(gemm_raw(c, ws, ws.Wt, N, Bc, ws.dxtmp, ws.nB, B, frames, pitch, st));
+  // gLN0 backward -> d_w (norm path) ; + product path ; ReLU mask of the encoder if any
+  CTN_TRY(gln_prelu_bwd(ws.nB, ws.w, ws.nB, nullptr, p->norm0_g, ws.stats0, (double)N * frames, c->eps, ws.sums, G(grads->norm0_g),
+                        G(grads->norm0_b), nullptr, nullptr, B, N, frames, pitch, st));
+  k_dw_combine<<<grid_cb(N, B), 256, 0, st>>>(ws.nB, ws.nC, ws.w, c->enc_relu, N, frames, pitch);
+  LAUNCH_CHECK();
+  // ---- encoder (filterbank.py:212,222): dWe
+  k_encdec_wgrad<<<dim3(L, N), 256, 0, st>>>(ws.nB, x, G(grads->enc_w), B, N, frames, pitch, T, L, c->stride, pl);
+  LAUNCH_CHECK();
+  return CTN_OK;
+}

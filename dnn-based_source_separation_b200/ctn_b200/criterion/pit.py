@@ -17,10 +17,47 @@ def _fused_ok(criterion, input, target):
             and input.shape == target.shape and input.is_cuda and input.size(1) <= 6)
 
 
+class _PitNegSisdrFn(torch.autograd.Function):
+    """loss_b (B) = min_perm -mean_i SI-SDR(est_i, tgt_perm[i]) with its gradient w.r.t. the estimate through the selected
+    permutation (the indices carry no gradient, pit.py:36-44); ctn_sisdr_pit_fwd / ctn_sisdr_pit_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, t, eps):
+        dev = N.require_cuda(x, t)
+        B, S, T = x.shape
+        loss_b = torch.empty(B, dtype=torch.float32, device=dev)
+        perm = torch.empty(B, S, dtype=torch.int64, device=dev)
+        scratch = torch.empty(N.ctn_sisdr_pit_scratch_bytes(B, S) // 8, dtype=torch.float64, device=dev)
+        N.check(N.ctn_sisdr_pit_fwd(x.data_ptr(), t.data_ptr(), B, S, T, float(eps), loss_b.data_ptr(), perm.data_ptr(), None,
+                                    None, scratch.data_ptr(), N.stream_ptr(dev)), "ctn_sisdr_pit_fwd")
+        ctx.save_for_backward(x, t, perm, scratch)
+        ctx.eps = float(eps)
+        ctx.mark_non_differentiable(perm)
+        return loss_b, perm
+
+    @staticmethod
+    def backward(ctx, g_loss_b, _g_perm):
+        x, t, perm, scratch = ctx.saved_tensors
+        B, S, T = x.shape
+        g = g_loss_b.contiguous().to(torch.float32)
+        d_est = torch.empty_like(x)
+        N.check(N.ctn_sisdr_pit_bwd(x.data_ptr(), t.data_ptr(), perm.data_ptr(), B, S, T, ctx.eps, scratch.data_ptr(),
+                                    g.data_ptr(), -1.0 / S, d_est.data_ptr(), N.stream_ptr(x.device)), "ctn_sisdr_pit_bwd")
+        return d_est, None, None
+
+
 def _fused(criterion, input, target, batch_mean):
-    if torch.is_grad_enabled() and (input.requires_grad or target.requires_grad):
-        raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
     x, t = input.contiguous(), target.contiguous()
+    if torch.is_grad_enabled() and target.requires_grad:
+        raise NotImplementedError("gradient w.r.t. the PIT target is not built")
+    if torch.is_grad_enabled() and x.requires_grad:
+        loss_b, perm = _PitNegSisdrFn.apply(x, t, float(criterion.eps))
+        S = x.shape[1]
+        scale = (S if criterion.reduction == 'sum' else 1) * (-1.0 if criterion.maximize else 1.0)
+        loss = loss_b.mean(dim=0) if batch_mean else loss_b
+        if scale != 1:
+            loss = loss * scale
+        return loss, perm
     dev = N.require_cuda(x, t)
     B, S, T = x.shape
     loss_b = torch.empty(B, dtype=torch.float32, device=dev)

@@ -219,10 +219,14 @@ class ConvTasNet(nn.Module):
             raise NotImplementedError("multichannel (4-D) input is outside the sm_100a kernel envelope")
         else:
             raise ValueError("Not support {} dimension input".format(n_dims))
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
         x = input.contiguous()
         dev = N.require_cuda(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: one autograd node over the whole model (ctn_convtasnet_fwd_train / ctn_convtasnet_bwd)
+            if want_latent:
+                raise NotImplementedError("extract_latent under autograd is not built: call it under torch.no_grad()")
+            from ._train import run_train
+            return run_train(self, x), None
         B, _, T = x.shape
         frames, _, _ = N.frames_of(T, self.kernel_size, self.stride)
         cfg = self.native_config()

@@ -170,6 +170,28 @@ int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params
                              int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
                              ctn_stream_t stream);
 
+/* ---- training path: what `loss.backward()` does in the reference trainer (egs/wsj0-mix/common/src/driver.py:146-150) ----
+ * ctn_convtasnet_fwd_train == ctn_convtasnet_fwd (same estimate) but keeps, inside `train_ws`, what the backward needs:
+ * encoder output, mask, every residual block's input and the two pre-activations (W1 x + b1, dwconv(..) + bd) and the gLN
+ * statistics.  ctn_convtasnet_bwd then turns d_out (B,S,T), the gradient of the estimate, into the gradients of all
+ * parameters.  `grads` has the layout of ctn_params_t (same shapes as the parameters); every gradient tensor must be
+ * ZERO on entry (kernels accumulate with atomics) and is complete on return.  The gradient w.r.t. the mixture is not
+ * produced (the reference trainer never asks for it).  train_ws: ctn_train_workspace_bytes(), 256-byte aligned, must
+ * be left untouched between the two calls.  Envelope: non-causal gLN, sigmoid mask, sep_kernel <= 8. */
+typedef ctn_params_t ctn_grads_t;
+int ctn_train_workspace_bytes(const ctn_config_t* cfg, int batch, int T, size_t* bytes);
+int ctn_convtasnet_fwd_train(const ctn_config_t* cfg, const ctn_params_t* params, const float* x, int B, int T, float* out,
+                             void* train_ws, size_t train_ws_bytes, ctn_stream_t stream);
+int ctn_convtasnet_bwd(const ctn_config_t* cfg, const ctn_params_t* params, const ctn_grads_t* grads, const float* x,
+                       const float* d_out, int B, int T, void* train_ws, size_t train_ws_bytes, ctn_stream_t stream);
+
+/* Backward of ctn_sisdr_pit_fwd through the selected permutation (src/criterion/pit.py:36-44; sdr.py:135-137):
+ * d_est (B,S,T) = grad_loss_b[b] * coef * dSI-SDR(est_i, tgt_perm[i])/d est_i.  fwd_scratch = the scratch buffer the
+ * forward call filled (pair statistics), perm = its permutation output.  grad_loss_b (B) nullable (= 1);
+ * coef = -1/S for NegSISDR(reduction='mean'), -1 for 'sum'. */
+int ctn_sisdr_pit_bwd(const float* est, const float* tgt, const int64_t* perm, int B, int S, int T, float eps,
+                      const double* fwd_scratch, const float* grad_loss_b, float coef, float* d_est, ctn_stream_t stream);
+
 /* Test hook: ONE pointwise (1x1) contraction D[b][m][t] = epi(sum_k W[m][k] A[b][k][t]) in the selected numeric mode,
  * so tests can compare the tcgen05 kernels with the FFMA kernels operand by operand.  A (B,K,pitch), D (B,M,pitch),
  * pitch % 128 == 0.  epi: 0 = raw, 2 = +bias, PReLU(slope), (sum,sumsq) -> stats_out.  dbg (nullable): 4 words

@@ -171,8 +171,10 @@ def test_no_cpu_fallback():
     with pytest.raises(ValueError):
         with torch.no_grad():
             m(torch.randn(4, 64))
-    with pytest.raises(NotImplementedError):   # grad mode without backward kernels must be loud, not silent
+    with pytest.raises(RuntimeError, match="no CPU fallback"):   # training path: native too, never an eager fallback
         m(x)
+    with pytest.raises(NotImplementedError):   # pieces without backward kernels stay loud under autograd
+        m.separator(torch.randn(1, 16, 20))
 
 
 def test_generic_pit_loop_matches_oracle_on_cpu():
