@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=4, help="mixtures per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train", action="store_true",
+                    help="time the TRAINING step instead (fwd + PIT + backward + gradient all-reduce + clip + Adam); prints its own line")
     return ap.parse_args()
 
 
@@ -219,6 +221,51 @@ def main():
         perm_pin.copy_(perm, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller reads loss / perm every step (driver.py:157 loss.item())
         return float(loss_pin[0])
+
+    if args.train:
+        # ---- training step (driver.py:146-157): fwd_train + PIT + native backward + ONE gradient all-reduce + clip + Adam ----
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+        nelem = 0
+
+        def step_train():
+            nonlocal nelem
+            opt.zero_grad(set_to_none=True)
+            loss, _ = crit(model(mixture_d), sources_d)
+            loss.backward()
+            nelem = D.allreduce_gradients(model)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+            return loss
+
+        for _ in range(max(args.warmup, 2)):
+            loss = step_train()
+        launches = model.last_launches + model.last_bwd_launches + 3
+        D.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(args.steps):
+                loss = step_train()
+            e1.record()
+            torch.cuda.synchronize()
+        D.barrier()
+        ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        if rank == 0:
+            print(json.dumps({
+                "mode": "train", "metric": "audio-sec/s Conv-TasNet %dspk %gs@8kHz TRAIN step (fwd+SI-SDR-PIT+bwd+allreduce+clip+Adam)" % (S, args.seconds),
+                "value": world * B * args.seconds * args.steps / (ms * 1e-3), "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "dtype": math_name, "data": "synthetic", "config": {"workload": f"cfg2/cfg3 shape, batch {B} per GPU", "global_batch": world * B,
+                "optimizer": "torch.optim.Adam(fused) + clip_grad_norm_ (torch; not part of the native path)"},
+                "gpu_launches": launches * args.steps, "allreduce_elems": nelem, "peak_mem_gb": peak_gb, "clocks": clk.summary(),
+                "last_loss": float(loss)}), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
 
     launches_per_step = 0
     with torch.no_grad():

@@ -25,6 +25,25 @@ t = D.max_over_ranks(10.0 + rank)
 assert t == 11.0
 s = D.sum_over_ranks(float(hi - lo))
 assert s == G
+# gradient all-reduce of the batch-sharded training step: unequal shards (4 + 3 of 7), both bucket paths
+class M(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.zeros(5, 3)); self.b = torch.nn.Parameter(torch.zeros(7))
+per_sample = torch.arange(G * 22, dtype=torch.float32).reshape(G, 22) / 10.0     # "per-sample gradients"
+want = per_sample.mean(dim=0)                                                    # gradient of the GLOBAL batch mean
+for aliased in (False, True):
+    m = M()
+    local = per_sample[lo:hi].mean(dim=0)                                        # gradient of this shard's mean loss
+    if aliased:   # the native backward hands out views of one flat buffer
+        flat = local.clone(); m.last_flat_grad = flat
+        m.a.grad = flat[:15].view(5, 3); m.b.grad = flat[15:].view(7)
+    else:
+        m.a.grad = local[:15].clone().view(5, 3); m.b.grad = local[15:].clone()
+    n = D.allreduce_gradients(m, local_batch=hi - lo, global_batch=G)
+    assert n == 22
+    got = torch.cat([m.a.grad.reshape(-1), m.b.grad.reshape(-1)])
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6), (aliased, got, want)
 D.barrier()
 print("rank", rank, "ok", lo, hi)
 """
