@@ -65,6 +65,11 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st);
 size_t ctn_umma_wimg_bytes(int M, int K, int math);
 int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st);
 
+// tcgen05 weight gradient of a 1x1 conv (ctn_wgrad_umma.cu): dW (M,K) += sum_{b,t} dY[b][m][t] X[b][k][t]; rows
+// [0,split_row) -> dWa, rest -> dWb (nullable).  dW must be zero-initialised by the caller (split-K partials are added).
+int ctn_wgrad_umma(const float* dy, size_t dy_bs, const float* x, size_t x_bs, float* dWa, float* dWb, int split_row, int M,
+                   int K, int B, int frames, int pitch, int math, cudaStream_t st);
+
 int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
                   int row_offset, cudaStream_t st);
 

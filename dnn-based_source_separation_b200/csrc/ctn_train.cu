@@ -13,6 +13,7 @@
 //     per-sample gLN reductions accumulated in double.
 // Saved per residual block: its input x_i, the pre-activations h_pre = W1 x + b1 and u_pre = dwconv(gLN1(PReLU h_pre)) + bd,
 // and the two (sum, sumsq) statistics; normalised tensors are recomputed in the backward.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "ctn_internal.h"
@@ -33,9 +34,37 @@ struct Carver {
 };
 
 // ================================================================================================================
-// streaming kernels.  Layout (B, C, pitch); only columns t < frames carry data, pad columns are written as zero.
+// streaming kernels.  Layout (B, C, pitch), pitch % 128 == 0, rows 16-byte aligned; only columns t < frames carry data,
+// pad columns are written as zero.  A thread owns 4 consecutive time steps (128-bit loads / stores).
 // Unless noted: grid (min(C, 1024), B), block 256, a block walks channels c = blockIdx.x, += gridDim.x.
 // ================================================================================================================
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// zero the lanes of a 4-vector that fall at or beyond `frames`
+__device__ __forceinline__ float4 mask4(float4 v, int t, int frames) {
+  if (t + 3 < frames) return v;
+  if (t + 0 >= frames) v.x = 0.f;
+  if (t + 1 >= frames) v.y = 0.f;
+  if (t + 2 >= frames) v.z = 0.f;
+  if (t + 3 >= frames) v.w = 0.f;
+  return v;
+}
+// 4 consecutive samples row[t0 .. t0+3] with zero outside [0, frames) (any alignment, any t0)
+__device__ __forceinline__ float4 ld4_shift(const float* __restrict__ row, int t0, int frames) {
+  if ((t0 & 3) == 0 && t0 >= 0 && t0 + 3 < frames) return ld4(row + t0);
+  float4 v;
+  v.x = (t0 + 0 >= 0 && t0 + 0 < frames) ? row[t0 + 0] : 0.f;
+  v.y = (t0 + 1 >= 0 && t0 + 1 < frames) ? row[t0 + 1] : 0.f;
+  v.z = (t0 + 2 >= 0 && t0 + 2 < frames) ? row[t0 + 2] : 0.f;
+  v.w = (t0 + 3 >= 0 && t0 + 3 < frames) ? row[t0 + 3] : 0.f;
+  return v;
+}
+__device__ __forceinline__ float4 prelu4(float4 v, float a) {
+  return make_float4(prelu_f(v.x, a), prelu_f(v.y, a), prelu_f(v.z, a), prelu_f(v.w, a));
+}
+__device__ __forceinline__ float sum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 
 // y = y + bias[c] (in place) ; stats[b] += (sum, sumsq) of PReLU(y)          (tdcn.py:116-119 before the norm)
 __global__ void __launch_bounds__(256) k_bias_prelu_stats(float* __restrict__ y, const float* __restrict__ bias,
@@ -49,15 +78,16 @@ __global__ void __launch_bounds__(256) k_bias_prelu_stats(float* __restrict__ y,
     float* r = y + ((size_t)b * C + c) * pitch;
     const float bc = bias[c];
     float ls = 0.f, lss = 0.f;
-    for (int t = threadIdx.x; t < pitch; t += 256) {
-      float v = 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 v = zero4();
       if (t < frames) {
-        v = r[t] + bc;
-        const float p = prelu_f(v, a);
-        ls += p;
-        lss = fmaf(p, p, lss);
+        v = ld4(r + t);
+        v = mask4(make_float4(v.x + bc, v.y + bc, v.z + bc, v.w + bc), t, frames);
+        const float4 p = prelu4(v, a);
+        ls += sum4(p);
+        lss += dot4(p, p);
       }
-      r[t] = v;
+      st4(r + t, v);
     }
     s += ls;
     ss += lss;
@@ -68,6 +98,7 @@ __global__ void __launch_bounds__(256) k_bias_prelu_stats(float* __restrict__ y,
 
 // u_pre[c][t] = sum_k wd[c][k] * hn[c][t + k*d - pl] + bd[c],  hn = gLN1(PReLU(h_pre)) inside [0,frames), 0 outside
 // (tdcn.py:120-130,181); stats2[b] += (sum, sumsq) of PReLU(u_pre; a2)
+#define CTN_MAX_P 8
 __global__ void __launch_bounds__(256) k_dw_train_fwd(const float* __restrict__ hpre, float* __restrict__ upre,
                                                       const float* __restrict__ g1, const float* __restrict__ b1,
                                                       const float* __restrict__ wd, const float* __restrict__ bd,
@@ -85,20 +116,26 @@ __global__ void __launch_bounds__(256) k_dw_train_fwd(const float* __restrict__ 
     const float gsc = g1[c] * mr.y, gsh = b1[c] - mr.x * mr.y * g1[c];
     const float bc = bd[c];
     float ls = 0.f, lss = 0.f;
-    for (int t = threadIdx.x; t < pitch; t += 256) {
-      float v = 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 v = zero4();
       if (t < frames) {
-        float acc = bc;
+        v = make_float4(bc, bc, bc, bc);
         for (int k = 0; k < P; ++k) {
-          const int tt = t + k * dil - pad_left;
-          if (tt >= 0 && tt < frames) acc = fmaf(wd[c * P + k], fmaf(gsc, prelu_f(h[tt], a1), gsh), acc);
+          const int t0 = t + k * dil - pad_left;
+          const float w = wd[c * P + k];
+          const float4 q = prelu4(ld4_shift(h, t0, frames), a1);
+          // hn = gsc*q + gsh inside [0,frames), exactly 0 outside (the zero padding is applied AFTER the norm, tdcn.py:123-130)
+          if (t0 + 0 >= 0 && t0 + 0 < frames) v.x = fmaf(w, fmaf(gsc, q.x, gsh), v.x);
+          if (t0 + 1 >= 0 && t0 + 1 < frames) v.y = fmaf(w, fmaf(gsc, q.y, gsh), v.y);
+          if (t0 + 2 >= 0 && t0 + 2 < frames) v.z = fmaf(w, fmaf(gsc, q.z, gsh), v.z);
+          if (t0 + 3 >= 0 && t0 + 3 < frames) v.w = fmaf(w, fmaf(gsc, q.w, gsh), v.w);
         }
-        v = acc;
-        const float p = prelu_f(v, a2);
-        ls += p;
-        lss = fmaf(p, p, lss);
+        v = mask4(v, t, frames);
+        const float4 p = mask4(prelu4(v, a2), t, frames);
+        ls += sum4(p);
+        lss += dot4(p, p);
       }
-      u[t] = v;
+      st4(u + t, v);
     }
     s += ls;
     ss += lss;
@@ -120,13 +157,14 @@ __global__ void __launch_bounds__(256) k_act_norm(const float* __restrict__ pre,
     const float* p = pre + ((size_t)b * C + c) * pitch;
     float* o = y + ((size_t)b * C + c) * pitch;
     const float gsc = g[c] * mr.y, gsh = bt[c] - mr.x * mr.y * g[c];
-    for (int t = threadIdx.x; t < pitch; t += 256) {
-      float v = 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 v = zero4();
       if (t < frames) {
-        const float x = act ? prelu_f(p[t], a) : p[t];
-        v = fmaf(gsc, x, gsh);
+        float4 x = ld4(p + t);
+        if (act) x = prelu4(x, a);
+        v = mask4(make_float4(fmaf(gsc, x.x, gsh), fmaf(gsc, x.y, gsh), fmaf(gsc, x.z, gsh), fmaf(gsc, x.w, gsh)), t, frames);
       }
-      o[t] = v;
+      st4(o + t, v);
     }
   }
 }
@@ -139,19 +177,20 @@ __global__ void __launch_bounds__(256) k_res_skip(const float* __restrict__ r, i
   const int b = blockIdx.y;
   for (int m = blockIdx.x; m < Mt; m += gridDim.x) {
     const float* rr = r + ((size_t)b * Mt + m) * pitch;
-    if (has_out && m < Bc) {
-      const float* xi = xin + ((size_t)b * Bc + m) * pitch;
-      float* xo = xout + ((size_t)b * Bc + m) * pitch;
-      const float bb = bo[m];
-      for (int t = threadIdx.x; t < pitch; t += 256) xo[t] = t < frames ? xi[t] + rr[t] + bb : 0.f;
-    } else {
-      const int j = m - (has_out ? Bc : 0);
-      float* sk = skip + ((size_t)b * Sc + j) * pitch;
-      const float bb = bs[j];
-      for (int t = threadIdx.x; t < pitch; t += 256) {
-        const float base = skip_init ? 0.f : sk[t];
-        sk[t] = t < frames ? base + rr[t] + bb : 0.f;
+    const bool is_x = has_out && m < Bc;
+    const int j = m - (has_out ? Bc : 0);
+    const float* src = is_x ? xin + ((size_t)b * Bc + m) * pitch : skip + ((size_t)b * Sc + j) * pitch;
+    float* dst = is_x ? xout + ((size_t)b * Bc + m) * pitch : skip + ((size_t)b * Sc + j) * pitch;
+    const float bb = is_x ? bo[m] : bs[j];
+    const bool fresh = !is_x && skip_init;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 v = zero4();
+      if (t < frames) {
+        const float4 q = ld4(rr + t);
+        const float4 base = fresh ? zero4() : ld4(src + t);
+        v = mask4(make_float4(base.x + q.x + bb, base.y + q.y + bb, base.z + q.z + bb, base.w + q.w + bb), t, frames);
       }
+      st4(dst + t, v);
     }
   }
 }
@@ -171,22 +210,27 @@ __global__ void __launch_bounds__(256) k_rows(float* __restrict__ dst, size_t ds
   for (int c = blockIdx.x; c < C; c += gridDim.x) {
     float* d = dst + (size_t)b * dst_bs + (size_t)c * pitch;
     const float* s = src + (size_t)b * src_bs + (size_t)c * pitch;
-    for (int t = threadIdx.x; t < pitch; t += 256) d[t] = t < frames ? (accumulate ? d[t] + s[t] : s[t]) : 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 v = zero4();
+      if (t < frames) {
+        v = ld4(s + t);
+        if (accumulate) { const float4 q = ld4(d + t); v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w); }
+        v = mask4(v, t, frames);
+      }
+      st4(d + t, v);
+    }
   }
 }
 
-// out[c] += sum_{b,t} dy[b][c][t]   (bias gradients).  grid (C), block 256
-__global__ void __launch_bounds__(256) k_rowsum(const float* __restrict__ dy, size_t batch_stride, int B, int frames, int pitch,
+// out[c] += sum_{b,t} dy[b][c][t]   (bias gradients).  grid (C, B), block 256
+__global__ void __launch_bounds__(256) k_rowsum(const float* __restrict__ dy, size_t batch_stride, int frames, int pitch,
                                                 float* __restrict__ out) {
   __shared__ double red[64];
-  const int c = blockIdx.x;
-  double s = 0.0, z = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const float* r = dy + (size_t)b * batch_stride + (size_t)c * pitch;
-    float ls = 0.f;
-    for (int t = threadIdx.x; t < frames; t += 256) ls += r[t];
-    s += ls;
-  }
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* r = dy + (size_t)b * batch_stride + (size_t)c * pitch;
+  float ls = 0.f;
+  for (int t = threadIdx.x * 4; t < frames; t += 1024) ls += sum4(mask4(ld4(r + t), t, frames));
+  double s = ls, z = 0.0;
   block_sum2_d(s, z, red);
   if (threadIdx.x == 0) atomicAdd(&out[c], (float)s);
 }
@@ -206,11 +250,13 @@ __global__ void __launch_bounds__(256) k_gln_bwd_reduce(const float* __restrict_
   const float* d = dy + ((size_t)b * C + c) * pitch;
   const float* p = pre + ((size_t)b * C + c) * pitch;
   float s0 = 0.f, s1 = 0.f;
-  for (int t = threadIdx.x; t < frames; t += 256) {
-    const float x = act ? prelu_f(p[t], a) : p[t];
-    const float xh = (x - mr.x) * mr.y;
-    s0 += d[t];
-    s1 = fmaf(d[t], xh, s1);
+  for (int t = threadIdx.x * 4; t < frames; t += 1024) {
+    const float4 dv = mask4(ld4(d + t), t, frames);
+    float4 x = ld4(p + t);
+    if (act) x = prelu4(x, a);
+    const float4 xh = make_float4((x.x - mr.x) * mr.y, (x.y - mr.x) * mr.y, (x.z - mr.x) * mr.y, (x.w - mr.x) * mr.y);
+    s0 += sum4(dv);
+    s1 += dot4(dv, xh);  // dv is zero in the pad lanes
   }
   double ds0 = s0, ds1 = s1;
   block_sum2_d(ds0, ds1, red);
@@ -243,22 +289,28 @@ __global__ void __launch_bounds__(256) k_gln_prelu_bwd_apply(const float* dy, co
   const float* p = pre + ((size_t)b * C + c) * pitch;
   float* o = dpre + ((size_t)b * C + c) * pitch;
   float sa = 0.f, sb = 0.f;
-  for (int t = threadIdx.x; t < pitch; t += 256) {
-    float v = 0.f;
+  for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+    float4 v = zero4();
     if (t < frames) {
-      const float pv = p[t];
-      const float x = act ? prelu_f(pv, a) : pv;
-      const float xh = (x - mr.x) * mr.y;
-      const float da = mr.y * (gc * d[t] - mg - xh * mgx);
-      if (act) {
-        v = pv > 0.f ? da : a * da;
-        if (!(pv > 0.f)) sa = fmaf(da, pv, sa);
-      } else {
-        v = da;
+      const float4 dv = ld4(d + t), pv = ld4(p + t);
+      const float dvv[4] = {dv.x, dv.y, dv.z, dv.w}, pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+      float ov[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = act ? prelu_f(pvv[j], a) : pvv[j];
+        const float xh = (x - mr.x) * mr.y;
+        const float da = mr.y * (gc * dvv[j] - mg - xh * mgx);
+        float r = da;
+        if (act) {
+          r = pvv[j] > 0.f ? da : a * da;
+          if (!(pvv[j] > 0.f) && t + j < frames) sa = fmaf(da, pvv[j], sa);
+        }
+        ov[j] = t + j < frames ? r : 0.f;
+        sb += ov[j];
       }
-      sb += v;
+      v = make_float4(ov[0], ov[1], ov[2], ov[3]);
     }
-    o[t] = v;
+    st4(o + t, v);
   }
   double dsa = sa, dsb = sb;
   block_sum2_d(dsa, dsb, red);
@@ -272,7 +324,6 @@ __global__ void __launch_bounds__(256) k_gln_prelu_bwd_apply(const float* dy, co
 //   d_hn[c][t] = sum_k wd[c][k] * dU[c][t - k*d + pl]
 //   dwd[c][k] += sum_{b,t} dU[c][t] * hn[c][t + k*d - pl],   hn = gLN1(PReLU(h_pre)) inside [0,frames), 0 outside
 // grid (C, B)
-#define CTN_MAX_P 8
 __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre, const float* __restrict__ hpre,
                                                 float* __restrict__ dhn, const float* __restrict__ slope1,
                                                 const float* __restrict__ g1, const float* __restrict__ b1,
@@ -290,21 +341,28 @@ __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre,
   float w[CTN_MAX_P], acc[CTN_MAX_P];
 #pragma unroll
   for (int k = 0; k < CTN_MAX_P; ++k) { w[k] = k < P ? wd[c * P + k] : 0.f; acc[k] = 0.f; }
-  for (int t = threadIdx.x; t < pitch; t += 256) {
-    float v = 0.f;
+  for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+    float4 v = zero4();
     if (t < frames) {
-      const float dut = du[t];
+      const float4 dut = mask4(ld4(du + t), t, frames);
 #pragma unroll
       for (int k = 0; k < CTN_MAX_P; ++k) {
         if (k < P) {
-          const int ts = t - k * dil + pad_left;  // u[ts] read hn[t] through tap k
-          if (ts >= 0 && ts < frames) v = fmaf(w[k], du[ts], v);
-          const int th = t + k * dil - pad_left;  // u[t] read hn[th] through tap k
-          if (th >= 0 && th < frames) acc[k] = fmaf(dut, fmaf(gsc, prelu_f(h[th], a1), gsh), acc[k]);
+          const float4 q = ld4_shift(du, t - k * dil + pad_left, frames);  // u[ts] read hn[t] through tap k
+          v.x = fmaf(w[k], q.x, v.x); v.y = fmaf(w[k], q.y, v.y); v.z = fmaf(w[k], q.z, v.z); v.w = fmaf(w[k], q.w, v.w);
+          const int th = t + k * dil - pad_left;                           // u[t] read hn[th] through tap k
+          const float4 hq = prelu4(ld4_shift(h, th, frames), a1);
+          float4 hn;
+          hn.x = (th + 0 >= 0 && th + 0 < frames) ? fmaf(gsc, hq.x, gsh) : 0.f;
+          hn.y = (th + 1 >= 0 && th + 1 < frames) ? fmaf(gsc, hq.y, gsh) : 0.f;
+          hn.z = (th + 2 >= 0 && th + 2 < frames) ? fmaf(gsc, hq.z, gsh) : 0.f;
+          hn.w = (th + 3 >= 0 && th + 3 < frames) ? fmaf(gsc, hq.w, gsh) : 0.f;
+          acc[k] += dot4(dut, hn);
         }
       }
+      v = mask4(v, t, frames);
     }
-    o[t] = v;
+    st4(o + t, v);
   }
   for (int k = 0; k < P; k += 2) {
     double x0 = acc[k], x1 = (k + 1 < P) ? acc[k + 1] : 0.0;
@@ -327,20 +385,21 @@ __global__ void __launch_bounds__(256) k_mask_bwd(float* __restrict__ dwhat, con
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     const float* wr = w + ((size_t)b * N + n) * pitch;
     float* dp = dwprod + ((size_t)b * N + n) * pitch;
-    for (int t = threadIdx.x; t < pitch; t += 256) {
-      float acc = 0.f;
-      const float wv = t < frames ? wr[t] : 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+      float4 acc = zero4();
+      const float4 wv = t < frames ? mask4(ld4(wr + t), t, frames) : zero4();
       for (int s = 0; s < S; ++s) {
         const size_t idx = (((size_t)b * S + s) * N + n) * pitch + t;
-        float v = 0.f;
+        float4 v = zero4();
         if (t < frames) {
-          const float d = dwhat[idx], m = mask[idx];
-          acc = fmaf(d, m, acc);
-          v = d * wv * m * (1.f - m);
+          const float4 d = mask4(ld4(dwhat + idx), t, frames), m = ld4(mask + idx);
+          acc.x = fmaf(d.x, m.x, acc.x); acc.y = fmaf(d.y, m.y, acc.y); acc.z = fmaf(d.z, m.z, acc.z); acc.w = fmaf(d.w, m.w, acc.w);
+          v = make_float4(d.x * wv.x * m.x * (1.f - m.x), d.y * wv.y * m.y * (1.f - m.y), d.z * wv.z * m.z * (1.f - m.z),
+                          d.w * wv.w * m.w * (1.f - m.w));
         }
-        dwhat[idx] = v;
+        st4(dwhat + idx, v);
       }
-      dp[t] = acc;
+      st4(dp + t, acc);
     }
   }
 }
@@ -352,7 +411,7 @@ __global__ void __launch_bounds__(256) k_prelu_apply(const float* __restrict__ x
   for (int c = blockIdx.x; c < C; c += gridDim.x) {
     const float* p = x + ((size_t)b * C + c) * pitch;
     float* o = y + ((size_t)b * C + c) * pitch;
-    for (int t = threadIdx.x; t < pitch; t += 256) o[t] = t < frames ? prelu_f(p[t], a) : 0.f;
+    for (int t = threadIdx.x * 4; t < pitch; t += 1024) st4(o + t, t < frames ? mask4(prelu4(ld4(p + t), a), t, frames) : zero4());
   }
 }
 
@@ -400,10 +459,50 @@ __global__ void __launch_bounds__(256) k_dw_combine(float* __restrict__ dw, cons
 
 // ---- filter-bank weight gradients: dW[n][k] += sum_{r,f} act[r][n][f] * sig[r][f*stride + k - pl]
 // (encoder: act = d_w, sig = mixture, filterbank.py:212,222; decoder: act = w_hat, sig = d_out, filterbank.py:243).
-// grid (L, N), block 256
+// Fast variant (L <= 32): grid (N, row groups), block 256; a thread walks frames of its rows with all L taps in registers
+// (the signal window comes from L1: neighbouring frames share L - stride samples), one reduction per block at the end.
+#define ENCDEC_MAX_L 32
 __global__ void __launch_bounds__(256) k_encdec_wgrad(const float* __restrict__ act, const float* __restrict__ sig,
                                                       float* __restrict__ dW, int R, int N, int frames, int pitch, int T, int L,
                                                       int stride, int pad_left) {
+  __shared__ float sacc[ENCDEC_MAX_L];
+  const int n = blockIdx.x;
+  float acc[ENCDEC_MAX_L];
+#pragma unroll
+  for (int k = 0; k < ENCDEC_MAX_L; ++k) acc[k] = 0.f;
+  if (threadIdx.x < ENCDEC_MAX_L) sacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int r = blockIdx.y; r < R; r += gridDim.y) {
+    const float* a = act + ((size_t)r * N + n) * pitch;
+    const float* sg = sig + (size_t)r * T;
+    for (int f = threadIdx.x; f < frames; f += 256) {
+      const float av = a[f];
+      const int t0 = f * stride - pad_left;
+      if (t0 >= 0 && t0 + L <= T) {
+#pragma unroll
+        for (int k = 0; k < ENCDEC_MAX_L; ++k)
+          if (k < L) acc[k] = fmaf(av, sg[t0 + k], acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < ENCDEC_MAX_L; ++k)
+          if (k < L && t0 + k >= 0 && t0 + k < T) acc[k] = fmaf(av, sg[t0 + k], acc[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ENCDEC_MAX_L; ++k) {
+    if (k < L) {
+      const float v = warp_sum(acc[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[k], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < L) atomicAdd(&dW[n * L + threadIdx.x], sacc[threadIdx.x]);
+}
+// generic variant (any L): grid (L, N), block 256
+__global__ void __launch_bounds__(256) k_encdec_wgrad_generic(const float* __restrict__ act, const float* __restrict__ sig,
+                                                              float* __restrict__ dW, int R, int N, int frames, int pitch, int T,
+                                                              int L, int stride, int pad_left) {
   __shared__ double red[64];
   const int k = blockIdx.x, n = blockIdx.y;
   double s = 0.0, z = 0.0;
@@ -605,22 +704,47 @@ int transpose(const float* W, float* Wt, int M, int K, cudaStream_t st) {
   return CTN_OK;
 }
 
-int wgrad(const float* dy, size_t dy_bs, const float* x, size_t x_bs, float* dW, int M, int K, int B, int frames, int pitch,
-          cudaStream_t st) {
-  const int tiles = ((M + 63) / 64) * ((K + 63) / 64);
-  const long long total = (long long)B * ((frames + WG_T - 1) / WG_T);
-  long long splits = (4 * 148 + tiles - 1) / tiles;
-  if (splits > total) splits = total;
-  if (splits < 1) splits = 1;
-  const int upc = (int)((total + splits - 1) / splits);
-  splits = (total + upc - 1) / upc;
-  k_wgrad<<<dim3(tiles, (unsigned)splits), 256, 0, st>>>(dy, dy_bs, x, x_bs, dW, M, K, B, frames, pitch, upc);
+// dW (M, K) += sum dY X^T; rows [0, split_row) -> dWa, the rest -> dWb (nullable).  Tensor cores (3xTF32 / TF32) unless the
+// configured mode is plain fp32, where the FFMA split-K kernel runs.
+int wgrad(const ctn_config_t* c, const float* dy, size_t dy_bs, const float* x, size_t x_bs, float* dWa, float* dWb, int split_row,
+          int M, int K, int B, int frames, int pitch, cudaStream_t st) {
+  static const char* env = getenv("CTN_WGRAD_SIMT");  // debug: force the FFMA kernel
+  if (c->math != CTN_MATH_FP32 && !(env && atoi(env)))
+    return ctn_wgrad_umma(dy, dy_bs, x, x_bs, dWa, dWb, split_row, M, K, B, frames, pitch, c->math, st);
+  const int parts = dWb ? 2 : 1;
+  for (int part = 0; part < parts; ++part) {
+    const int r0 = part == 0 ? 0 : split_row, Mp = part == 0 ? (dWb ? split_row : M) : M - split_row;
+    float* dW = part == 0 ? dWa : dWb;
+    const float* dyp = dy + (size_t)r0 * pitch;
+    const int tiles = ((Mp + 63) / 64) * ((K + 63) / 64);
+    const long long total = (long long)B * ((frames + WG_T - 1) / WG_T);
+    long long splits = (4 * 148 + tiles - 1) / tiles;
+    if (splits > total) splits = total;
+    if (splits < 1) splits = 1;
+    const int upc = (int)((total + splits - 1) / splits);
+    splits = (total + upc - 1) / upc;
+    k_wgrad<<<dim3(tiles, (unsigned)splits), 256, 0, st>>>(dyp, dy_bs, x, x_bs, dW, Mp, K, B, frames, pitch, upc);
+    LAUNCH_CHECK();
+  }
+  return CTN_OK;
+}
+
+int encdec_wgrad(const float* act, const float* sig, float* dW, int R, int N, int frames, int pitch, int T, int L, int stride,
+                 int pad_left, cudaStream_t st) {
+  if (L <= ENCDEC_MAX_L) {
+    int gy = (4 * 148 + N - 1) / N;
+    if (gy > R) gy = R;
+    if (gy < 1) gy = 1;
+    k_encdec_wgrad<<<dim3(N, gy), 256, 0, st>>>(act, sig, dW, R, N, frames, pitch, T, L, stride, pad_left);
+  } else {
+    k_encdec_wgrad_generic<<<dim3(L, N), 256, 0, st>>>(act, sig, dW, R, N, frames, pitch, T, L, stride, pad_left);
+  }
   LAUNCH_CHECK();
   return CTN_OK;
 }
 
 int rowsum(const float* dy, size_t bs, int C, int B, int frames, int pitch, float* out, cudaStream_t st) {
-  k_rowsum<<<C, 256, 0, st>>>(dy, bs, B, frames, pitch, out);
+  k_rowsum<<<dim3(C, B), 256, 0, st>>>(dy, bs, frames, pitch, out);
   LAUNCH_CHECK();
   return CTN_OK;
 }
@@ -765,15 +889,14 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
 
   // ---- decoder (filterbank.py:243-249): d_what = conv1d(d_out; Wd) (the transposed conv's adjoint), dWd
   CTN_TRY(ctn_encoder_fwd(d_out, p->dec_w, ws.dwhat, B * S, T, pl, pr, N, L, c->stride, 0, pitch, nullptr, stream));
-  k_encdec_wgrad<<<dim3(L, N), 256, 0, st>>>(ws.what, d_out, G(grads->dec_w), B * S, N, frames, pitch, T, L, c->stride, pl);
-  LAUNCH_CHECK();
+  CTN_TRY(encdec_wgrad(ws.what, d_out, G(grads->dec_w), B * S, N, frames, pitch, T, L, c->stride, pl, st));
   // ---- w_hat = w * sigmoid(m_pre): d_mpre (in place), d_wprod
   k_mask_bwd<<<grid_cb(N, B), 256, 0, st>>>(ws.dwhat, ws.w, ws.mask, ws.nC, S, N, frames, pitch);
   LAUNCH_CHECK();
   // ---- mask conv (conv_tasnet.py:341,374): dWm, dbm, d_sp = Wm^T d_mpre
   k_prelu_apply<<<grid_cb(Sc, B), 256, 0, st>>>(ws.skip, ws.sp, p->prelu_out, Sc, frames, pitch);
   LAUNCH_CHECK();
-  CTN_TRY(wgrad(ws.dwhat, bsSN, ws.sp, bsSc, G(grads->mask_w), S * N, Sc, B, frames, pitch, st));
+  CTN_TRY(wgrad(c, ws.dwhat, bsSN, ws.sp, bsSc, G(grads->mask_w), nullptr, 0, S * N, Sc, B, frames, pitch, st));
   CTN_TRY(rowsum(ws.dwhat, bsSN, S * N, B, frames, pitch, G(grads->mask_b), st));
   CTN_TRY(transpose(p->mask_w, ws.Wt, S * N, Sc, st));
   CTN_TRY(gemm_raw(c, ws, ws.Wt, Sc, S * N, ws.dwhat, ws.dsp, B, frames, pitch, st));
@@ -799,11 +922,12 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
     k_act_norm<<<grid_cb(H, B), 256, 0, st>>>(ws.upre[i], ws.T1, q.prelu2, q.norm2_g, q.norm2_b, st2, nH, c->eps_tcn, H, frames, pitch);
     LAUNCH_CHECK();
     if (has_out) {
-      CTN_TRY(wgrad(dY, dY_bs, ws.T1, bsH, G(gq.out_w), Bc, H, B, frames, pitch, st));
+      CTN_TRY(wgrad(c, dY, dY_bs, ws.T1, bsH, G(gq.out_w), G(gq.skip_w), Bc, Bc + Sc, H, B, frames, pitch, st));
       CTN_TRY(rowsum(dY, dY_bs, Bc, B, frames, pitch, G(gq.out_b), st));
+    } else {
+      CTN_TRY(wgrad(c, dY, dY_bs, ws.T1, bsH, G(gq.skip_w), nullptr, 0, Sc, H, B, frames, pitch, st));
     }
     const float* dYs = dY + (has_out ? bsBc : 0);
-    CTN_TRY(wgrad(dYs, dY_bs, ws.T1, bsH, G(gq.skip_w), Sc, H, B, frames, pitch, st));
     CTN_TRY(rowsum(dYs, dY_bs, Sc, B, frames, pitch, G(gq.skip_b), st));
     // d_un = [Wo; Ws]^T dY
     {
@@ -824,7 +948,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
     CTN_TRY(gln_prelu_bwd(ws.G2, ws.hpre[i], ws.G2, q.prelu1, q.norm1_g, st1, nH, c->eps_tcn, ws.sums, G(gq.norm1_g), G(gq.norm1_b),
                           G(gq.prelu1), G(gq.bottleneck_b), B, H, frames, pitch, st));
     // bottleneck 1x1: dW1 = d_h_pre x_i^T ; d_x_i = W1^T d_h_pre (+ residual path)
-    CTN_TRY(wgrad(ws.G2, bsH, ws.x[i], bsBc, G(gq.bottleneck_w), H, Bc, B, frames, pitch, st));
+    CTN_TRY(wgrad(c, ws.G2, bsH, ws.x[i], bsBc, G(gq.bottleneck_w), nullptr, 0, H, Bc, B, frames, pitch, st));
     CTN_TRY(transpose(q.bottleneck_w, ws.Wt, H, Bc, st));
     CTN_TRY(gemm_raw(c, ws, ws.Wt, Bc, H, ws.G2, ws.dxtmp, B, frames, pitch, st));
     k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dcat, bsCat, ws.dxtmp, bsBc, Bc, has_out ? 1 : 0, frames, pitch);
@@ -834,7 +958,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
   k_act_norm<<<grid_cb(N, B), 256, 0, st>>>(ws.w, ws.nA, nullptr, p->norm0_g, p->norm0_b, ws.stats0, (double)N * frames, c->eps, N,
                                             frames, pitch);
   LAUNCH_CHECK();
-  CTN_TRY(wgrad(ws.dcat, bsCat, ws.nA, bsN, G(grads->bn_w), Bc, N, B, frames, pitch, st));
+  CTN_TRY(wgrad(c, ws.dcat, bsCat, ws.nA, bsN, G(grads->bn_w), nullptr, 0, Bc, N, B, frames, pitch, st));
   CTN_TRY(rowsum(ws.dcat, bsCat, Bc, B, frames, pitch, G(grads->bn_b), st));
   // d_wn = Wb^T d_x0 (the operand of the contraction must be dense (B, K, pitch): copy the rows out of dcat)
   k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dxtmp, bsBc, ws.dcat, bsCat, Bc, 0, frames, pitch);
@@ -847,7 +971,6 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
   k_dw_combine<<<grid_cb(N, B), 256, 0, st>>>(ws.nB, ws.nC, ws.w, c->enc_relu, N, frames, pitch);
   LAUNCH_CHECK();
   // ---- encoder (filterbank.py:212,222): dWe
-  k_encdec_wgrad<<<dim3(L, N), 256, 0, st>>>(ws.nB, x, G(grads->enc_w), B, N, frames, pitch, T, L, c->stride, pl);
-  LAUNCH_CHECK();
+  CTN_TRY(encdec_wgrad(ws.nB, x, G(grads->enc_w), B, N, frames, pitch, T, L, c->stride, pl, st));
   return CTN_OK;
 }
