@@ -40,6 +40,7 @@ struct PwArgs {
   double n_in;             // EPI_HEAD: element count of a gLN group of the input
   float eps;               // EPI_HEAD
   double* stats_out;       // EPI_H: (B,2) += (sum, sumsq) over valid outputs
+  int store_pre;           // EPI_H (tcgen05 path only): store W A + bias (pre-activation) instead of PReLU(.); stats unchanged
   const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
   int Nb;                  // EPI_MASK: n_basis
   float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)

@@ -328,13 +328,16 @@ __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre,
                                                 float* __restrict__ dhn, const float* __restrict__ slope1,
                                                 const float* __restrict__ g1, const float* __restrict__ b1,
                                                 const double* __restrict__ stats1, double n1, float eps,
-                                                const float* __restrict__ wd, float* __restrict__ dwd, int C, int frames,
-                                                int pitch, int P, int dil, int pad_left) {
+                                                const float* __restrict__ wd, float* __restrict__ dwd,
+                                                double* __restrict__ sums, float* __restrict__ dgamma,
+                                                float* __restrict__ dbeta, int C, int frames, int pitch, int P, int dil,
+                                                int pad_left) {
   __shared__ double red[64];
   const int c = blockIdx.x, b = blockIdx.y;
   const float a1 = slope1[0];
   const float2 mr = gln_mean_rstd(stats1 + 2 * b, n1, eps);
   const float gsc = g1[c] * mr.y, gsh = b1[c] - mr.x * mr.y * g1[c];
+  float s0 = 0.f, s1 = 0.f;  // phase 1 of the gLN1 backward on the d_hn this kernel produces (saves a pass over d_hn and h)
   const float* du = dupre + ((size_t)b * C + c) * pitch;
   const float* h = hpre + ((size_t)b * C + c) * pitch;
   float* o = dhn + ((size_t)b * C + c) * pitch;
@@ -361,8 +364,24 @@ __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre,
         }
       }
       v = mask4(v, t, frames);
+      const float4 hc = prelu4(ld4(h + t), a1);
+      const float4 xh = make_float4((hc.x - mr.x) * mr.y, (hc.y - mr.x) * mr.y, (hc.z - mr.x) * mr.y, (hc.w - mr.x) * mr.y);
+      s0 += sum4(v);
+      s1 += dot4(v, xh);  // v is zero in the pad lanes
     }
     st4(o + t, v);
+  }
+  {
+    double ds0 = s0, ds1 = s1;
+    block_sum2_d(ds0, ds1, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&dbeta[c], (float)ds0);
+      atomicAdd(&dgamma[c], (float)ds1);
+      const double gc = (double)g1[c];
+      atomicAdd(&sums[2 * b], gc * ds0);
+      atomicAdd(&sums[2 * b + 1], gc * ds1);
+    }
+    __syncthreads();
   }
   for (int k = 0; k < P; k += 2) {
     double x0 = acc[k], x1 = (k + 1 < P) ? acc[k + 1] : 0.0;
@@ -472,13 +491,26 @@ __global__ void __launch_bounds__(256) k_encdec_wgrad(const float* __restrict__ 
   for (int k = 0; k < ENCDEC_MAX_L; ++k) acc[k] = 0.f;
   if (threadIdx.x < ENCDEC_MAX_L) sacc[threadIdx.x] = 0.f;
   __syncthreads();
+  const bool vec = (L % 4 == 0) && (stride % 4 == 0) && (pad_left % 4 == 0) && (T % 4 == 0) && ((((uintptr_t)sig) & 15) == 0);
   for (int r = blockIdx.y; r < R; r += gridDim.y) {
     const float* a = act + ((size_t)r * N + n) * pitch;
     const float* sg = sig + (size_t)r * T;
     for (int f = threadIdx.x; f < frames; f += 256) {
       const float av = a[f];
       const int t0 = f * stride - pad_left;
-      if (t0 >= 0 && t0 + L <= T) {
+      if (t0 >= 0 && t0 + L <= T && vec) {
+        // 128-bit loads of the window (a warp's windows are 4*stride bytes apart: 4x fewer L1 wavefronts than scalar)
+#pragma unroll
+        for (int k4 = 0; k4 < ENCDEC_MAX_L / 4; ++k4) {
+          if (k4 * 4 < L) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(sg + t0) + k4);
+            acc[k4 * 4 + 0] = fmaf(av, q.x, acc[k4 * 4 + 0]);
+            acc[k4 * 4 + 1] = fmaf(av, q.y, acc[k4 * 4 + 1]);
+            acc[k4 * 4 + 2] = fmaf(av, q.z, acc[k4 * 4 + 2]);
+            acc[k4 * 4 + 3] = fmaf(av, q.w, acc[k4 * 4 + 3]);
+          }
+        }
+      } else if (t0 >= 0 && t0 + L <= T) {
 #pragma unroll
         for (int k = 0; k < ENCDEC_MAX_L; ++k)
           if (k < L) acc[k] = fmaf(av, sg[t0 + k], acc[k]);
@@ -752,11 +784,13 @@ int rowsum(const float* dy, size_t bs, int C, int B, int frames, int pitch, floa
 // gLN (+ optional PReLU in front) backward: dy (B,C,pitch) -> dpre (may alias dy); accumulates dgamma, dbeta, dslope, dbias
 int gln_prelu_bwd(const float* dy, const float* pre, float* dpre, const float* slope, const float* g, const double* stats,
                   double n, float eps, double* sums, float* dgamma, float* dbeta, float* dslope, float* dbias, int B, int C,
-                  int frames, int pitch, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st);
-  if (e != cudaSuccess) return (int)e;
-  k_gln_bwd_reduce<<<dim3(C, B), 256, 0, st>>>(dy, pre, slope, g, stats, n, eps, sums, dgamma, dbeta, C, frames, pitch);
-  LAUNCH_CHECK();
+                  int frames, int pitch, cudaStream_t st, bool reduced = false) {
+  if (!reduced) {  // phase 1 (skipped when the producer of dy already accumulated sums / dgamma / dbeta)
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st);
+    if (e != cudaSuccess) return (int)e;
+    k_gln_bwd_reduce<<<dim3(C, B), 256, 0, st>>>(dy, pre, slope, g, stats, n, eps, sums, dgamma, dbeta, C, frames, pitch);
+    LAUNCH_CHECK();
+  }
   k_gln_prelu_bwd_apply<<<dim3(C, B), 256, 0, st>>>(dy, pre, dpre, slope, g, stats, n, eps, sums, dslope, dbias, C, frames, pitch);
   LAUNCH_CHECK();
   return CTN_OK;
@@ -824,9 +858,19 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
     double* st1 = ws.stats + (size_t)(2 * i) * B * 2;
     double* st2 = ws.stats + (size_t)(2 * i + 1) * B * 2;
     // h_pre = W1 x + b1 ; stats1 of PReLU(h_pre)
-    CTN_TRY(gemm_raw(c, ws, q.bottleneck_w, H, Bc, ws.x[i], ws.hpre[i], B, frames, pitch, st));
-    k_bias_prelu_stats<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], q.bottleneck_b, q.prelu1, st1, H, frames, pitch);
-    LAUNCH_CHECK();
+    if (c->math == CTN_MATH_FP32) {
+      CTN_TRY(gemm_raw(c, ws, q.bottleneck_w, H, Bc, ws.x[i], ws.hpre[i], B, frames, pitch, st));
+      k_bias_prelu_stats<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], q.bottleneck_b, q.prelu1, st1, H, frames, pitch);
+      LAUNCH_CHECK();
+    } else {  // bias, PReLU statistics fused into the contraction's epilogue; the PRE-activation is what gets stored
+      PwArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = ws.x[i]; a.W = q.bottleneck_w; a.D = ws.hpre[i]; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
+      a.bias = q.bottleneck_b; a.slope = q.prelu1; a.stats_out = st1; a.store_pre = 1;
+      CTN_TRY(ctn_umma_build_wimg(q.bottleneck_w, H, Bc, c->math, ws.wimg, st));
+      a.wimg = ws.wimg;
+      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_H, c->math, st));
+    }
     // u_pre = dwconv(gLN1(PReLU(h_pre))) + bd ; stats2 of PReLU(u_pre)
     k_dw_train_fwd<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], ws.upre[i], q.norm1_g, q.norm1_b, q.dw_w, q.dw_b, q.prelu1, q.prelu2,
                                                   st1, st2, H, frames, pitch, c->sep_kernel, dil, pad_left, nH, c->eps_tcn);
@@ -940,13 +984,18 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
     // gLN2 + PReLU2 backward -> d_u_pre (G1 in place); dgamma2, dbeta2, da2, d(bd)
     CTN_TRY(gln_prelu_bwd(ws.G1, ws.upre[i], ws.G1, q.prelu2, q.norm2_g, st2, nH, c->eps_tcn, ws.sums, G(gq.norm2_g), G(gq.norm2_b),
                           G(gq.prelu2), G(gq.dw_b), B, H, frames, pitch, st));
-    // depthwise conv backward -> d_hn (G2), d(wd)
+    // depthwise conv backward -> d_hn (G2), d(wd); fused: phase 1 of the gLN1 backward (per-sample sums, dgamma1, dbeta1)
+    {
+      cudaError_t e = cudaMemsetAsync(ws.sums, 0, sizeof(double) * 2 * B, st);
+      if (e != cudaSuccess) return (int)e;
+    }
     k_dw_bwd<<<dim3(H, B), 256, 0, st>>>(ws.G1, ws.hpre[i], ws.G2, q.prelu1, q.norm1_g, q.norm1_b, st1, nH, c->eps_tcn, q.dw_w,
-                                         G(gq.dw_w), H, frames, pitch, c->sep_kernel, dil, pad_left);
+                                         G(gq.dw_w), ws.sums, G(gq.norm1_g), G(gq.norm1_b), H, frames, pitch, c->sep_kernel, dil,
+                                         pad_left);
     LAUNCH_CHECK();
-    // gLN1 + PReLU1 backward -> d_h_pre (G2 in place); dgamma1, dbeta1, da1, db1
+    // gLN1 + PReLU1 backward, phase 2 -> d_h_pre (G2 in place); da1, db1
     CTN_TRY(gln_prelu_bwd(ws.G2, ws.hpre[i], ws.G2, q.prelu1, q.norm1_g, st1, nH, c->eps_tcn, ws.sums, G(gq.norm1_g), G(gq.norm1_b),
-                          G(gq.prelu1), G(gq.bottleneck_b), B, H, frames, pitch, st));
+                          G(gq.prelu1), G(gq.bottleneck_b), B, H, frames, pitch, st, /*reduced=*/true));
     // bottleneck 1x1: dW1 = d_h_pre x_i^T ; d_x_i = W1^T d_h_pre (+ residual path)
     CTN_TRY(wgrad(c, ws.G2, bsH, ws.x[i], bsBc, G(gq.bottleneck_w), nullptr, 0, H, Bc, B, frames, pitch, st));
     CTN_TRY(transpose(q.bottleneck_w, ws.Wt, H, Bc, st));

@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     // in flight while the current chunk is transformed and stored (one coalesced 128-byte row segment per warp-store).
     float eslope = 0.f;
     if (EPI == EPI_H) eslope = a.slope[0];
+    const bool store_pre = EPI == EPI_H && a.store_pre != 0;  // training forward: keep the PRE-activation, statistics of PReLU(.)
     float* sp = reinterpret_cast<float*>(smem + SMEM_PARAMS);  // [256] per-channel epilogue parameter
     const int egroup = (EGROUPS == 2 && warp >= 13) ? 1 : 0;                     // second warpgroup handles the upper half of the columns
     const int te = (warp & 3) * 32 + lane;                     // time step within the tile == TMEM lane
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           float v = __uint_as_float(buf[j]);
           mk[j] = 0.f;
           if (EPI == EPI_HEAD) v = fmaf(mscale, v, pv[j]);
-          if (EPI == EPI_H) v = prelu_f(v + pv[j], eslope);
+          if (EPI == EPI_H) v = store_pre ? v + pv[j] : prelu_f(v + pv[j], eslope);
           if (EPI == EPI_MASK) {
             mk[j] = __fdividef(1.f, 1.f + __expf(-(v + pv[j])));
             v = mk[j] * wv[j];
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           for (int j = 0; j < 16; ++j) {
             *q = o[j];
             q += a.pitch;
-            if (EPI == EPI_H) { ls += o[j]; lss = fmaf(o[j], o[j], lss); }
+            if (EPI == EPI_H) { const float sv = store_pre ? prelu_f(o[j], eslope) : o[j]; ls += sv; lss = fmaf(sv, sv, lss); }
           }
           if (EPI == EPI_MASK && qm) {
 #pragma unroll
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
                 q[(size_t)j * a.pitch] = v;
                 if (EPI == EPI_MASK && qm) qm[(size_t)j * a.pitch] = tvalid ? mk[j] : 0.f;
               }
-              if (EPI == EPI_H) { ls += v; lss = fmaf(v, v, lss); }
+              if (EPI == EPI_H) { const float sv = store_pre ? prelu_f(v, eslope) : v; ls += sv; lss = fmaf(sv, sv, lss); }
             }
           }
         }

@@ -12,8 +12,8 @@
 // (hi = x rounded to 10 mantissa bits, lo = x - hi exact; D += hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).
 //
 // Warp roles (672 threads): warps 0-3 epilogue (idle until the end), warp 4 TMEM allocator + MMA issuer, warps 5-20
-// producers (global 128-bit loads -> split -> swizzled st.shared; a warp moves 4 rows x 128 B per instruction, the loads
-// of the next stage are in flight while the current one is split and stored).
+// producers in two groups that take alternate stages (global 128-bit loads -> split -> swizzled st.shared; a warp moves
+// 4 rows x 128 B per instruction; the loads of a group's next stage are in flight for two stage periods).
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
 #include <stdlib.h>
@@ -25,7 +25,6 @@ constexpr int WG_THREADS = 21 * 32;
 constexpr int WG_PW = 16;            // producer warps
 constexpr int WG_KT = 32;            // time steps per stage
 constexpr int WG_A_BYTES = 128 * 128;  // 128 rows x 128 B per precision
-constexpr int WG_MAXG = 6;           // 4-row groups per producer warp and stage: (128 + 256) / 4 / 16
 constexpr int WG_HEADER = 1024;
 constexpr int WG_MAX_STAGES = 4;
 
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_umma(const WgArgs g) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), WG_PW);
+      ptx::mbar_init(ptx::smem_u32(&hdr->full[s]), WG_PW / 2);  // one group of 8 producer warps fills a stage
       ptx::mbar_init(ptx::smem_u32(&hdr->empty[s]), 1);
     }
     ptx::mbar_init(ptx::smem_u32(&hdr->done), 1);
@@ -82,35 +81,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_umma(const WgArgs g) {
 
   if (warp >= 5) {
     // ===================================== PRODUCERS ========================================================
+    // Two groups of 8 warps take alternate steps (group = step parity): a warp issues the loads of its NEXT step right
+    // after storing the current one, two step periods before they are needed, so the global-load latency (1.5-3 us
+    // under load: 128-byte row segments) hides behind a full extra step without a second register buffer.
     const int pw = warp - 5;
-    const int groups = 32 + g.n_tile / 4;  // 4-row groups per stage: 32 of dY, n_tile/4 of X
+    const int grp = pw & 1, pwl = pw >> 1;   // group, warp within the group (0..7)
     const int r4 = lane >> 3, ch = lane & 7;
-    // group gi = pw + 16*i of this warp: i < 2 <=> gi < 32 <=> a dY group (compile-time per i); per group keep the element
-    // offset of this lane's 4 samples inside a sample (0xffffffff = row outside the tensor -> zeros) and the smem offset
-    uint32_t roff[WG_MAXG], off_hi[WG_MAXG];
-#pragma unroll
-    for (int i = 0; i < WG_MAXG; ++i) {
-      const int gi = pw + WG_PW * i;
-      const bool isA = i < 2;
-      roff[i] = 0xffffffffu; off_hi[i] = 0;
-      if (gi < groups) {
-        const int row = (isA ? gi : gi - 32) * 4 + r4;
-        const int grow = (isA ? m0 : n0) + row;
-        if (isA ? grow < g.M : grow < g.K) roff[i] = (uint32_t)grow * (uint32_t)g.pitch + (uint32_t)(ch * 4);
-        off_hi[i] = (isA ? 0u : b_off) + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-      }
-    }
-    auto load = [&](long long step, float4 (&v)[WG_MAXG]) {
+    // row groups of this warp in a step: gi = pwl + 8*i, i < 4 -> dY rows (gi < 32), i >= 4 -> X rows; rows advance by 32
+    // per i, so global offsets advance by 32*pitch and shared-memory offsets by 4096 bytes (row & 7 is invariant)
+    const int rowA = pwl * 4 + r4;                       // first dY row of this lane (i = 0)
+    const uint32_t sw = (uint32_t)(rowA & 7);
+    const uint32_t offA0 = (uint32_t)(rowA >> 3) * 1024u + sw * 128u + (uint32_t)((ch ^ sw) << 4);
+    const uint32_t offB0 = b_off + offA0;                // same lane pattern inside the X operand
+    const int nB = g.n_tile / 32;                        // X row groups of 32 rows per step (<= 8)
+    constexpr int NG = 12;                               // 4 dY + up to 8 X groups of 32 rows
+    auto load = [&](long long step, float4 (&v)[NG]) {
       const int b = (int)(step / g.chunks), t0 = (int)(step % g.chunks) * WG_KT;
       const int t = t0 + ch * 4;
-      const float* pa = g.dy + (size_t)b * g.dy_bs + t0;
-      const float* pb = g.x + (size_t)b * g.x_bs + t0;
+      const float* pa = g.dy + (size_t)b * g.dy_bs + (size_t)(m0 + rowA) * g.pitch + t;
+      const float* pb = g.x + (size_t)b * g.x_bs + (size_t)(n0 + rowA) * g.pitch + t;
+      const bool tail = t + 3 >= g.frames;
 #pragma unroll
-      for (int i = 0; i < WG_MAXG; ++i) {
+      for (int i = 0; i < NG; ++i) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (roff[i] != 0xffffffffu) {
-          q = __ldg(reinterpret_cast<const float4*>((i < 2 ? pa : pb) + roff[i]));
-          if (t + 3 >= g.frames) {  // pad columns never contribute
+        const bool isA = i < 4;
+        const int j = isA ? i : i - 4;
+        const bool ok = isA ? (m0 + rowA + 32 * j < g.M) : (j < nB && n0 + rowA + 32 * j < g.K);
+        if (ok) {
+          q = __ldg(reinterpret_cast<const float4*>((isA ? pa : pb) + (size_t)(32 * j) * g.pitch));
+          if (tail) {  // pad columns never contribute
             if (t + 0 >= g.frames) q.x = 0.f;
             if (t + 1 >= g.frames) q.y = 0.f;
             if (t + 2 >= g.frames) q.z = 0.f;
@@ -120,35 +119,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_umma(const WgArgs g) {
         v[i] = q;
       }
     };
-    float4 cur[WG_MAXG], nxt[WG_MAXG];
-    load(s0, cur);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < nsteps; ++it) {
-      if (it + 1 < nsteps) load(s0 + it + 1, nxt);
+    float4 cur[NG];
+    if (grp < nsteps) load(s0 + grp, cur);
+    for (int it = grp; it < nsteps; it += 2) {
+      const int s = it % g.stages;
+      const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
       ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
       uint8_t* st = smem + WG_HEADER + (size_t)s * g.stage_bytes;
 #pragma unroll
-      for (int i = 0; i < WG_MAXG; ++i) {
-        if (pw + WG_PW * i < groups) {
+      for (int i = 0; i < NG; ++i) {
+        const bool isA = i < 4;
+        const int j = isA ? i : i - 4;
+        if (isA || j < nB) {
           const float4 x = cur[i];
           float4 hi, lo;
           hi.x = ptx::hi_tf32(x.x); hi.y = ptx::hi_tf32(x.y); hi.z = ptx::hi_tf32(x.z); hi.w = ptx::hi_tf32(x.w);
-          *reinterpret_cast<float4*>(st + off_hi[i]) = hi;
+          const uint32_t off = (isA ? offA0 : offB0) + (uint32_t)j * 4096u;
+          *reinterpret_cast<float4*>(st + off) = hi;
           if (NPASS == 3) {
             lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
             // the lo plane of an operand sits right behind its hi plane
-            const uint32_t plane = i < 2 ? (uint32_t)WG_A_BYTES : g.n_tile * 128u;
-            *reinterpret_cast<float4*>(st + off_hi[i] + plane) = lo;
+            *reinterpret_cast<float4*>(st + off + (isA ? (uint32_t)WG_A_BYTES : g.n_tile * 128u)) = lo;
           }
         }
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
-#pragma unroll
-      for (int i = 0; i < WG_MAXG; ++i) cur[i] = nxt[i];
-      if (++s == g.stages) { s = 0; ph ^= 1u; }
+      if (it + 2 < nsteps) load(s0 + it + 2, cur);
     }
   } else if (warp == 4) {
     // ===================================== MMA ISSUER =======================================================
@@ -243,7 +241,7 @@ int ctn_wgrad_umma(const float* dy, size_t dy_bs, const float* x, size_t x_bs, f
   memset(&g, 0, sizeof(g));
   g.dy = dy; g.dy_bs = dy_bs; g.x = x; g.x_bs = x_bs; g.dWa = dWa; g.dWb = dWb; g.split_row = dWb ? split_row : M;
   g.M = M; g.K = K; g.B = B; g.frames = frames; g.pitch = pitch;
-  g.n_tile = K >= 256 ? 256 : ((K + 15) / 16) * 16;
+  g.n_tile = K >= 256 ? 256 : ((K + 31) / 32) * 32;  // the producers stage X in groups of 32 rows
   g.tiles_n = (K + g.n_tile - 1) / g.n_tile;
   g.tiles = ((M + 127) / 128) * g.tiles_n;
   g.chunks = (frames + WG_KT - 1) / WG_KT;
