@@ -104,6 +104,7 @@ struct TcnWs {
   std::vector<float*> rblk;          // per block: raw [out;skip] contraction output r_i (B, Bc+Sc, pitch), kept for the
                                      // deferred skip reduction (the skip accumulator is written once, at the end)
   float *x, *skip, *h, *u, *outraw;
+  void* causal_ws;  // causal (cLN) models: scratch of the un-fused pipeline (ctn_causal.cu)
   float* xalt;  // second residual-stream buffer (tcgen05 modes ping-pong x between blocks: the update is fused into pw1)
   size_t stats_bytes;
 };
@@ -113,7 +114,6 @@ static int check_tcn_cfg(const ctn_config_t* c) {
   if (c->bottleneck <= 0 || c->hidden <= 0 || c->skip <= 0 || c->sep_kernel <= 0 || c->num_blocks <= 0 || c->num_layers <= 0)
     return CTN_EINVAL;
   if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
-  if (c->causal) return CTN_EUNSUPPORTED;  // cLN inside the fused path: not built yet (module-level ctn_cln_fwd exists)
   if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
   return CTN_OK;
 }
@@ -143,7 +143,12 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
   ws->u = cv.take<float>(bp * c->hidden);
   ws->outraw = nullptr;
   ws->rblk.assign(RX, nullptr);
-  for (int i = 0; i < RX; ++i) ws->rblk[i] = cv.take<float>(bp * Mt);
+  ws->causal_ws = nullptr;
+  if (c->causal) {
+    ws->causal_ws = cv.take<char>(ctn_causal_ws_bytes(c, B, pitch));
+  } else {
+    for (int i = 0; i < RX; ++i) ws->rblk[i] = cv.take<float>(bp * Mt);
+  }
 }
 
 static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
@@ -155,6 +160,8 @@ static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t
 static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnWs* ws, int B, int frames, int pitch,
                    cudaStream_t st) {
   const int R = c->num_blocks, X = c->num_layers, Bc = c->bottleneck, H = c->hidden, Sc = c->skip;
+  if (c->causal)  // cLN: cumulative statistics -> un-fused pipeline in the reference's operation order
+    return ctn_causal_tcn(c, blocks, ws->x, ws->skip, ws->h, ws->u, B, frames, pitch, ws->causal_ws, st);
   // weight preparation for all blocks: gLN2 folding, then (tcgen05 modes) the swizzled hi/lo operand images
   {
     StageTimer tm(CTN_ST_PREP, st);
@@ -334,23 +341,33 @@ extern "C" int ctn_workspace_bytes(const ctn_config_t* cfg, int batch, int T, si
 static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* ws, int B, int frames, int pitch,
                          float* mask_out, cudaStream_t st) {
   const int N = c->n_basis, Bc = c->bottleneck, Sc = c->skip, S = c->n_sources;
-  // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371)
-  { StageTimer tm(CTN_ST_PREP, st);
-    CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st));
+  if (c->causal) {
+    // cLN0 -> bottleneck 1x1; ws->what is free until the mask kernel writes it: use it as the (B, N, pitch) scratch
+    CTN_TRY(ctn_causal_head(c, p, ws->w, ws->what, ws->tcn.x, B, frames, pitch, ws->tcn.causal_ws, st));
     if (c->math != CTN_MATH_FP32) {
-      CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, c->math, ws->wimg_head, st));
+      StageTimer tm(CTN_ST_PREP, st);
       CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
     }
+  } else {
+    // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371)
+    { StageTimer tm(CTN_ST_PREP, st);
+      CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st));
+      if (c->math != CTN_MATH_FP32) {
+        CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, c->math, ws->wimg_head, st));
+        CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
+      }
+    }
+    PwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws->w; a.W = ws->head.Wf; a.D = ws->tcn.x; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
+    a.v1 = ws->head.v1; a.v2 = ws->head.v2; a.stats_in = ws->stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
+    a.wimg = ws->wimg_head;
+    { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, c->math, st)); }
   }
-  PwArgs a;
-  memset(&a, 0, sizeof(a));
-  a.A = ws->w; a.W = ws->head.Wf; a.D = ws->tcn.x; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
-  a.v1 = ws->head.v1; a.v2 = ws->head.v2; a.stats_in = ws->stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
-  a.wimg = ws->wimg_head;
-  { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, c->math, st)); }
   // TCN (conv_tasnet.py:372)
   CTN_TRY(run_tcn(c, p->blocks, &ws->tcn, B, frames, pitch, st));
   // tail: PReLU -> mask 1x1 -> sigmoid -> * w  (conv_tasnet.py:373-376, 159-160)
+  PwArgs a;
   memset(&a, 0, sizeof(a));
   a.A = ws->tcn.skip; a.W = p->mask_w; a.D = ws->what; a.B = B; a.M = S * N; a.K = Sc; a.frames = frames; a.pitch = pitch;
   a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws->w; a.Nb = N; a.mask_out = mask_out; a.wimg = ws->wimg_mask;

@@ -99,3 +99,18 @@ int ctn_skip_reduce(const SkipJobs& jobs, double n2, float eps, float* skip, int
 
 int ctn_copy_to_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);
 int ctn_copy_from_pitch(const float* src, float* dst, int rows, int frames, int pitch, cudaStream_t st);
+
+// cLN (src/modules/norm.py:78-90) on the padded (B, C, pitch) layout, in place allowed; scratch double[B][frames][2]
+int ctn_cln_pitch_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int frames, int pitch,
+                      float eps, double* scratch, cudaStream_t st);
+
+// Causal (cLN) models: un-fused pipeline in the reference's operation order (ctn_causal.cu).  The cumulative statistics of
+// cLN depend on every earlier frame, so the gLN tricks of the fused stack (statistics from the producing epilogue, affine
+// folded into the next contraction) do not apply; each block is contraction -> cLN -> causal depthwise -> cLN -> contraction.
+size_t ctn_causal_ws_bytes(const ctn_config_t* c, int B, int pitch);
+// x: (B, Bc, pitch) block-0 input (updated in place); skip: (B, Sc, pitch) result; h, u: (B, H, pitch) scratch
+int ctn_causal_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, float* x, float* skip, float* h, float* u, int B,
+                   int frames, int pitch, void* cws, cudaStream_t st);
+// separator head for causal models: x0 = Wb cLN0(w) + bb;  tmp: (B, N, pitch) scratch
+int ctn_causal_head(const ctn_config_t* c, const ctn_params_t* p, const float* w, float* tmp, float* x0, int B, int frames,
+                    int pitch, void* cws, cudaStream_t st);

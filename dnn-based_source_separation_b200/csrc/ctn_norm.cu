@@ -60,13 +60,14 @@ extern "C" int ctn_gln_fwd(const float* x, const float* gamma, const float* beta
 }
 
 // ---- cLN: src/modules/norm.py:78-90 --------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_cln_step(const float* __restrict__ x, int C, int T, double* __restrict__ st) {
+// x rows are `pitch` floats apart (pitch == T for PyTorch-contiguous tensors, the padded pitch inside the fused forward)
+__global__ void __launch_bounds__(128) k_cln_step(const float* __restrict__ x, int C, int T, int pitch, double* __restrict__ st) {
   const int b = blockIdx.y, t = blockIdx.x * 128 + threadIdx.x;
   if (t >= T) return;
-  const float* xb = x + (size_t)b * C * T + t;
+  const float* xb = x + (size_t)b * C * pitch + t;
   double s = 0.0, ss = 0.0;
   for (int c = 0; c < C; ++c) {
-    const double v = (double)xb[(size_t)c * T];
+    const double v = (double)xb[(size_t)c * pitch];
     s += v;
     ss += v * v;
   }
@@ -113,36 +114,46 @@ __global__ void __launch_bounds__(1024) k_cln_scan(double* __restrict__ st, int 
   }
 }
 
-__global__ void __launch_bounds__(128) k_cln_apply(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                   const float* __restrict__ beta, float* __restrict__ y, int C, int T,
+// y may alias x.  Columns [T, pitch) of y are written as zero (padded layout).
+__global__ void __launch_bounds__(128) k_cln_apply(const float* x, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float* y, int C, int T, int pitch,
                                                    float eps, const double* __restrict__ st) {
   const int b = blockIdx.z, t = blockIdx.x * 128 + threadIdx.x;
-  if (t >= T) return;
+  if (t >= pitch) return;
+  if (t >= T) {
+    for (int c = blockIdx.y; c < C; c += gridDim.y) y[((size_t)b * C + c) * pitch + t] = 0.f;
+    return;
+  }
   const double n = (double)C * (double)(t + 1);
   const double mean = st[((size_t)b * T + t) * 2] / n;
   double var = st[((size_t)b * T + t) * 2 + 1] / n - mean * mean;
   var = var > 0.0 ? var : 0.0;  // the reference can go NaN here; we clamp
   const float m = (float)mean, inv = 1.f / ((float)sqrt(var) + eps);  // eps OUTSIDE the sqrt (norm.py:90)
   for (int c = blockIdx.y; c < C; c += gridDim.y) {
-    const size_t i = ((size_t)b * C + c) * T + t;
+    const size_t i = ((size_t)b * C + c) * pitch + t;
     y[i] = (x[i] - m) * inv * gamma[c] + beta[c];
   }
+}
+
+// internal: cLN on a (B, C, pitch) tensor with `frames` valid columns (in place allowed); scratch double[B][frames][2]
+int ctn_cln_pitch_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int frames, int pitch,
+                      float eps, double* scratch, cudaStream_t st) {
+  k_cln_step<<<dim3((frames + 127) / 128, B), 128, 0, st>>>(x, C, frames, pitch, scratch);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  k_cln_scan<<<B, 1024, 0, st>>>(scratch, frames);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  int gy = C < 64 ? C : 64;
+  k_cln_apply<<<dim3((pitch + 127) / 128, gy, B), 128, 0, st>>>(x, gamma, beta, y, C, frames, pitch, eps, scratch);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
 }
 
 extern "C" int ctn_cln_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T,
                            float eps, double* scratch, ctn_stream_t stream) {
   LaunchScope scope;
   if (!x || !gamma || !beta || !y || !scratch || B <= 0 || C <= 0 || T <= 0) return CTN_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
-  k_cln_step<<<dim3((T + 127) / 128, B), 128, 0, st>>>(x, C, T, scratch);
-  CTN_COUNT_LAUNCH();
-  CTN_RETURN_IF_CUDA_ERR();
-  k_cln_scan<<<B, 1024, 0, st>>>(scratch, T);
-  CTN_COUNT_LAUNCH();
-  CTN_RETURN_IF_CUDA_ERR();
-  int gy = C < 64 ? C : 64;
-  k_cln_apply<<<dim3((T + 127) / 128, gy, B), 128, 0, st>>>(x, gamma, beta, y, C, T, eps, scratch);
-  CTN_COUNT_LAUNCH();
-  CTN_RETURN_IF_CUDA_ERR();
-  return CTN_OK;
+  return ctn_cln_pitch_fwd(x, gamma, beta, y, B, C, T, T, eps, scratch, (cudaStream_t)stream);
 }

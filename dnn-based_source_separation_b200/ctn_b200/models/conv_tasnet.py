@@ -9,8 +9,8 @@ bottleneck 1x1 -> R*X fused residual blocks -> PReLU + mask 1x1 + sigmoid + (w *
 the crop fused.  Internally activations are (batch, channels, pitch) fp32 with pitch = frames rounded up to 128.
 
 Kernel envelope (anything else raises NotImplementedError, there is no eager fallback): enc_basis = dec_basis =
-'trainable', in_channels = 1, 3-D input, dilated, separable, sep_nonlinear='prelu', sep_norm, mask_nonlinear='sigmoid',
-causal=False.
+'trainable', in_channels = 1, 3-D input, dilated, separable, sep_nonlinear='prelu', sep_norm, mask_nonlinear='sigmoid'.
+causal=False (gLN) runs the fused stack; causal=True (cLN) an un-fused pipeline (forward only, csrc/ctn_causal.cu).
 """
 import ctypes as C
 

@@ -8,7 +8,8 @@ one C call (ctn_tcn_fwd) that runs, per residual block,
     1x1 conv (+bias, PReLU, gLN statistics)  ->  gLN-apply + dilated depthwise conv + PReLU (+ statistics)
       ->  [output;skip] 1x1 convs with the second gLN folded into the weights  ->  residual / skip accumulation.
 
-Kernel envelope: dilated=True, separable=True, nonlinear='prelu', norm=True, causal=False (gLN).  Anything else
+Kernel envelope: dilated=True, separable=True, nonlinear='prelu', norm=True; causal=False (gLN, fused stack) or
+causal=True (cLN, un-fused forward pipeline).  Anything else
 raises NotImplementedError -- there is no eager fallback.
 """
 import ctypes as C

@@ -74,9 +74,12 @@ def test_workspace_bytes_and_envelope():
     # per-sample activations at pitch 4096: w(512)+what(1024)+x(128)+skip(128)+h(512)+u(512) rows + 24 blocks x r(256)
     rows = 512 + 1024 + 128 + 128 + 512 + 512 + 24 * 256
     assert b32 >= 32 * rows * 4096 * 4
-    for bad in (dict(causal=1), dict(mask_softmax=1)):
-        cb = _cfg(**bad)
-        assert N.ctn_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
+    cb = _cfg(mask_softmax=1)
+    assert N.ctn_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
+    cc = _cfg(causal=1)   # cLN models: forward built (un-fused pipeline), training path not
+    assert N.ctn_workspace_bytes(C.byref(cc), 1, 32000, C.byref(need)) == 0 and need.value > 0
+    assert N.ctn_train_workspace_bytes(C.byref(cc), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
+    assert N.ctn_train_workspace_bytes(C.byref(c), 32, 32000, C.byref(need)) == 0 and 10 << 30 < need.value < 40 << 30
     cb = _cfg(kernel_size=16, stride=7)
     assert N.ctn_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == N.CTN_EINVAL
     with pytest.raises(NotImplementedError):

@@ -122,18 +122,54 @@ def test_tdcn_golden(golden_dir, mode, cls):
     torch.testing.assert_close(y.cpu(), r["y"], rtol=RTOL, atol=ATOL)
 
 
-def test_tdcn_causal_is_loud(golden_dir):
-    net = TimeDilatedConvNet(12, hidden_channels=24, skip_channels=10, num_blocks=1, num_layers=2, separable=True, causal=True,
-                             nonlinear='prelu').cuda()
-    with torch.no_grad(), pytest.raises(NotImplementedError):
-        net(torch.randn(1, 12, 50).cuda())
+@pytest.mark.parametrize("mode", MODES)
+def test_tdcn_causal_vs_oracle(mode):
+    """causal=True: cLN + all-left padding (tdcn.py:125-127; norm.py:78-90) through the un-fused cLN pipeline."""
+    cfg = O.OracleConfig(n_basis=12, sep_hidden_channels=24, sep_bottleneck_channels=12, sep_skip_channels=10, sep_num_blocks=2,
+                         sep_num_layers=3, causal=True)
+    full = O.synth_state_dict(cfg, seed=17)
+    sub = {k[len("separator.tdcn."):]: v for k, v in full.items() if k.startswith("separator.tdcn.")}
+    net = TimeDilatedConvNet(12, hidden_channels=24, skip_channels=10, kernel_size=3, num_blocks=2, num_layers=3, dilated=True,
+                             separable=True, causal=True, nonlinear='prelu', norm=True)
+    net.load_state_dict(sub, strict=True)
+    net.math = mode
+    x = torch.randn(2, 12, 333, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        y = net.cuda()(x.cuda())
+        ref = O.tdcn_fwd(x, full, "separator.tdcn.", kernel_size=3, num_blocks=2, num_layers=3, dilated=True, causal=True,
+                         nonlinear='prelu', norm=True, eps=1e-12)
+    torch.testing.assert_close(y.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_causal_model_vs_oracle(mode):
+    """whole causal Conv-TasNet vs the oracle (the golden tiny_cln minted from the reference is covered by test_model_golden)."""
+    cfg2 = O.OracleConfig(n_basis=40, kernel_size=16, sep_hidden_channels=72, sep_bottleneck_channels=24, sep_skip_channels=16,
+                          sep_num_blocks=2, sep_num_layers=4, causal=True, n_sources=3)
+    sd = O.synth_state_dict(cfg2, seed=23)
+    model = build_model(cfg2, sd, math=mode)
+    mixture, sources = O.synth_batch(2, 3, 2100, seed=24)
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        ref_out, ref_lat = O.conv_tasnet_fwd(mixture, sd, cfg2)
+        wr = torch.randn(2, 40, 301, generator=torch.Generator().manual_seed(5))
+        mask = model.separator(wr.cuda())
+        ref_mask = O.separator_fwd(wr, sd, cfg2)
+        loss_b, perm = PIT1d(NegSISDR(), 3)(out, sources.cuda(), batch_mean=False)
+    torch.testing.assert_close(out.cpu(), ref_out, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), ref_lat, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(mask.cpu(), ref_mask, rtol=RTOL, atol=ATOL)
+    ref_l, ref_p = O.pit_neg_sisdr(ref_out, sources, batch_mean=False)
+    assert torch.equal(perm.cpu(), ref_p)
+    with pytest.raises(NotImplementedError):   # the training path of causal models is not built: loud, not silent
+        model.train()(mixture.cuda())
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # whole model vs golden (reference outputs)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("name", ["tiny_gln", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
+@pytest.mark.parametrize("name", ["tiny_gln", "tiny_cln", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
 def test_model_golden(golden_dir, name, mode):
     rec = _load(golden_dir, name)
     cfg = O.OracleConfig(**rec["cfg"])
@@ -162,14 +198,6 @@ def test_model_golden(golden_dir, name, mode):
     assert abs(float(loss) - float(rec["loss"])) < 1e-4
     torch.testing.assert_close(loss_b.cpu(), rec["loss_b"], rtol=0, atol=1e-4)
     assert model.last_launches > 0
-
-
-def test_model_causal_is_loud(golden_dir):
-    rec = _load(golden_dir, "tiny_cln")
-    cfg = O.OracleConfig(**rec["cfg"])
-    model = build_model(cfg, O.synth_state_dict(cfg, seed=rec["wseed"]))
-    with torch.no_grad(), pytest.raises(NotImplementedError):
-        model(torch.randn(1, 1, 203).cuda())
 
 
 @pytest.mark.parametrize("mode", MODES)
