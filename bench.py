@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
     ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--sample-rate", type=int, default=8000, help="Hz; cfg5 of BASELINE.json is 8 s @ 16 kHz")
     ap.add_argument("--n-sources", type=int, default=2)
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=4, help="mixtures per CPU-baseline step (bounded sample)")
@@ -106,7 +107,7 @@ def cpu_reference_leg(args, steps, warmup):
     cores = os.cpu_count() or 1
     cfg = O.OracleConfig(**PAPER, causal=False, n_sources=args.n_sources)
     sd = O.synth_state_dict(cfg, seed=111)
-    T = int(args.seconds * SR)
+    T = int(args.seconds * args.sample_rate)
     mixture, sources = O.synth_batch(args.cpu_batch, args.n_sources, T, seed=111)
     # "all the host threads it can use": torch's intra-op pool saturates well below 128 threads on these tensor sizes and
     # gets SLOWER beyond that, so sweep a few team sizes on one sample and keep the fastest (reported as `cores`).
@@ -134,7 +135,7 @@ def cpu_reference_leg(args, steps, warmup):
     total = sum(times)
     value = args.cpu_batch * args.seconds * len(times) / total
     return dict(value=value, unit="audio-sec/s", cores=best_thr, threads=torch.get_num_threads(), kind="port",
-                sample=f"{args.cpu_batch} x {args.seconds:g} s @ {SR} Hz per step, {len(times)} steps (+{warmup} warm-up), "
+                sample=f"{args.cpu_batch} x {args.seconds:g} s @ {args.sample_rate} Hz per step, {len(times)} steps (+{warmup} warm-up), "
                        f"oracle/convtasnet_oracle.py fwd+PIT under no_grad, {best_thr} torch threads (fastest of {sweep}) on "
                        f"{cores} logical cores",
                 ms_per_step=1e3 * total / len(times))
@@ -189,7 +190,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    S, B, T = args.n_sources, args.batch, int(args.seconds * SR)
+    S, B, T = args.n_sources, args.batch, int(args.seconds * args.sample_rate)
 
     torch.manual_seed(111)  # reference default seed (train.sh:59); default init = the reference's default init
     model = ConvTasNet(PAPER["n_basis"], PAPER["kernel_size"], enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
@@ -355,7 +356,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32x3": "f32 via 3xTF32 split on tcgen05, fp32 accumulate", "tf32": "tf32 (single pass), fp32 accumulate"}[math_name],
         "data": "synthetic",
-        "config": {"workload": f"cfg2: Conv-TasNet {S}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN sigmoid, batch {B} x {args.seconds:g}s@8kHz per GPU, "
+        "config": {"workload": f"cfg2: Conv-TasNet {S}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN sigmoid, batch {B} x {args.seconds:g}s@{args.sample_rate // 1000}kHz per GPU, "
                                f"fwd + PIT(NegSISDR)", "global_batch": world * B, "math": math_name,
                    "l2": "per-step activation traffic (>2 GB) exceeds the 126 MB L2 many times over; no explicit flush",
                    "parallelism": f"batch shards x{world}, no data-path collective"},
