@@ -157,14 +157,26 @@ __global__ void __launch_bounds__(256) k_act_norm(const float* __restrict__ pre,
     const float* p = pre + ((size_t)b * C + c) * pitch;
     float* o = y + ((size_t)b * C + c) * pitch;
     const float gsc = g[c] * mr.y, gsh = bt[c] - mr.x * mr.y * g[c];
-    for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
-      float4 v = zero4();
-      if (t < frames) {
-        float4 x = ld4(p + t);
-        if (act) x = prelu4(x, a);
-        v = mask4(make_float4(fmaf(gsc, x.x, gsh), fmaf(gsc, x.y, gsh), fmaf(gsc, x.z, gsh), fmaf(gsc, x.w, gsh)), t, frames);
+    // 4 independent 128-bit loads in flight per thread before any of them is used (memory-level parallelism)
+    for (int tb = threadIdx.x * 4; tb < pitch; tb += 4096) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = tb + u * 1024;
+        x[u] = t < frames ? ld4(p + t) : zero4();
       }
-      st4(o + t, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = tb + u * 1024;
+        if (t >= pitch) break;
+        float4 v = zero4();
+        if (t < frames) {
+          float4 q = x[u];
+          if (act) q = prelu4(q, a);
+          v = mask4(make_float4(fmaf(gsc, q.x, gsh), fmaf(gsc, q.y, gsh), fmaf(gsc, q.z, gsh), fmaf(gsc, q.w, gsh)), t, frames);
+        }
+        st4(o + t, v);
+      }
     }
   }
 }
@@ -250,13 +262,26 @@ __global__ void __launch_bounds__(256) k_gln_bwd_reduce(const float* __restrict_
   const float* d = dy + ((size_t)b * C + c) * pitch;
   const float* p = pre + ((size_t)b * C + c) * pitch;
   float s0 = 0.f, s1 = 0.f;
-  for (int t = threadIdx.x * 4; t < frames; t += 1024) {
-    const float4 dv = mask4(ld4(d + t), t, frames);
-    float4 x = ld4(p + t);
-    if (act) x = prelu4(x, a);
-    const float4 xh = make_float4((x.x - mr.x) * mr.y, (x.y - mr.x) * mr.y, (x.z - mr.x) * mr.y, (x.w - mr.x) * mr.y);
-    s0 += sum4(dv);
-    s1 += dot4(dv, xh);  // dv is zero in the pad lanes
+  for (int tb = threadIdx.x * 4; tb < frames; tb += 4096) {
+    float4 dq[4], xq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + u * 1024;
+      dq[u] = t < frames ? ld4(d + t) : zero4();
+      xq[u] = t < frames ? ld4(p + t) : zero4();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + u * 1024;
+      if (t < frames) {
+        const float4 dv = mask4(dq[u], t, frames);
+        float4 x = xq[u];
+        if (act) x = prelu4(x, a);
+        const float4 xh = make_float4((x.x - mr.x) * mr.y, (x.y - mr.x) * mr.y, (x.z - mr.x) * mr.y, (x.w - mr.x) * mr.y);
+        s0 += sum4(dv);
+        s1 += dot4(dv, xh);  // dv is zero in the pad lanes
+      }
+    }
   }
   double ds0 = s0, ds1 = s1;
   block_sum2_d(ds0, ds1, red);
@@ -289,10 +314,21 @@ __global__ void __launch_bounds__(256) k_gln_prelu_bwd_apply(const float* dy, co
   const float* p = pre + ((size_t)b * C + c) * pitch;
   float* o = dpre + ((size_t)b * C + c) * pitch;
   float sa = 0.f, sb = 0.f;
-  for (int t = threadIdx.x * 4; t < pitch; t += 1024) {
+  for (int tb = threadIdx.x * 4; tb < pitch; tb += 4096) {
+   float4 dq[4], pq[4];
+#pragma unroll
+   for (int u = 0; u < 4; ++u) {  // all loads of the batch before the first (possibly aliasing, in-place) store
+     const int t = tb + u * 1024;
+     dq[u] = t < frames ? ld4(d + t) : zero4();
+     pq[u] = t < frames ? ld4(p + t) : zero4();
+   }
+#pragma unroll
+   for (int u = 0; u < 4; ++u) {
+    const int t = tb + u * 1024;
+    if (t >= pitch) break;
     float4 v = zero4();
     if (t < frames) {
-      const float4 dv = ld4(d + t), pv = ld4(p + t);
+      const float4 dv = dq[u], pv = pq[u];
       const float dvv[4] = {dv.x, dv.y, dv.z, dv.w}, pvv[4] = {pv.x, pv.y, pv.z, pv.w};
       float ov[4];
 #pragma unroll
@@ -311,6 +347,7 @@ __global__ void __launch_bounds__(256) k_gln_prelu_bwd_apply(const float* dy, co
       v = make_float4(ov[0], ov[1], ov[2], ov[3]);
     }
     st4(o + t, v);
+   }
   }
   double dsa = sa, dsb = sb;
   block_sum2_d(dsa, dsb, red);
@@ -332,7 +369,6 @@ __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre,
                                                 double* __restrict__ sums, float* __restrict__ dgamma,
                                                 float* __restrict__ dbeta, int C, int frames, int pitch, int P, int dil,
                                                 int pad_left) {
-  __shared__ double red[64];
   const int c = blockIdx.x, b = blockIdx.y;
   const float a1 = slope1[0];
   const float2 mr = gln_mean_rstd(stats1 + 2 * b, n1, eps);
@@ -371,26 +407,31 @@ __global__ void __launch_bounds__(256) k_dw_bwd(const float* __restrict__ dupre,
     }
     st4(o + t, v);
   }
+  // one block-wide reduction for all per-row sums: P tap gradients + the two gLN1 sums (warp shuffles, then 8 partials each)
   {
-    double ds0 = s0, ds1 = s1;
-    block_sum2_d(ds0, ds1, red);
-    if (threadIdx.x == 0) {
-      atomicAdd(&dbeta[c], (float)ds0);
-      atomicAdd(&dgamma[c], (float)ds1);
-      const double gc = (double)g1[c];
-      atomicAdd(&sums[2 * b], gc * ds0);
-      atomicAdd(&sums[2 * b + 1], gc * ds1);
+    __shared__ float part[8][CTN_MAX_P + 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < CTN_MAX_P; ++k) {
+      if (k < P) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) part[wid][k] = v;
+      }
     }
+    const float v0 = warp_sum(s0), v1 = warp_sum(s1);
+    if (lane == 0) { part[wid][CTN_MAX_P] = v0; part[wid][CTN_MAX_P + 1] = v1; }
     __syncthreads();
-  }
-  for (int k = 0; k < P; k += 2) {
-    double x0 = acc[k], x1 = (k + 1 < P) ? acc[k + 1] : 0.0;
-    block_sum2_d(x0, x1, red);
-    if (threadIdx.x == 0) {
-      atomicAdd(&dwd[c * P + k], (float)x0);
-      if (k + 1 < P) atomicAdd(&dwd[c * P + k + 1], (float)x1);
+    if (threadIdx.x < CTN_MAX_P + 2) {
+      const int k = threadIdx.x;
+      if (k < P || k >= CTN_MAX_P) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += (double)part[w][k];
+        if (k < P) atomicAdd(&dwd[c * P + k], (float)t);
+        else if (k == CTN_MAX_P) { atomicAdd(&dbeta[c], (float)t); atomicAdd(&sums[2 * b], (double)g1[c] * t); }
+        else { atomicAdd(&dgamma[c], (float)t); atomicAdd(&sums[2 * b + 1], (double)g1[c] * t); }
+      }
     }
-    __syncthreads();
   }
 }
 
