@@ -409,3 +409,35 @@ def test_tf32_fast_mode_stated_tolerance(golden_dir):
         _, perm = PIT1d(NegSISDR(), cfg.n_sources)(out, sources.cuda())
     torch.testing.assert_close(out.cpu()[..., ::rec["out_stride"]], rec["out"], rtol=2e-2, atol=5e-3)
     assert torch.equal(perm.cpu(), rec["perm"])
+
+
+def test_forward_and_loss_are_cuda_graph_capturable():
+    """The forward + PIT loss is a fixed launch sequence with no host reads: capture it once in a
+    CUDA graph, replay it on new inputs, compare with the eager calls."""
+    cfg = O.OracleConfig(n_basis=64, kernel_size=16, sep_hidden_channels=128, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=2)
+    model = build_model(cfg, O.synth_state_dict(cfg, seed=2))
+    crit = PIT1d(NegSISDR(), 2)
+    m1, s1 = O.synth_batch(3, 2, 4000, seed=5)
+    m2, s2 = O.synth_batch(3, 2, 4000, seed=6)
+    xs, ts = m1.cuda().clone(), s1.cuda().clone()
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up on the capture stream (function attributes, workspaces)
+            for _ in range(2):
+                crit(model(xs), ts, batch_mean=False)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            out_g = model(xs)
+            loss_g, perm_g = crit(out_g, ts, batch_mean=False)
+        for mix, src in ((m2, s2), (m1, s1)):
+            xs.copy_(mix.cuda()); ts.copy_(src.cuda())
+            g.replay()
+            torch.cuda.synchronize()
+            out_e = model(mix.cuda())
+            loss_e, perm_e = crit(out_e, src.cuda(), batch_mean=False)
+            torch.testing.assert_close(out_g, out_e, rtol=0, atol=1e-6)
+            torch.testing.assert_close(loss_g, loss_e, rtol=0, atol=1e-5)
+            assert torch.equal(perm_g, perm_e)
