@@ -105,16 +105,22 @@ extern "C" int ctn_encoder_fwd(const float* x, const float* enc_w, float* w, int
 // thread = output segment j (stride consecutive samples); grid (ceil(nseg/128), BS), block 128.
 // The crop of src/models/conv_tasnet.py:169 is fused: y[t] = full[t + crop_left].
 // ------------------------------------------------------------------------------------------------
+// The channel sum is split over DEC_SPLIT thread groups of a block (each walks N/DEC_SPLIT channels with its own
+// accumulators, partial sums meet in shared memory): 4x the loads in flight per SM of a thread-per-segment kernel, which
+// was latency-bound at ~1 TB/s (2048 resident threads instead of 896).
+constexpr int DEC_SPLIT = 4;
 template <int STRIDE, int R>
-__global__ void __launch_bounds__(128) k_decoder(const float* __restrict__ what, const float* __restrict__ Wd,
-                                                 float* __restrict__ y, int N, int frames, int in_pitch,
-                                                 int crop_left, int T_out) {
+__global__ void __launch_bounds__(128 * DEC_SPLIT) k_decoder(const float* __restrict__ what, const float* __restrict__ Wd,
+                                                             float* __restrict__ y, int N, int frames, int in_pitch,
+                                                             int crop_left, int T_out) {
   constexpr int L = STRIDE * R;
-  extern __shared__ float sm[];  // Wd as [N][L]
+  extern __shared__ float sm[];  // Wd as [N][L], then the partial sums [DEC_SPLIT-1][STRIDE][128]
+  float* red = sm + (size_t)N * L;
   const int tid = threadIdx.x, bs = blockIdx.y;
-  for (int i = tid; i < N * L; i += 128) sm[i] = Wd[i];
+  const int seg = tid & 127, part = tid >> 7;
+  for (int i = tid; i < N * L; i += 128 * DEC_SPLIT) sm[i] = Wd[i];
   __syncthreads();
-  const int j = blockIdx.x * 128 + tid;  // segment index, 0 .. frames+R-2
+  const int j = blockIdx.x * 128 + seg;  // segment index, 0 .. frames+R-2
   const float* wb = what + (size_t)bs * N * in_pitch;
   float acc[STRIDE];
 #pragma unroll
@@ -122,7 +128,9 @@ __global__ void __launch_bounds__(128) k_decoder(const float* __restrict__ what,
   bool ok[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) ok[r] = (j - r) >= 0 && (j - r) < frames;
-  for (int n = 0; n < N; ++n) {
+  const int nper = (N + DEC_SPLIT - 1) / DEC_SPLIT;
+  const int n_begin = part * nper, n_end = min(N, n_begin + nper);
+  for (int n = n_begin; n < n_end; ++n) {
     const float* wrow = wb + (size_t)n * in_pitch;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -131,11 +139,21 @@ __global__ void __launch_bounds__(128) k_decoder(const float* __restrict__ what,
       for (int q = 0; q < STRIDE; ++q) acc[q] = fmaf(v, sm[n * L + r * STRIDE + q], acc[q]);
     }
   }
-  float* yb = y + (size_t)bs * T_out;
+  if (part > 0) {
 #pragma unroll
-  for (int q = 0; q < STRIDE; ++q) {
-    const int t = j * STRIDE + q - crop_left;
-    if (t >= 0 && t < T_out && j < frames + R - 1) yb[t] = acc[q];
+    for (int q = 0; q < STRIDE; ++q) red[((part - 1) * STRIDE + q) * 128 + seg] = acc[q];
+  }
+  __syncthreads();
+  if (part == 0) {
+    float* yb = y + (size_t)bs * T_out;
+#pragma unroll
+    for (int q = 0; q < STRIDE; ++q) {
+      float v = acc[q];
+#pragma unroll
+      for (int p2 = 0; p2 < DEC_SPLIT - 1; ++p2) v += red[(p2 * STRIDE + q) * 128 + seg];
+      const int t = j * STRIDE + q - crop_left;
+      if (t >= 0 && t < T_out && j < frames + R - 1) yb[t] = v;
+    }
   }
 }
 
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(128) k_decoder_generic(const float* __restrict
 template <int STRIDE, int R>
 static int launch_decoder(const float* what, const float* Wd, float* y, int BS, int N, int frames, int in_pitch,
                           int crop_left, int T_out, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (size_t)N * STRIDE * R;
+  const size_t smem = sizeof(float) * ((size_t)N * STRIDE * R + (size_t)(DEC_SPLIT - 1) * STRIDE * 128);
   if (smem > 200 * 1024) return CTN_EUNSUPPORTED;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_decoder<STRIDE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -170,7 +188,7 @@ static int launch_decoder(const float* what, const float* Wd, float* y, int BS, 
   }
   const int nseg = frames + R - 1;
   dim3 grid((nseg + 127) / 128, BS);
-  k_decoder<STRIDE, R><<<grid, 128, smem, st>>>(what, Wd, y, N, frames, in_pitch, crop_left, T_out);
+  k_decoder<STRIDE, R><<<grid, 128 * DEC_SPLIT, smem, st>>>(what, Wd, y, N, frames, in_pitch, crop_left, T_out);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
