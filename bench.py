@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--sample-rate", type=int, default=8000, help="Hz; cfg5 of BASELINE.json is 8 s @ 16 kHz")
     ap.add_argument("--n-sources", type=int, default=2)
-    ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32", "f16x3"])
     ap.add_argument("--cpu-batch", type=int, default=4, help="mixtures per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train", action="store_true",
@@ -198,7 +198,7 @@ def main():
                        sep_skip_channels=PAPER["sep_skip_channels"], sep_kernel_size=3, sep_num_blocks=3, sep_num_layers=8,
                        causal=False, n_sources=S).to(dev).eval()
     model.math = args.math
-    math_name = args.math or ("tf32x3" if N.ctn_has_tcgen05() else "fp32")
+    math_name = args.math or ("f16x3" if N.ctn_has_tcgen05() else "fp32")
     crit = PIT1d(NegSISDR(), S)
     g = torch.Generator().manual_seed(111 + rank)
     sources_h = (0.1 * torch.randn(B, S, T, generator=g)).pin_memory()
@@ -316,7 +316,8 @@ def main():
 
     pk = peaks()
     model_bf = stage_model(args, B, frames, T)
-    tf32_peak = pk["bf16_sustained"] / 2.0   # TF32 dense = 1/2 bf16 on tcgen05; sustained figure (kernel timed inside a long step)
+    # TF32 dense = 1/2 bf16 on tcgen05; fp16 operands (f16x3) run at the bf16 rate.  Sustained figure (kernel timed inside a long step)
+    tf32_peak = pk["bf16_sustained"] / (1.0 if math_name == "f16x3" else 2.0)
     stages = {}
     for name, (t_ms, n) in prof.items():
         if n == 0:
@@ -345,8 +346,9 @@ def main():
     if d["bound"] == "tensor":
         roof = {"kernel": dom, "bound": "tensor", "achieved": d["TFLOPs"], "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": d["TFLOPs"] / tf32_peak, "traffic": traffic,
-                "peak_note": f"TF32 dense = bf16_tflops_sustained/2 of {pk['source']}; algorithmic 2*M*N*K flops "
-                             f"(the 3-pass tf32x3 split issues 3x that on the tensor pipe)"}
+                "peak_note": (f"fp16 dense = bf16_tflops_sustained of {pk['source']}" if math_name == "f16x3" else
+                              f"TF32 dense = bf16_tflops_sustained/2 of {pk['source']}") +
+                             "; algorithmic 2*M*N*K flops (the 3-pass hi/lo split issues 3x that on the tensor pipe)"}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                 "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "peak_note": f"hbm_gbs of {pk['source']}"}
@@ -354,7 +356,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32x3": "f32 via 3xTF32 split on tcgen05, fp32 accumulate", "tf32": "tf32 (single pass), fp32 accumulate"}[math_name],
+        "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32x3": "f32 via 3xTF32 split on tcgen05, fp32 accumulate", "tf32": "tf32 (single pass), fp32 accumulate", "f16x3": "f32 via 3xFP16 split on tcgen05 (kind::f16), fp32 accumulate"}[math_name],
         "data": "synthetic",
         "config": {"workload": f"cfg2: Conv-TasNet {S}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN sigmoid, batch {B} x {args.seconds:g}s@{args.sample_rate // 1000}kHz per GPU, "
                                f"fwd + PIT(NegSISDR)", "global_batch": world * B, "math": math_name,

@@ -114,7 +114,7 @@ static int check_tcn_cfg(const ctn_config_t* c) {
   if (c->bottleneck <= 0 || c->hidden <= 0 || c->skip <= 0 || c->sep_kernel <= 0 || c->num_blocks <= 0 || c->num_layers <= 0)
     return CTN_EINVAL;
   if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
-  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
+  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32 && c->math != CTN_MATH_F16X3) return CTN_EINVAL;
   return CTN_OK;
 }
 
@@ -349,11 +349,13 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
       CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
     }
   } else {
-    // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371)
+    // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371).  Its operand is the un-normalised encoder output
+    // (any input scale), so the fp16-piece mode falls back to the tf32 pieces here (0.14 ms of the step).
+    const int head_math = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
     { StageTimer tm(CTN_ST_PREP, st);
       CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st));
       if (c->math != CTN_MATH_FP32) {
-        CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, c->math, ws->wimg_head, st));
+        CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, head_math, ws->wimg_head, st));
         CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
       }
     }
@@ -362,7 +364,7 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
     a.A = ws->w; a.W = ws->head.Wf; a.D = ws->tcn.x; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
     a.v1 = ws->head.v1; a.v2 = ws->head.v2; a.stats_in = ws->stats0; a.n_in = (double)N * (double)frames; a.eps = c->eps;
     a.wimg = ws->wimg_head;
-    { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, c->math, st)); }
+    { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, head_math, st)); }
   }
   // TCN (conv_tasnet.py:372)
   CTN_TRY(run_tcn(c, p->blocks, &ws->tcn, B, frames, pitch, st));

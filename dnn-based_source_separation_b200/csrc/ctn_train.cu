@@ -755,20 +755,24 @@ int check_train_cfg(const ctn_config_t* c) {
   if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
   if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
   if (c->causal || c->mask_softmax || c->sep_kernel > CTN_MAX_P) return CTN_EUNSUPPORTED;
-  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32) return CTN_EINVAL;
+  if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32 && c->math != CTN_MATH_F16X3) return CTN_EINVAL;
   return CTN_OK;
 }
 
 // D (B, M, pitch) = W (M, K) . A (B, K, pitch), raw epilogue, in the configured numeric mode
+// grad = true: the operand is a GRADIENT tensor.  Gradients have no fixed scale (1e-3 .. 1e-9 and below), which the fp16
+// pieces of 'f16x3' cannot represent (subnormal below 6e-5, zero below 6e-8), so data-gradient contractions always use the
+// tf32 pieces (8-bit exponent); 'f16x3' applies to the forward contractions, whose operands sit behind normalisations.
 int gemm_raw(const ctn_config_t* c, TrainWs& ws, const float* W, int M, int K, const float* A, float* D, int B, int frames,
-             int pitch, cudaStream_t st) {
+             int pitch, cudaStream_t st, bool grad = false) {
   PwArgs a;
   memset(&a, 0, sizeof(a));
   a.A = A; a.W = W; a.D = D; a.B = B; a.M = M; a.K = K; a.frames = frames; a.pitch = pitch;
   if (c->math == CTN_MATH_FP32) return ctn_pw_simt(a, PRO_NONE, EPI_RAW, st);
-  CTN_TRY(ctn_umma_build_wimg(W, M, K, c->math, ws.wimg, st));
+  const int math = (grad && c->math == CTN_MATH_F16X3) ? CTN_MATH_TF32X3 : c->math;
+  CTN_TRY(ctn_umma_build_wimg(W, M, K, math, ws.wimg, st));
   a.wimg = ws.wimg;
-  return ctn_pw_umma(a, PRO_NONE, EPI_RAW, c->math, st);
+  return ctn_pw_umma(a, PRO_NONE, EPI_RAW, math, st);
 }
 
 int transpose(const float* W, float* Wt, int M, int K, cudaStream_t st) {
@@ -884,9 +888,11 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
     if (c->math == CTN_MATH_FP32) {
       CTN_TRY(ctn_pw_simt(a, PRO_NONE, EPI_HEAD, st));
     } else {
-      CTN_TRY(ctn_umma_build_wimg(ws.head.Wf, Bc, N, c->math, ws.wimg, st));
+      // the head reads the un-normalised encoder output: tf32 pieces even in the fp16-piece mode (see ctn_api.cu)
+      const int head_math = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
+      CTN_TRY(ctn_umma_build_wimg(ws.head.Wf, Bc, N, head_math, ws.wimg, st));
       a.wimg = ws.wimg;
-      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_HEAD, c->math, st));
+      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_HEAD, head_math, st));
     }
   }
   const double nH = (double)H * (double)frames;
@@ -984,7 +990,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
   CTN_TRY(wgrad(c, ws.dwhat, bsSN, ws.sp, bsSc, G(grads->mask_w), nullptr, 0, S * N, Sc, B, frames, pitch, st));
   CTN_TRY(rowsum(ws.dwhat, bsSN, S * N, B, frames, pitch, G(grads->mask_b), st));
   CTN_TRY(transpose(p->mask_w, ws.Wt, S * N, Sc, st));
-  CTN_TRY(gemm_raw(c, ws, ws.Wt, Sc, S * N, ws.dwhat, ws.dsp, B, frames, pitch, st));
+  CTN_TRY(gemm_raw(c, ws, ws.Wt, Sc, S * N, ws.dwhat, ws.dsp, B, frames, pitch, st, /*grad=*/true));
   // ---- PReLU on the skip sum (conv_tasnet.py:340,373): dS (the gradient of EVERY block's skip output)
   k_prelu_bwd<<<dim3(Sc, B), 256, 0, st>>>(ws.dsp, ws.skip, ws.dS, p->prelu_out, G(grads->prelu_out), Sc, frames, pitch);
   LAUNCH_CHECK();
@@ -1021,7 +1027,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
       if ((e = cudaMemcpyAsync(ws.Wcat + (has_out ? (size_t)Bc * H : 0), q.skip_w, sizeof(float) * (size_t)Sc * H, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return (int)e;
     }
     CTN_TRY(transpose(ws.Wcat, ws.Wt, Mt, H, st));
-    CTN_TRY(gemm_raw(c, ws, ws.Wt, H, Mt, dY, ws.G1, B, frames, pitch, st));
+    CTN_TRY(gemm_raw(c, ws, ws.Wt, H, Mt, dY, ws.G1, B, frames, pitch, st, /*grad=*/true));
     // gLN2 + PReLU2 backward -> d_u_pre (G1 in place); dgamma2, dbeta2, da2, d(bd)
     CTN_TRY(gln_prelu_bwd(ws.G1, ws.upre[i], ws.G1, q.prelu2, q.norm2_g, st2, nH, c->eps_tcn, ws.sums, G(gq.norm2_g), G(gq.norm2_b),
                           G(gq.prelu2), G(gq.dw_b), B, H, frames, pitch, st));
@@ -1040,7 +1046,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
     // bottleneck 1x1: dW1 = d_h_pre x_i^T ; d_x_i = W1^T d_h_pre (+ residual path)
     CTN_TRY(wgrad(c, ws.G2, bsH, ws.x[i], bsBc, G(gq.bottleneck_w), nullptr, 0, H, Bc, B, frames, pitch, st));
     CTN_TRY(transpose(q.bottleneck_w, ws.Wt, H, Bc, st));
-    CTN_TRY(gemm_raw(c, ws, ws.Wt, Bc, H, ws.G2, ws.dxtmp, B, frames, pitch, st));
+    CTN_TRY(gemm_raw(c, ws, ws.Wt, Bc, H, ws.G2, ws.dxtmp, B, frames, pitch, st, /*grad=*/true));
     k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dcat, bsCat, ws.dxtmp, bsBc, Bc, has_out ? 1 : 0, frames, pitch);
     LAUNCH_CHECK();
   }
@@ -1054,7 +1060,7 @@ extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, 
   k_rows<<<grid_cb(Bc, B), 256, 0, st>>>(ws.dxtmp, bsBc, ws.dcat, bsCat, Bc, 0, frames, pitch);
   LAUNCH_CHECK();
   CTN_TRY(transpose(p->bn_w, ws.Wt, Bc, N, st));
-  CTN_TRY(gemm_raw(c, ws, ws.Wt, N, Bc, ws.dxtmp, ws.nB, B, frames, pitch, st));
+  CTN_TRY(gemm_raw(c, ws, ws.Wt, N, Bc, ws.dxtmp, ws.nB, B, frames, pitch, st, /*grad=*/true));
   // gLN0 backward -> d_w (norm path) ; + product path ; ReLU mask of the encoder if any
   CTN_TRY(gln_prelu_bwd(ws.nB, ws.w, ws.nB, nullptr, p->norm0_g, ws.stats0, (double)N * frames, c->eps, ws.sums, G(grads->norm0_g),
                         G(grads->norm0_b), nullptr, nullptr, B, N, frames, pitch, st));

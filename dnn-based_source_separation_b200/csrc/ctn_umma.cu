@@ -20,6 +20,7 @@
 // Pipelines: smem ring (full/empty mbarriers, tcgen05.commit frees a stage) and a 2-deep TMEM accumulator ring.
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -37,15 +38,17 @@ constexpr uint32_t W_LAYOUT = KS == 32 ? 2u : 4u;    // UMMA layout type of the 
 constexpr uint32_t W_SBO = KS == 32 ? 1024u : 512u;  // bytes between 8-row groups of the weight image
 constexpr int NUM_THREADS_DW = 21 * 32;   // PRO_DW kernels: 4 epilogue + 1 MMA + 16 producer warps (2 channels each)
 constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: 4 + 1 + 8 producer warps + a second epilogue warpgroup (13-16)
-constexpr int SMEM_HEADER = 2048;   // barriers + tmem pointer, then the epilogue parameter row
+constexpr int SMEM_HEADER = 3072;   // barriers + tmem pointer, the epilogue parameter row, the fp16-mode output scales
+constexpr int SMEM_SCALES = 2048;   // byte offset of float[256]: per-output-channel power-of-two scale (F16 kernels)
 constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
 
 struct UmmaArgs {
   PwArgs a;
   const float* wimg;  // [n_tiles][k_slabs][NPASS][n_tile*32] swizzled images
+  const float* oscale;  // fp16-piece mode: [n_tiles*n_tile] per-output-channel scale 2^-e (stored behind the images)
   int n_tile, n_tiles, k_slabs, t_tiles, num_items, stages;
   uint32_t stage_bytes, w_bytes;  // w_bytes: bytes per precision of a weight slab (n_tile*128)
-  uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w;
+  uint32_t idesc, lbo_a, sbo_a, lbo_w, sbo_w, a_layout, w_layout;
   int cluster, tiles_total, cluster_items, wsplit;  // 2 = CTA pair (cta_group::2 MMA, each CTA stages half of the weight slab); B*t_tiles; n_tiles*ceil(tiles/cluster)
   uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
@@ -160,9 +163,14 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
 
 // PAIR: the kernel runs as clusters of 2 CTAs driving cta_group::2 MMAs.  It is a template parameter (not a run-time
 // flag) because a kernel that contains cta_group::2 instructions can only be launched with an even cluster size.
-template <int PRO, int EPI, int NPASS, bool PAIR>
+// F16: operands are staged as fp16 hi/lo pieces (kind::f16, "3xFP16"): A MN-major SWIZZLE_128B (atoms of 64 time steps x 8
+// channels), W K-major SWIZZLE_64B (rows of 32 channels = 64 bytes) -- both pinned on hardware by tools/umma_unit_f16.cu.
+// Half the shared-memory bytes per stage (4-deep ring at N = 256) and half the tensor-pipe time of the TF32 split.
+template <int PRO, int EPI, int NPASS, bool PAIR, bool F16>
 __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
   constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
+  constexpr int A_BYTES = F16 ? TM * KS * 2 : TM * KS * 4;  // bytes of one precision of the activation slab (shadows the tf32 constant)
+  static_assert(!F16 || (NPASS == 3 && !PAIR), "fp16 operands: 3-pass split, single-CTA only");
   constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;  // epilogue warpgroups (each covers all 128 TMEM lanes)
   constexpr int PROD_WARPS = PRO == PRO_DW ? 16 : 8;
   constexpr int CPW = KS / PROD_WARPS;            // channels of a slab per producer warp (2 or 4)
@@ -353,6 +361,18 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           if (PRO == PRO_PRELU) {
             x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
           }
+          if constexpr (F16) {
+            // MN-major 16-bit SWIZZLE_128B: atoms of 64 time steps x 8 channels (1024 B): channel row r = kl & 7 at r*128 B,
+            // 16-byte chunks (8 time steps) XOR r; time atoms 1024 B apart (LBO), 8-channel groups 2048 B apart (SBO)
+            const uint32_t r8 = (uint32_t)(kl & 7);
+            const uint32_t off16 = (uint32_t)(kl >> 3) * 2048u + (uint32_t)(lane >> 4) * 1024u + r8 * 128u +
+                                   (((uint32_t)((lane & 15) >> 1) ^ r8) << 4) + (uint32_t)(lane & 1) * 8u;
+            uint2 h2, l2;
+            ptx::split_f16x2(x.x, x.y, h2.x, l2.x);
+            ptx::split_f16x2(x.z, x.w, h2.y, l2.y);
+            *reinterpret_cast<uint2*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + off16) = h2;
+            *reinterpret_cast<uint2*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off16) = l2;
+          } else {
           float4 hi, lo;
           hi.x = ptx::hi_tf32(x.x); hi.y = ptx::hi_tf32(x.y); hi.z = ptx::hi_tf32(x.z); hi.w = ptx::hi_tf32(x.w);
           {  // lo = x - hi (exact), two elements per FADD2
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
           }
           *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + off) = hi;
           if (NPASS == 3) *reinterpret_cast<float4*>(smem + SMEM_HEADER + (size_t)s * g.stage_bytes + A_BYTES + off) = lo;
+          }
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -385,8 +406,8 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
       const bool leader = ptx::elect_one();
       const uint32_t w_lo_off = (pair ? g.w_bytes / 2 : g.w_bytes) >> 4;
       // descriptor templates: only the 14-bit start-address field changes
-      const uint64_t da_t = ptx::make_smem_desc(0, g.lbo_a, g.sbo_a, 1);
-      const uint64_t dw_t = ptx::make_smem_desc(0, g.lbo_w, g.sbo_w, W_LAYOUT);
+      const uint64_t da_t = ptx::make_smem_desc(0, g.lbo_a, g.sbo_a, g.a_layout);
+      const uint64_t dw_t = ptx::make_smem_desc(0, g.lbo_w, g.sbo_w, g.w_layout);
       for (int it = 0; it < items_per_cta; ++it) {
         const int acc = it & 1;
         if (pair) ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -411,10 +432,13 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
             };
             auto mma = [&](uint64_t da, uint64_t dw, uint32_t accum) {
               if constexpr (pair) ptx::mma2_tf32(d_tmem, da, dw, g.idesc, accum);
+              else if constexpr (F16) ptx::mma_f16(d_tmem, da, dw, g.idesc, accum);
               else ptx::mma_tf32(d_tmem, da, dw, g.idesc, accum);
             };
 #pragma unroll
-            for (int kk = 0; kk < KS / 8; ++kk) {
+            // per instruction: 8 channels (tf32) or 16 (fp16); either way the A start address advances by 4096 B (two channel
+            // groups) and the W start address by 32 B
+            for (int kk = 0; kk < (F16 ? KS / 16 : KS / 8); ++kk) {
               if (g.dbg & 8u) break;
               const uint64_t da_hi = da_t | (uint64_t)(a_hi + kk * 256), dw_hi = dw_t | (uint64_t)(w_hi + kk * 2);
               mma(da_hi, dw_hi, (ks | kk) ? 1u : 0u);
@@ -479,8 +503,12 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         float2 mr = make_float2(0.f, 1.f);
         if (EPI == EPI_HEAD) { mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps); mscale = mr.y; }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");  // previous item's readers are done with sp
+        // fp16-piece mode: the weight rows were scaled by a power of two into fp16's sweet spot; the inverse is staged per
+        // channel next to the bias-like parameter (both global loads of an iteration are in flight together)
+        float* ssc = reinterpret_cast<float*>(smem + SMEM_SCALES);
         for (int i = tid_e; i < g.n_tile; i += 128 * EGROUPS) {
           float pv = 0.f;
+          if constexpr (F16) ssc[i] = i < nvalid ? __ldg(g.oscale + n0 + i) : 1.f;
           if (i < nvalid) {
             if (EPI == EPI_HEAD) pv = __ldg(a.v1 + n0 + i) - mr.x * mr.y * __ldg(a.v2 + n0 + i);
             if (EPI == EPI_H || EPI == EPI_MASK) pv = __ldg(a.bias + n0 + i);
@@ -517,34 +545,44 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
             wv[j] = (c0 + j < nvalid) ? __ldg(Wp + (size_t)nn * a.pitch) : 0.f;
           }
         }
-        float pv[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 p4 = *reinterpret_cast<const float4*>(sp + c0 + j4 * 4);
-          pv[j4 * 4] = p4.x; pv[j4 * 4 + 1] = p4.y; pv[j4 * 4 + 2] = p4.z; pv[j4 * 4 + 3] = p4.w;
-        }
         float* q = Dp + (size_t)c0 * a.pitch;
         float* qm = Mp ? Mp + (size_t)c0 * a.pitch : nullptr;
         const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
         float o[16], mk[16];
+        // per-channel parameters are fetched 4 columns at a time (8 live registers instead of 32: the epilogue shares the
+        // register budget of the producers)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(buf[j]);
-          mk[j] = 0.f;
-          if (EPI == EPI_HEAD) v = fmaf(mscale, v, pv[j]);
-          if (EPI == EPI_H) v = store_pre ? v + pv[j] : prelu_f(v + pv[j], eslope);
-          if (EPI == EPI_MASK) {
-            mk[j] = __fdividef(1.f, 1.f + __expf(-(v + pv[j])));
-            v = mk[j] * wv[j];
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(sp + c0 + j4 * 4);
+          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if constexpr (F16) s4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + SMEM_SCALES) + c0 + j4 * 4);
+          const float pvv[4] = {p4.x, p4.y, p4.z, p4.w}, osc[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            float v = __uint_as_float(buf[j]);
+            mk[j] = 0.f;
+            // F16: v * osc undoes the power-of-two row scaling of the weights (exact), folded into the bias FMA
+            if (EPI == EPI_RAW && F16) v *= osc[jj];
+            if (EPI == EPI_HEAD) v = F16 ? fmaf(mscale * osc[jj], v, pvv[jj]) : fmaf(mscale, v, pvv[jj]);
+            if (EPI == EPI_H) {
+              const float pre = F16 ? fmaf(v, osc[jj], pvv[jj]) : v + pvv[jj];
+              const float act = prelu_f(pre, eslope);
+              v = store_pre ? pre : act;
+              if (full) { ls += act; lss = fmaf(act, act, lss); }  // gLN statistics are always those of PReLU(.)
+            }
+            if (EPI == EPI_MASK) {
+              mk[j] = __fdividef(1.f, 1.f + __expf(-(F16 ? fmaf(v, osc[jj], pvv[jj]) : v + pvv[jj])));
+              v = mk[j] * wv[j];
+            }
+            o[j] = v;
           }
-          o[j] = v;
         }
         if (full) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             *q = o[j];
             q += a.pitch;
-            if (EPI == EPI_H) { const float sv = store_pre ? prelu_f(o[j], eslope) : o[j]; ls += sv; lss = fmaf(sv, sv, lss); }
           }
           if (EPI == EPI_MASK && qm) {
 #pragma unroll
@@ -628,6 +666,50 @@ __global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W,
   }
 }
 
+// fp16 variant ("3xFP16"): K-major SWIZZLE_64B rows of 32 k x 2 B; per slab a hi image then a lo image of n_tile*64 bytes.
+// Every weight ROW (output channel) is first scaled by a power of two 2^e so that its largest entry lands in [2^9, 2^10):
+// hi and lo pieces then sit in fp16's normal range whatever the magnitude of the weights (tiny gamma-folded rows would
+// otherwise lose their lo piece to fp16's subnormal floor of 6e-8, huge ones would saturate); the epilogue multiplies the
+// accumulator of channel n by the exact inverse 2^-e (oscale, stored behind the images).
+// One warp per row; block = 8 warps = one 8-row swizzle group; grid (ceil(n_tile/8), n_tiles).
+__device__ __forceinline__ void wimg_f16_rows(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs, int nt,
+                                              __half* __restrict__ img, float* __restrict__ oscale) {
+  const int lane = threadIdx.x & 31, nl = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (nl >= n_tile) return;
+  const int n = nt * n_tile + nl;
+  const float* row = W + (size_t)n * K;
+  float mx = 0.f;
+  if (n < M)
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, fabsf(row[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int e = 0;
+  if (mx > 0.f && mx < INFINITY) e = 9 - ilogbf(mx);  // 2^e * mx in [2^9, 2^10)
+  e = max(-100, min(100, e));
+  const float up = ldexpf(1.f, e), down = ldexpf(1.f, -e);
+  if (lane == 0) oscale[n] = down;
+  const size_t per = (size_t)n_tile * KS;  // halves per precision
+  for (int ks = 0; ks < k_slabs; ++ks) {
+    const int kl = lane, k = ks * KS + kl;  // KS == 32 == warp size
+    const float x = (n < M && k < K) ? row[k] * up : 0.f;
+    __half* dst = img + ((size_t)nt * k_slabs + ks) * 2 * per;
+    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 3) ^ ((nl >> 1) & 3))) << 3) + (kl & 7);  // in halves
+    const __half hi = __float2half_rn(x);
+    dst[off] = hi;
+    dst[per + off] = __float2half_rn(x - __half2float(hi));
+  }
+}
+__host__ __device__ inline size_t wimg_f16_image_bytes(int n_tile, int n_tiles, int k_slabs) {
+  return (size_t)n_tiles * k_slabs * 2 * n_tile * KS * sizeof(__half);
+}
+__global__ void __launch_bounds__(256) k_build_wimg_f16(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs,
+                                                        int n_tiles, float* __restrict__ wimg) {
+  static_assert(KS == 32, "one lane per channel of a slab");
+  __half* img = reinterpret_cast<__half*>(wimg);
+  float* oscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wimg) + wimg_f16_image_bytes(n_tile, n_tiles, k_slabs));
+  wimg_f16_rows(W, M, K, n_tile, k_slabs, blockIdx.y, img, oscale);
+}
+
 struct WimgJobs { WimgJob j[CTN_MAX_JOBS]; };
 // grid (max k_slabs * max n_tiles, jobs): one block per (slab, n-tile) of one job
 __global__ void __launch_bounds__(256) k_build_wimg_batch(const WimgJobs jobs, int nprec) {
@@ -650,6 +732,44 @@ __global__ void __launch_bounds__(256) k_build_wimg_batch(const WimgJobs jobs, i
   }
 }
 
+// grid (row groups of the largest job, jobs): blockIdx.x walks (n-tile, 8-row group) pairs of its job
+__global__ void __launch_bounds__(256) k_build_wimg_batch_f16(const WimgJobs jobs) {
+  const WimgJob& jb = jobs.j[blockIdx.y];
+  const int n_tile = jb.M >= 256 ? 256 : ((jb.M + 15) / 16) * 16;
+  const int n_tiles = (jb.M + n_tile - 1) / n_tile, k_slabs = (jb.K + KS - 1) / KS;
+  const int groups = (n_tile + 7) / 8;
+  __half* img = reinterpret_cast<__half*>(jb.wimg);
+  float* oscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(jb.wimg) + wimg_f16_image_bytes(n_tile, n_tiles, k_slabs));
+  const int lane = threadIdx.x & 31;
+  for (int blk = blockIdx.x; blk < n_tiles * groups; blk += gridDim.x) {
+    const int nt = blk / groups, grp = blk - nt * groups;
+    const int nl = grp * 8 + (threadIdx.x >> 5);
+    if (nl >= n_tile) continue;
+    const int n = nt * n_tile + nl;
+    const float* row = jb.W + (size_t)n * jb.K;
+    float mx = 0.f;
+    if (n < jb.M)
+      for (int k = lane; k < jb.K; k += 32) mx = fmaxf(mx, fabsf(row[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 9 - ilogbf(mx);
+    e = max(-100, min(100, e));
+    const float up = ldexpf(1.f, e), down = ldexpf(1.f, -e);
+    if (lane == 0) oscale[n] = down;
+    const size_t per = (size_t)n_tile * KS;
+    for (int ks = 0; ks < k_slabs; ++ks) {
+      const int kl = lane, k = ks * KS + kl;
+      const float x = (n < jb.M && k < jb.K) ? row[k] * up : 0.f;
+      __half* dst = img + ((size_t)nt * k_slabs + ks) * 2 * per;
+      const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 3) ^ ((nl >> 1) & 3))) << 3) + (kl & 7);
+      const __half hi = __float2half_rn(x);
+      dst[off] = hi;
+      dst[per + off] = __float2half_rn(x - __half2float(hi));
+    }
+  }
+}
+
 int pick_n_tile(int M) {
   static const char* env_nt = getenv("CTN_UMMA_NTILE");
   if (env_nt && atoi(env_nt) >= 16 && atoi(env_nt) <= 256 && atoi(env_nt) % 16 == 0 && M >= atoi(env_nt)) return atoi(env_nt);
@@ -668,12 +788,12 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int PRO, int EPI, int NPASS, bool PAIR>
+template <int PRO, int EPI, int NPASS, bool PAIR, bool F16>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
   constexpr int NT = PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS, PAIR, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -691,10 +811,10 @@ int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_pw_umma<PRO, EPI, NPASS, PAIR>, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_pw_umma<PRO, EPI, NPASS, PAIR, F16>, g);
     if (e != cudaSuccess) return (int)e;
   } else {
-    k_pw_umma<PRO, EPI, NPASS, PAIR><<<grid, NT, smem, st>>>(g);
+    k_pw_umma<PRO, EPI, NPASS, PAIR, F16><<<grid, NT, smem, st>>>(g);
   }
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
@@ -713,16 +833,23 @@ extern "C" int ctn_debug_timeline(unsigned long long* host, int n) {
 }
 
 size_t ctn_umma_wimg_bytes(int M, int K, int math) {
-  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  const int nprec = math == CTN_MATH_TF32 ? 1 : 2;
   const int n_tile = pick_n_tile(M);
   const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
-  return (size_t)n_tiles * k_slabs * nprec * n_tile * KS * sizeof(float);
+  // fp16 images are half the size but carry the per-channel scale array behind them; the tf32x3 size + scales covers both
+  return (size_t)n_tiles * k_slabs * nprec * n_tile * KS * sizeof(float) + (size_t)n_tiles * n_tile * sizeof(float) + 256;
 }
 
 int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st) {
-  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;  // hi [, lo]
+  const int nprec = math == CTN_MATH_TF32 ? 1 : 2;  // hi [, lo]
   const int n_tile = pick_n_tile(M);
   const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
+  if (math == CTN_MATH_F16X3) {
+    k_build_wimg_f16<<<dim3((n_tile + 7) / 8, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, n_tiles, wimg);
+    CTN_COUNT_LAUNCH();
+    CTN_RETURN_IF_CUDA_ERR();
+    return CTN_OK;
+  }
   k_build_wimg<<<dim3(k_slabs, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, nprec, wimg);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
@@ -730,7 +857,7 @@ int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cud
 }
 
 int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t st) {
-  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  const int nprec = math == CTN_MATH_TF32 ? 1 : 2;
   if (getenv("CTN_UMMA_NTILE")) {  // debug override changes the tiling: fall back to per-job launches
     for (int i = 0; i < n; ++i) CTN_TRY(ctn_umma_build_wimg(jobs[i].W, jobs[i].M, jobs[i].K, math, jobs[i].wimg, st));
     return CTN_OK;
@@ -745,14 +872,15 @@ int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t
       const int blocks = ((jobs[i0 + i].M + n_tile - 1) / n_tile) * ((jobs[i0 + i].K + KS - 1) / KS);
       if (blocks > maxb) maxb = blocks;
     }
-    k_build_wimg_batch<<<dim3(maxb, m), 256, 0, st>>>(wj, nprec);
+    if (math == CTN_MATH_F16X3) k_build_wimg_batch_f16<<<dim3(64, m), 256, 0, st>>>(wj);
+    else k_build_wimg_batch<<<dim3(maxb, m), 256, 0, st>>>(wj, nprec);
     CTN_COUNT_LAUNCH();
   }
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
 }
 
-#define NPREC_HOST(m) ((m) == CTN_MATH_TF32X3 ? 2u : 1u)
+#define NPREC_HOST(m) ((m) == CTN_MATH_TF32 ? 1u : 2u)
 int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (!a.wimg) return CTN_EINVAL;
   if (a.pitch % TM != 0) return CTN_EALIGN;
@@ -765,8 +893,10 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   g.k_slabs = (a.K + KS - 1) / KS;
   g.t_tiles = a.pitch / TM;
   g.num_items = a.B * g.t_tiles * g.n_tiles;
-  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
-  g.w_bytes = (uint32_t)g.n_tile * (uint32_t)(KS * 4);
+  const int nprec = math == CTN_MATH_TF32 ? 1 : 2;
+  const bool f16 = math == CTN_MATH_F16X3;
+  const uint32_t a_bytes = f16 ? (uint32_t)(TM * KS * 2) : (uint32_t)A_BYTES;
+  g.w_bytes = (uint32_t)g.n_tile * (uint32_t)(KS * (f16 ? 2 : 4));
   static const char* env_dbg = getenv("CTN_UMMA_DBG");
   g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
   int grid = num_sms();
@@ -780,13 +910,14 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   static const char* env_cl = getenv("CTN_UMMA_CLUSTER");
   int cluster = env_cl ? atoi(env_cl) : 1;
   if (cluster != 1 && cluster != 2) cluster = 1;
+  if (f16) cluster = 1;  // fp16 operands: single-CTA kernel only
   g.tiles_total = a.B * g.t_tiles;
   static const char* env_pm = getenv("CTN_UMMA_PAIR_MIN_N");
   const int pair_min_n = env_pm ? atoi(env_pm) : 64;  // N = 64 / 256 are the pair shapes pinned by tools/umma_unit2.cu
   if (cluster == 2 && (grid % 2 != 0 || g.tiles_total < 2 || g.n_tile % 32 != 0 || g.n_tile < pair_min_n)) cluster = 1;
   g.cluster = cluster;
   const uint32_t w_stage = cluster == 2 ? g.w_bytes / 2 : g.w_bytes;
-  g.stage_bytes = (uint32_t)nprec * (A_BYTES + w_stage);
+  g.stage_bytes = (uint32_t)nprec * (a_bytes + w_stage);
   const size_t budget = 227 * 1024 - SMEM_HEADER - 1024;
   int stages = (int)(budget / g.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -794,11 +925,20 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (env_st && atoi(env_st) >= 1 && atoi(env_st) < stages) stages = atoi(env_st);
   if (stages < 1) return CTN_EUNSUPPORTED;
   g.stages = stages;
-  g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(cluster == 2 ? 2 * TM : TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
-  g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
-  g.sbo_a = a.dbg_sbo_a ? a.dbg_sbo_a : 2048u;  // between 4-channel groups
-  g.lbo_w = 16u;                                 // unused for swizzled K-major
-  g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : W_SBO;  // between 8-row (output channel) groups
+  g.oscale = nullptr;
+  if (f16) {
+    g.oscale = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.wimg) + wimg_f16_image_bytes(g.n_tile, g.n_tiles, g.k_slabs));
+    g.idesc = ptx::make_idesc_f16(TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
+    g.lbo_a = 1024u; g.sbo_a = 2048u; g.a_layout = 2u;  // 64-time-step atoms adjacent, 8-channel groups 2048 B apart
+    g.lbo_w = 16u; g.sbo_w = 512u; g.w_layout = 4u;      // SWIZZLE_64B rows of 32 k
+  } else {
+    g.idesc = a.dbg_idesc ? a.dbg_idesc : ptx::make_idesc_tf32(cluster == 2 ? 2 * TM : TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
+    g.lbo_a = a.dbg_lbo_a ? a.dbg_lbo_a : 512u;   // between 32-time-step atoms
+    g.sbo_a = a.dbg_sbo_a ? a.dbg_sbo_a : 2048u;  // between 4-channel groups
+    g.lbo_w = 16u;                                 // unused for swizzled K-major
+    g.sbo_w = a.dbg_sbo_w ? a.dbg_sbo_w : W_SBO;  // between 8-row (output channel) groups
+    g.a_layout = 1u; g.w_layout = W_LAYOUT;
+  }
   const size_t smem = SMEM_HEADER + 1024 + (size_t)stages * g.stage_bytes;
   static const char* env_ws = getenv("CTN_UMMA_WSPLIT");
   g.wsplit = env_ws ? atoi(env_ws) : 1;
@@ -808,8 +948,9 @@ int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (grid > max_grid) grid = max_grid;
 #define UM_LAUNCH(P, E)                                                                   \
   if (pro == P && epi == E)                                                               \
-    return nprec == 2 ? (cluster == 2 ? launch<P, E, 3, true>(g, smem, grid, st) : launch<P, E, 3, false>(g, smem, grid, st)) \
-                      : (cluster == 2 ? launch<P, E, 1, true>(g, smem, grid, st) : launch<P, E, 1, false>(g, smem, grid, st));
+    return f16 ? launch<P, E, 3, false, true>(g, smem, grid, st)                                                                  \
+           : nprec == 2 ? (cluster == 2 ? launch<P, E, 3, true, false>(g, smem, grid, st) : launch<P, E, 3, false, false>(g, smem, grid, st)) \
+                        : (cluster == 2 ? launch<P, E, 1, true, false>(g, smem, grid, st) : launch<P, E, 1, false, false>(g, smem, grid, st));
   UM_LAUNCH(PRO_NONE, EPI_RAW)
   UM_LAUNCH(PRO_DW, EPI_RAW)
   UM_LAUNCH(PRO_NONE, EPI_HEAD)

@@ -120,6 +120,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp16 operands (K = 16 per instruction, twice the rate of kind::tf32)
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -195,6 +205,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// fp16 hi/lo split of two fp32 values ("3xFP16"): hi = rn_f16(x) (saturating, never inf), lo = rn_f16(x - hi).
+// Both pieces carry 11 significant bits like TF32; packed as f16x2 (element 0 in the low half).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float h0, h1;
+  asm("{\n\t.reg .f16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
 __device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // ---- descriptors -------------------------------------------------------------------------------------------------
@@ -220,6 +239,12 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
 __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with F16 inputs (a_format = b_format = 0), fp32 accumulate
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -274,7 +274,7 @@ int ctn_wgrad_umma(const float* dy, size_t dy_bs, const float* x, size_t x_bs, f
   if (splits > total) splits = total;
   g.steps_per_split = (int)((total + splits - 1) / splits);
   splits = (total + g.steps_per_split - 1) / g.steps_per_split;
-  const int nprec = math == CTN_MATH_TF32X3 ? 2 : 1;
+  const int nprec = math == CTN_MATH_TF32 ? 1 : 2;  // F16X3 forwards use the 3xTF32 weight-gradient kernel
   g.stage_bytes = (uint32_t)nprec * (WG_A_BYTES + (uint32_t)g.n_tile * 128u);
   int stages = (int)((227 * 1024 - WG_HEADER - 1024) / g.stage_bytes);
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;

@@ -23,8 +23,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 CTN_OK, CTN_EINVAL, CTN_EUNSUPPORTED, CTN_EALIGN, CTN_EWORKSPACE, CTN_ENOTBUILT = 0, -1, -2, -3, -4, -5
-MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
-MATH_NAMES = {"fp32": MATH_FP32, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32}
+MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_F16X3 = 0, 1, 2, 3
+MATH_NAMES = {"fp32": MATH_FP32, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "f16x3": MATH_F16X3}
 
 _fp = C.c_void_p  # device pointers are passed as integers
 

@@ -41,7 +41,9 @@ enum ctn_status {
 enum ctn_math {
   CTN_MATH_FP32 = 0,   /* CUDA-core FFMA, exact fp32 products (verification mode)          */
   CTN_MATH_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass hi/lo split, fp32 accumulate (default) */
-  CTN_MATH_TF32 = 2    /* tcgen05 kind::tf32 single pass (fast mode, looser tolerance)      */
+  CTN_MATH_TF32 = 2,   /* tcgen05 kind::tf32 single pass (fast mode, looser tolerance)      */
+  CTN_MATH_F16X3 = 3   /* tcgen05 kind::f16, 3-pass fp16 hi/lo split (11-bit pieces like TF32, twice the MMA rate), fp32
+                          accumulate.  Envelope: |activations|, |folded weights| < 65504 (saturating conversion beyond) */
 };
 
 /* Constructor arguments of ConvTasNet / Separator (src/models/conv_tasnet.py:57-66, 322-328). */

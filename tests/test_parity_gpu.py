@@ -28,7 +28,7 @@ from ctn_b200.criterion.pit import PIT1d
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-4, 2e-5
-MODES = ["fp32"] + (["tf32x3"] if N.ctn_has_tcgen05() else [])
+MODES = ["fp32"] + (["tf32x3", "f16x3"] if N.ctn_has_tcgen05() else [])
 
 
 def _load(golden_dir, name):
@@ -441,3 +441,29 @@ def test_forward_and_loss_are_cuda_graph_capturable():
             torch.testing.assert_close(out_g, out_e, rtol=0, atol=1e-6)
             torch.testing.assert_close(loss_g, loss_e, rtol=0, atol=1e-5)
             assert torch.equal(perm_g, perm_e)
+
+
+@pytest.mark.skipif(not N.ctn_has_tcgen05(), reason="tcgen05 family not built")
+@pytest.mark.parametrize("mode", ["tf32x3", "f16x3"])
+def test_split_modes_are_robust_to_weight_magnitudes(mode):
+    """The fp16-piece mode rescales every weight row by a power of two (ctn_umma.cu: wimg_f16_rows), so tiny (gamma-folded)
+    or huge rows keep fp32-level accuracy although fp16 itself spans only 6e-8 .. 65504."""
+    cfg = O.OracleConfig(n_basis=64, kernel_size=16, sep_hidden_channels=96, sep_bottleneck_channels=48, sep_skip_channels=32,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=2)
+    sd = O.synth_state_dict(cfg, seed=77)
+    g = torch.Generator().manual_seed(78)
+    for k in list(sd):
+        if k.endswith("separable_conv1d.norm1d.norm.weight"):      # gamma2 is folded into [Wo; Ws]: rows of 1e-5 .. 1e-3
+            sd[k] = sd[k] * (10.0 ** (-5 + 2 * torch.rand(sd[k].shape, generator=g)))
+        elif k.endswith("output_pointwise_conv1d.weight"):
+            sd[k] = sd[k] * 3e3                                     # compensates gamma2 on the residual path
+        elif k.endswith("skip_pointwise_conv1d.weight"):
+            sd[k] = sd[k] * 3e4
+        elif k.endswith("bottleneck_conv1d.weight") and ".net." in k:
+            sd[k] = sd[k] * 1e-3                                    # tiny W1 (h is re-normalised by gLN1)
+    model = build_model(cfg, sd, math=mode)
+    mixture, sources = O.synth_batch(2, 2, 3000, seed=79)
+    with torch.no_grad():
+        out = model(mixture.cuda())
+        ref, _ = O.conv_tasnet_fwd(mixture, sd, cfg)
+    torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL * max(1.0, float(ref.abs().max())))

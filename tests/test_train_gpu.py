@@ -18,7 +18,7 @@ from test_parity_gpu import build_model
 pytestmark = pytest.mark.gpu
 
 GRAD_RTOL, GRAD_ATOL = 2e-4, 1e-9
-MODES = ["fp32"] + (["tf32x3"] if N.ctn_has_tcgen05() else [])
+MODES = ["fp32"] + (["tf32x3", "f16x3"] if N.ctn_has_tcgen05() else [])
 
 
 def _oracle_grads(cfg, sd, mixture, sources):
