@@ -548,31 +548,32 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
         float* q = Dp + (size_t)c0 * a.pitch;
         float* qm = Mp ? Mp + (size_t)c0 * a.pitch : nullptr;
         const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
+        // F16: the 16 output channels of a chunk share one power-of-two weight scale (wimg_f16_rows scales 16-row groups)
+        float osc = 1.f;
+        if constexpr (F16) osc = reinterpret_cast<const float*>(smem + SMEM_SCALES)[c0];
         float o[16], mk[16];
         // per-channel parameters are fetched 4 columns at a time (8 live registers instead of 32: the epilogue shares the
         // register budget of the producers)
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 p4 = *reinterpret_cast<const float4*>(sp + c0 + j4 * 4);
-          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if constexpr (F16) s4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + SMEM_SCALES) + c0 + j4 * 4);
-          const float pvv[4] = {p4.x, p4.y, p4.z, p4.w}, osc[4] = {s4.x, s4.y, s4.z, s4.w};
+          const float pvv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int j = j4 * 4 + jj;
             float v = __uint_as_float(buf[j]);
             mk[j] = 0.f;
             // F16: v * osc undoes the power-of-two row scaling of the weights (exact), folded into the bias FMA
-            if (EPI == EPI_RAW && F16) v *= osc[jj];
-            if (EPI == EPI_HEAD) v = F16 ? fmaf(mscale * osc[jj], v, pvv[jj]) : fmaf(mscale, v, pvv[jj]);
+            if (EPI == EPI_RAW && F16) v *= osc;
+            if (EPI == EPI_HEAD) v = F16 ? fmaf(mscale * osc, v, pvv[jj]) : fmaf(mscale, v, pvv[jj]);
             if (EPI == EPI_H) {
-              const float pre = F16 ? fmaf(v, osc[jj], pvv[jj]) : v + pvv[jj];
+              const float pre = F16 ? fmaf(v, osc, pvv[jj]) : v + pvv[jj];
               const float act = prelu_f(pre, eslope);
               v = store_pre ? pre : act;
               if (full) { ls += act; lss = fmaf(act, act, lss); }  // gLN statistics are always those of PReLU(.)
             }
             if (EPI == EPI_MASK) {
-              mk[j] = __fdividef(1.f, 1.f + __expf(-(F16 ? fmaf(v, osc[jj], pvv[jj]) : v + pvv[jj])));
+              mk[j] = __fdividef(1.f, 1.f + __expf(-(F16 ? fmaf(v, osc, pvv[jj]) : v + pvv[jj])));
               v = mk[j] * wv[j];
             }
             o[j] = v;
@@ -667,31 +668,41 @@ __global__ void __launch_bounds__(256) k_build_wimg(const float* __restrict__ W,
 }
 
 // fp16 variant ("3xFP16"): K-major SWIZZLE_64B rows of 32 k x 2 B; per slab a hi image then a lo image of n_tile*64 bytes.
-// Every weight ROW (output channel) is first scaled by a power of two 2^e so that its largest entry lands in [2^9, 2^10):
+// Every group of 16 weight ROWS (output channels) is first scaled by a power of two 2^e so that its largest entry lands in
+// [2^9, 2^10) (one scale per 16 rows = per 16-column epilogue chunk, so the epilogue needs a single scalar per chunk):
 // hi and lo pieces then sit in fp16's normal range whatever the magnitude of the weights (tiny gamma-folded rows would
 // otherwise lose their lo piece to fp16's subnormal floor of 6e-8, huge ones would saturate); the epilogue multiplies the
 // accumulator of channel n by the exact inverse 2^-e (oscale, stored behind the images).
-// One warp per row; block = 8 warps = one 8-row swizzle group; grid (ceil(n_tile/8), n_tiles).
-__device__ __forceinline__ void wimg_f16_rows(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs, int nt,
-                                              __half* __restrict__ img, float* __restrict__ oscale) {
-  const int lane = threadIdx.x & 31, nl = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (nl >= n_tile) return;
+// One warp per row; block = 16 warps = one 16-row scale group (the epilogue reads one scale per 16-column chunk);
+// grid (ceil(n_tile/16), n_tiles).
+__device__ __forceinline__ void wimg_f16_group(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs, int nt, int grp,
+                                               __half* __restrict__ img, float* __restrict__ oscale, float* smax) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nl = grp * 16 + wid;
   const int n = nt * n_tile + nl;
+  const bool live = nl < n_tile && n < M;
   const float* row = W + (size_t)n * K;
   float mx = 0.f;
-  if (n < M)
+  if (live)
     for (int k = lane; k < K; k += 32) mx = fmaxf(mx, fabsf(row[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) smax[wid] = mx;
+  __syncthreads();
+  mx = smax[lane & 15];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();  // smax is reused by the next group of this block
   int e = 0;
-  if (mx > 0.f && mx < INFINITY) e = 9 - ilogbf(mx);  // 2^e * mx in [2^9, 2^10)
+  if (mx > 0.f && mx < INFINITY) e = 9 - ilogbf(mx);  // 2^e * (largest entry of the 16 rows) in [2^9, 2^10)
   e = max(-100, min(100, e));
   const float up = ldexpf(1.f, e), down = ldexpf(1.f, -e);
+  if (nl >= n_tile) return;
   if (lane == 0) oscale[n] = down;
   const size_t per = (size_t)n_tile * KS;  // halves per precision
   for (int ks = 0; ks < k_slabs; ++ks) {
     const int kl = lane, k = ks * KS + kl;  // KS == 32 == warp size
-    const float x = (n < M && k < K) ? row[k] * up : 0.f;
+    const float x = (live && k < K) ? row[k] * up : 0.f;
     __half* dst = img + ((size_t)nt * k_slabs + ks) * 2 * per;
     const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 3) ^ ((nl >> 1) & 3))) << 3) + (kl & 7);  // in halves
     const __half hi = __float2half_rn(x);
@@ -702,12 +713,13 @@ __device__ __forceinline__ void wimg_f16_rows(const float* __restrict__ W, int M
 __host__ __device__ inline size_t wimg_f16_image_bytes(int n_tile, int n_tiles, int k_slabs) {
   return (size_t)n_tiles * k_slabs * 2 * n_tile * KS * sizeof(__half);
 }
-__global__ void __launch_bounds__(256) k_build_wimg_f16(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs,
+__global__ void __launch_bounds__(512) k_build_wimg_f16(const float* __restrict__ W, int M, int K, int n_tile, int k_slabs,
                                                         int n_tiles, float* __restrict__ wimg) {
   static_assert(KS == 32, "one lane per channel of a slab");
+  __shared__ float smax[16];
   __half* img = reinterpret_cast<__half*>(wimg);
   float* oscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wimg) + wimg_f16_image_bytes(n_tile, n_tiles, k_slabs));
-  wimg_f16_rows(W, M, K, n_tile, k_slabs, blockIdx.y, img, oscale);
+  wimg_f16_group(W, M, K, n_tile, k_slabs, blockIdx.y, blockIdx.x, img, oscale, smax);
 }
 
 struct WimgJobs { WimgJob j[CTN_MAX_JOBS]; };
@@ -732,42 +744,17 @@ __global__ void __launch_bounds__(256) k_build_wimg_batch(const WimgJobs jobs, i
   }
 }
 
-// grid (row groups of the largest job, jobs): blockIdx.x walks (n-tile, 8-row group) pairs of its job
-__global__ void __launch_bounds__(256) k_build_wimg_batch_f16(const WimgJobs jobs) {
+// grid (64, jobs), block 512: blockIdx.x walks the (n-tile, 16-row group) pairs of its job
+__global__ void __launch_bounds__(512) k_build_wimg_batch_f16(const WimgJobs jobs) {
+  __shared__ float smax[16];
   const WimgJob& jb = jobs.j[blockIdx.y];
   const int n_tile = jb.M >= 256 ? 256 : ((jb.M + 15) / 16) * 16;
   const int n_tiles = (jb.M + n_tile - 1) / n_tile, k_slabs = (jb.K + KS - 1) / KS;
-  const int groups = (n_tile + 7) / 8;
+  const int groups = n_tile / 16;
   __half* img = reinterpret_cast<__half*>(jb.wimg);
   float* oscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(jb.wimg) + wimg_f16_image_bytes(n_tile, n_tiles, k_slabs));
-  const int lane = threadIdx.x & 31;
-  for (int blk = blockIdx.x; blk < n_tiles * groups; blk += gridDim.x) {
-    const int nt = blk / groups, grp = blk - nt * groups;
-    const int nl = grp * 8 + (threadIdx.x >> 5);
-    if (nl >= n_tile) continue;
-    const int n = nt * n_tile + nl;
-    const float* row = jb.W + (size_t)n * jb.K;
-    float mx = 0.f;
-    if (n < jb.M)
-      for (int k = lane; k < jb.K; k += 32) mx = fmaxf(mx, fabsf(row[k]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int e = 0;
-    if (mx > 0.f && mx < INFINITY) e = 9 - ilogbf(mx);
-    e = max(-100, min(100, e));
-    const float up = ldexpf(1.f, e), down = ldexpf(1.f, -e);
-    if (lane == 0) oscale[n] = down;
-    const size_t per = (size_t)n_tile * KS;
-    for (int ks = 0; ks < k_slabs; ++ks) {
-      const int kl = lane, k = ks * KS + kl;
-      const float x = (n < jb.M && k < jb.K) ? row[k] * up : 0.f;
-      __half* dst = img + ((size_t)nt * k_slabs + ks) * 2 * per;
-      const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 3) ^ ((nl >> 1) & 3))) << 3) + (kl & 7);
-      const __half hi = __float2half_rn(x);
-      dst[off] = hi;
-      dst[per + off] = __float2half_rn(x - __half2float(hi));
-    }
-  }
+  for (int blk = blockIdx.x; blk < n_tiles * groups; blk += gridDim.x)
+    wimg_f16_group(jb.W, jb.M, jb.K, n_tile, k_slabs, blk / groups, blk % groups, img, oscale, smax);
 }
 
 int pick_n_tile(int M) {
@@ -845,7 +832,7 @@ int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cud
   const int n_tile = pick_n_tile(M);
   const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
   if (math == CTN_MATH_F16X3) {
-    k_build_wimg_f16<<<dim3((n_tile + 7) / 8, n_tiles), 256, 0, st>>>(W, M, K, n_tile, k_slabs, n_tiles, wimg);
+    k_build_wimg_f16<<<dim3(n_tile / 16, n_tiles), 512, 0, st>>>(W, M, K, n_tile, k_slabs, n_tiles, wimg);
     CTN_COUNT_LAUNCH();
     CTN_RETURN_IF_CUDA_ERR();
     return CTN_OK;
@@ -872,7 +859,7 @@ int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t
       const int blocks = ((jobs[i0 + i].M + n_tile - 1) / n_tile) * ((jobs[i0 + i].K + KS - 1) / KS);
       if (blocks > maxb) maxb = blocks;
     }
-    if (math == CTN_MATH_F16X3) k_build_wimg_batch_f16<<<dim3(64, m), 256, 0, st>>>(wj);
+    if (math == CTN_MATH_F16X3) k_build_wimg_batch_f16<<<dim3(64, m), 512, 0, st>>>(wj);
     else k_build_wimg_batch<<<dim3(maxb, m), 256, 0, st>>>(wj, nprec);
     CTN_COUNT_LAUNCH();
   }
