@@ -9,8 +9,10 @@
 //     swizzled shared-memory image so that one 1-D bulk async copy (TMA engine) brings a 32-channel slab in;
 //   * the epilogue reads a TMEM lane = one time step per thread, so every global store of a warp is a contiguous
 //     128-byte row segment of D.
-// fp32-parity numerics ("3xTF32"): x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi);
-//   D = A_hi W_hi + A_lo W_hi + A_hi W_lo  accumulated in fp32 in TMEM  (the dropped lo*lo term is ~2^-22 relative).
+// fp32-parity numerics: x = hi + lo with 11-bit pieces, D = A_hi W_hi + A_lo W_hi + A_hi W_lo accumulated in fp32 in TMEM
+// (the dropped lo*lo term is ~2^-22 relative).  Pieces are TF32 ("3xTF32", kind::tf32) or FP16 ("3xFP16", kind::f16: twice
+// the tensor rate, half the shared memory per stage; weights pre-scaled per 16-row group, see wimg_f16_group) -- template
+// parameter F16.  The layouts described here are the TF32 ones; the FP16 ones are next to the code that stages them.
 //
 // One persistent CTA per SM, warp-specialised:
 //   warps 0-3   epilogue  (TMEM -> registers -> fused epilogue -> coalesced global stores)
