@@ -209,3 +209,19 @@ def test_dropin_shims_resolve():
             "print('ok')")
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=pkg), capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_training_param_slots_cover_every_parameter():
+    """The autograd node passes the parameters to C in a fixed slot order (ctn_params_t / ctn_block_params_t); every
+    nn.Parameter of the model must appear exactly once, and nothing else."""
+    from ctn_b200.models._train import param_list, TOP_FIELDS
+    m = _paper(n_sources=3)
+    slots = param_list(m)
+    tensors = [t for _, t in slots if t is not None]
+    assert len(tensors) == len(list(m.parameters())) == 343
+    assert {id(t) for t in tensors} == {id(p) for p in m.parameters()}
+    assert [s for s, _ in slots[:len(TOP_FIELDS)]] == list(TOP_FIELDS)
+    # the last residual block has no output head (tdcn.py:58-61): its two slots are None, all others are tensors
+    none_slots = [s for s, t in slots if t is None]
+    assert none_slots == [(23, "out_w"), (23, "out_b")]
+    assert N.MATH_NAMES["f16x3"] == 3 and N.MATH_NAMES["tf32x3"] == 1
