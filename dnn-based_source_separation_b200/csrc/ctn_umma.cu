@@ -40,6 +40,7 @@ constexpr uint32_t W_LAYOUT = KS == 32 ? 2u : 4u;    // UMMA layout type of the 
 constexpr uint32_t W_SBO = KS == 32 ? 1024u : 512u;  // bytes between 8-row groups of the weight image
 constexpr int NUM_THREADS_DW = 21 * 32;   // PRO_DW kernels: 4 epilogue + 1 MMA + 16 producer warps (2 channels each)
 constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: 4 + 1 + 8 producer warps + a second epilogue warpgroup (13-16)
+constexpr int NUM_THREADS_RES = 25 * 32;  // PRO_RES kernels (CTN_RES_WARPS16): 4 + 1 + 16 producer warps + second epilogue warpgroup (21-24)
 constexpr int SMEM_HEADER = 3072;   // barriers + tmem pointer, the epilogue parameter row, the fp16-mode output scales
 constexpr int SMEM_SCALES = 2048;   // byte offset of float[256]: per-output-channel power-of-two scale (F16 kernels)
 constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
@@ -54,6 +55,18 @@ struct UmmaArgs {
   int cluster, tiles_total, cluster_items, wsplit;  // 2 = CTA pair (cta_group::2 MMA, each CTA stages half of the weight slab); B*t_tiles; n_tiles*ceil(tiles/cluster)
   uint32_t dbg;  // CTN_UMMA_DBG bits: 1 = no epilogue stores, 2 = no activation loads, 4 = no weight copies, 8 = no MMA
 };
+
+// producer warps per prologue: the depthwise producer always runs 16; the residual-update producer (pw1, the second
+// largest kernel, latency-bound: 47 % issue-active) can run 8 or 16 -- compile-time switch CTN_RES_WARPS16
+#ifndef CTN_RES_WARPS16
+#define CTN_RES_WARPS16 0  // measured: 16 warps (72 registers) 3.66 ms vs 3.28 ms with 8 warps (96 registers) at cfg2
+#endif
+template <int PRO> struct Roles {
+  static constexpr int PROD_WARPS = (PRO == PRO_DW || (PRO == PRO_RES && CTN_RES_WARPS16)) ? 16 : 8;
+  static constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;
+  static constexpr int THREADS = (4 + 1 + PROD_WARPS + 4 * (EGROUPS - 1)) * 32;
+};
+static_assert(Roles<PRO_DW>::THREADS == NUM_THREADS_DW && Roles<PRO_NONE>::THREADS == NUM_THREADS_E8, "role layout");
 
 // debug timeline (CTN_UMMA_DBG bit 128): CTA 0 records globaltimer stamps per role and slab
 __device__ unsigned long long g_timeline[3 * 4096];
@@ -169,12 +182,12 @@ __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, 
 // channels), W K-major SWIZZLE_64B (rows of 32 channels = 64 bytes) -- both pinned on hardware by tools/umma_unit_f16.cu.
 // Half the shared-memory bytes per stage (4-deep ring at N = 256) and half the tensor-pipe time of the TF32 split.
 template <int PRO, int EPI, int NPASS, bool PAIR, bool F16>
-__global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8, 1) k_pw_umma(const UmmaArgs g) {
+__global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaArgs g) {
   constexpr int NPREC = NPASS == 3 ? 2 : 1;  // precisions staged per operand (hi [, lo])
   constexpr int A_BYTES = F16 ? TM * KS * 2 : TM * KS * 4;  // bytes of one precision of the activation slab (shadows the tf32 constant)
   static_assert(!F16 || (NPASS == 3 && !PAIR), "fp16 operands: 3-pass split, single-CTA only");
-  constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;  // epilogue warpgroups (each covers all 128 TMEM lanes)
-  constexpr int PROD_WARPS = PRO == PRO_DW ? 16 : 8;
+  constexpr int EGROUPS = Roles<PRO>::EGROUPS;  // epilogue warpgroups (each covers all 128 TMEM lanes)
+  constexpr int PROD_WARPS = Roles<PRO>::PROD_WARPS;
   constexpr int CPW = KS / PROD_WARPS;            // channels of a slab per producer warp (2 or 4)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E
     if (EPI == EPI_H) eslope = a.slope[0];
     const bool store_pre = EPI == EPI_H && a.store_pre != 0;  // training forward: keep the PRE-activation, statistics of PReLU(.)
     float* sp = reinterpret_cast<float*>(smem + SMEM_PARAMS);  // [256] per-channel epilogue parameter
-    const int egroup = (EGROUPS == 2 && warp >= 13) ? 1 : 0;                     // second warpgroup handles the upper half of the columns
+    const int egroup = (EGROUPS == 2 && warp >= 5 + PROD_WARPS) ? 1 : 0;                     // second warpgroup handles the upper half of the columns
     const int te = (warp & 3) * 32 + lane;                     // time step within the tile == TMEM lane
     const int tid_e = egroup * 128 + te;
     for (int it = 0; it < items_per_cta; ++it) {
@@ -779,7 +792,7 @@ int num_sms() {
 
 template <int PRO, int EPI, int NPASS, bool PAIR, bool F16>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
-  constexpr int NT = PRO == PRO_DW ? NUM_THREADS_DW : NUM_THREADS_E8;
+  constexpr int NT = Roles<PRO>::THREADS;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS, PAIR, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
