@@ -41,8 +41,11 @@ constexpr uint32_t W_SBO = KS == 32 ? 1024u : 512u;  // bytes between 8-row grou
 constexpr int NUM_THREADS_DW = 21 * 32;   // PRO_DW kernels: 4 epilogue + 1 MMA + 16 producer warps (2 channels each)
 constexpr int NUM_THREADS_E8 = 17 * 32;   // other kernels: 4 + 1 + 8 producer warps + a second epilogue warpgroup (13-16)
 constexpr int NUM_THREADS_RES = 25 * 32;  // PRO_RES kernels (CTN_RES_WARPS16): 4 + 1 + 16 producer warps + second epilogue warpgroup (21-24)
-constexpr int SMEM_HEADER = 3072;   // barriers + tmem pointer, the epilogue parameter row, the fp16-mode output scales
-constexpr int SMEM_SCALES = 2048;   // byte offset of float[256]: per-output-channel power-of-two scale (F16 kernels)
+constexpr int F16_MAX_ROWS = 2048;  // fp16-piece mode: padded output channels whose scales fit the shared-memory table
+constexpr int SMEM_HEADER = 2048 + F16_MAX_ROWS * 4;  // barriers + tmem pointer, the epilogue parameter row, the fp16-mode output scales
+constexpr int SMEM_SCALES = 2048;   // byte offset of float[F16_MAX_ROWS]: power-of-two scale of every padded output channel of the
+                                    // contraction (F16 kernels), loaded ONCE per CTA (a per-item staging put a global-load latency
+                                    // on the epilogue's critical path: +0.9 us per item, 0.5 ms per step)
 constexpr int SMEM_PARAMS = 1024;   // byte offset of float[256] inside the header
 
 struct UmmaArgs {
@@ -214,6 +217,10 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
   if (warp == 4) {
     if constexpr (pair) ptx::tmem_alloc2(ptx::smem_u32(&hdr->tmem_base), 512);
     else ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  }
+  if constexpr (F16) {
+    float* ssc_all = reinterpret_cast<float*>(smem + SMEM_SCALES);
+    for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += blockDim.x) ssc_all[i] = __ldg(g.oscale + i);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -518,12 +525,8 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
         float2 mr = make_float2(0.f, 1.f);
         if (EPI == EPI_HEAD) { mr = gln_mean_rstd(a.stats_in + 2 * b, a.n_in, a.eps); mscale = mr.y; }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");  // previous item's readers are done with sp
-        // fp16-piece mode: the weight rows were scaled by a power of two into fp16's sweet spot; the inverse is staged per
-        // channel next to the bias-like parameter (both global loads of an iteration are in flight together)
-        float* ssc = reinterpret_cast<float*>(smem + SMEM_SCALES);
         for (int i = tid_e; i < g.n_tile; i += 128 * EGROUPS) {
           float pv = 0.f;
-          if constexpr (F16) ssc[i] = i < nvalid ? __ldg(g.oscale + n0 + i) : 1.f;
           if (i < nvalid) {
             if (EPI == EPI_HEAD) pv = __ldg(a.v1 + n0 + i) - mr.x * mr.y * __ldg(a.v2 + n0 + i);
             if (EPI == EPI_H || EPI == EPI_MASK) pv = __ldg(a.bias + n0 + i);
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
         const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
         // F16: the 16 output channels of a chunk share one power-of-two weight scale (wimg_f16_rows scales 16-row groups)
         float osc = 1.f;
-        if constexpr (F16) osc = reinterpret_cast<const float*>(smem + SMEM_SCALES)[c0];
+        if constexpr (F16) osc = reinterpret_cast<const float*>(smem + SMEM_SCALES)[n0 + c0];
         float o[16], mk[16];
         // per-channel parameters are fetched 4 columns at a time (8 live registers instead of 32: the epilogue shares the
         // register budget of the producers)
@@ -772,6 +775,15 @@ __global__ void __launch_bounds__(512) k_build_wimg_batch_f16(const WimgJobs job
     wimg_f16_group(jb.W, jb.M, jb.K, n_tile, k_slabs, blk / groups, blk % groups, img, oscale, smax);
 }
 
+int pick_n_tile(int M);
+// the fp16-piece mode keeps one scale per padded output channel in shared memory: contractions with more than
+// F16_MAX_ROWS padded output channels use the tf32 pieces instead (images and kernel are chosen by the same rule)
+int eff_math(int M, int math) {
+  if (math != CTN_MATH_F16X3) return math;
+  const int n_tile = pick_n_tile(M);
+  return ((M + n_tile - 1) / n_tile) * n_tile > F16_MAX_ROWS ? CTN_MATH_TF32X3 : math;
+}
+
 int pick_n_tile(int M) {
   static const char* env_nt = getenv("CTN_UMMA_NTILE");
   if (env_nt && atoi(env_nt) >= 16 && atoi(env_nt) <= 256 && atoi(env_nt) % 16 == 0 && M >= atoi(env_nt)) return atoi(env_nt);
@@ -843,6 +855,7 @@ size_t ctn_umma_wimg_bytes(int M, int K, int math) {
 }
 
 int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cudaStream_t st) {
+  math = eff_math(M, math);
   const int nprec = math == CTN_MATH_TF32 ? 1 : 2;  // hi [, lo]
   const int n_tile = pick_n_tile(M);
   const int n_tiles = (M + n_tile - 1) / n_tile, k_slabs = (K + KS - 1) / KS;
@@ -860,7 +873,9 @@ int ctn_umma_build_wimg(const float* W, int M, int K, int math, float* wimg, cud
 
 int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t st) {
   const int nprec = math == CTN_MATH_TF32 ? 1 : 2;
-  if (getenv("CTN_UMMA_NTILE")) {  // debug override changes the tiling: fall back to per-job launches
+  bool uniform = true;
+  for (int i = 0; i < n; ++i) uniform = uniform && eff_math(jobs[i].M, math) == math;
+  if (getenv("CTN_UMMA_NTILE") || !uniform) {  // debug override changes the tiling: fall back to per-job launches
     for (int i = 0; i < n; ++i) CTN_TRY(ctn_umma_build_wimg(jobs[i].W, jobs[i].M, jobs[i].K, math, jobs[i].wimg, st));
     return CTN_OK;
   }
@@ -885,6 +900,7 @@ int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t
 #define NPREC_HOST(m) ((m) == CTN_MATH_TF32 ? 1u : 2u)
 int ctn_pw_umma(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (!a.wimg) return CTN_EINVAL;
+  math = eff_math(a.M, math);
   if (a.pitch % TM != 0) return CTN_EALIGN;
   if ((((uintptr_t)a.A) | ((uintptr_t)a.wimg)) & 15) return CTN_EALIGN;
   UmmaArgs g;
