@@ -43,7 +43,10 @@ enum ctn_math {
   CTN_MATH_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass hi/lo split, fp32 accumulate (default) */
   CTN_MATH_TF32 = 2,   /* tcgen05 kind::tf32 single pass (fast mode, looser tolerance)      */
   CTN_MATH_F16X3 = 3   /* tcgen05 kind::f16, 3-pass fp16 hi/lo split (11-bit pieces like TF32, twice the MMA rate), fp32
-                          accumulate.  Envelope: |activations|, |folded weights| < 65504 (saturating conversion beyond) */
+                          accumulate; default of the Python classes.  Weight rows are rescaled by powers of two inside the
+                          library (any magnitude is fine); activations must stay below 65504 in magnitude (conversion
+                          saturates beyond) -- always true behind the normalisations of this network; the separator head
+                          (un-normalised encoder output) and all gradient contractions use the TF32 pieces regardless */
 };
 
 /* Constructor arguments of ConvTasNet / Separator (src/models/conv_tasnet.py:57-66, 322-328). */
