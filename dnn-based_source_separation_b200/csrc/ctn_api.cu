@@ -269,7 +269,7 @@ extern "C" int ctn_tcn_workspace_bytes(const ctn_config_t* cfg, int batch, int f
 
 extern "C" int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, const float* x, float* skip_out, int B,
                            int frames, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   CTN_TRY(check_tcn_cfg(cfg));
   if (!blocks || !x || !skip_out || !workspace || B <= 0 || frames <= 0) return CTN_EINVAL;
   if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
@@ -379,7 +379,7 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
 
 extern "C" int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* x, int B, int T,
                                   float* out, float* latent, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   CTN_TRY(check_model_cfg(cfg));
   if (!params || !params->blocks || !x || !out || !workspace || B <= 0 || T <= 0) return CTN_EINVAL;
   if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256) k_stats_pitch(const float* __restrict__ x
 
 extern "C" int ctn_separator_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* w, int B, int frames,
                                  float* mask, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(w);
   CTN_TRY(check_model_cfg(cfg));
   if (!params || !params->blocks || !w || !mask || !workspace || B <= 0 || frames <= 0) return CTN_EINVAL;
   if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
@@ -487,7 +487,7 @@ extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_param
                                         const float* tgt_host, int B, int T, float* out_host, float* loss_mean_host,
                                         int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
                                         ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(dev_io);
   if (!cfg || !x_host || !tgt_host || !loss_mean_host || !perm_host || !dev_io) return CTN_EINVAL;
   if (((uintptr_t)dev_io) & 255) return CTN_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
@@ -512,7 +512,7 @@ extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_param
 extern "C" int ctn_debug_pointwise(const float* A, const float* W, float* D, int B, int M, int K, int frames, int pitch,
                                    const float* bias, const float* slope, double* stats_out, int epi, int math,
                                    const uint32_t* dbg, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(A);
   if (!A || !W || !D || B <= 0 || M <= 0 || K <= 0 || frames <= 0 || pitch < frames || pitch % 128 != 0) return CTN_EINVAL;
   if (epi != EPI_RAW && epi != EPI_H) return CTN_EUNSUPPORTED;
   if (epi == EPI_H && (!bias || !slope || !stats_out)) return CTN_EINVAL;

@@ -11,11 +11,39 @@ extern thread_local int g_ctn_launches;
 extern thread_local int g_ctn_depth;
 extern thread_local int g_ctn_last_launches;
 #define CTN_COUNT_LAUNCH() (++g_ctn_launches)
-// every extern "C" entry opens one; the outermost scope resets / publishes the launch count
+// every extern "C" entry opens one; the outermost scope resets / publishes the launch count and makes the device that owns
+// `devptr` (any device pointer argument of the call) current for the duration of the call: kernels, memsets and function
+// attributes always go to the tensors' GPU, whatever the caller's current device is (restored on exit)
 struct LaunchScope {
-  LaunchScope() { if (g_ctn_depth++ == 0) g_ctn_launches = 0; }
-  ~LaunchScope() { if (--g_ctn_depth == 0) g_ctn_last_launches = g_ctn_launches; }
+  int prev_dev = -1;
+  explicit LaunchScope(const void* devptr = nullptr) {
+    if (g_ctn_depth++ == 0) {
+      g_ctn_launches = 0;
+      if (devptr) {
+        cudaPointerAttributes at;
+        int cur = 0;
+        if (cudaPointerGetAttributes(&at, devptr) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+            cudaGetDevice(&cur) == cudaSuccess && cur != at.device) {
+          prev_dev = cur;
+          cudaSetDevice(at.device);
+        }
+        cudaGetLastError();  // a host pointer is not an error here
+      }
+    }
+  }
+  ~LaunchScope() {
+    if (--g_ctn_depth == 0) {
+      g_ctn_last_launches = g_ctn_launches;
+      if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    }
+  }
 };
+#define CTN_MAX_DEVICES 64
+static inline int ctn_current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < CTN_MAX_DEVICES) ? d : 0;
+}
 
 #define CTN_RETURN_IF_CUDA_ERR()                      \
   do {                                                \

@@ -84,7 +84,7 @@ static int launch_encoder(const float* x, const float* W, float* w, int B, int T
 
 extern "C" int ctn_encoder_fwd(const float* x, const float* enc_w, float* w, int B, int T, int pad_left, int pad_right,
                                int N, int L, int stride, int relu, int w_pitch, double* stats, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(w);
   if (!x || !enc_w || !w || B <= 0 || T <= 0 || N <= 0 || L <= 0 || stride <= 0) return CTN_EINVAL;
   const int Tp = T + pad_left + pad_right;
   if (Tp < L || (Tp - L) % stride != 0) return CTN_EINVAL;
@@ -196,7 +196,7 @@ static int launch_decoder(const float* what, const float* Wd, float* y, int BS, 
 
 extern "C" int ctn_decoder_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int N, int frames,
                                int in_pitch, int L, int stride, int crop_left, int T_out, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(w_hat);
   if (!w_hat || !dec_w || !y || BS <= 0 || N <= 0 || frames <= 0 || L <= 0 || stride <= 0 || L % stride != 0)
     return CTN_EINVAL;
   if (in_pitch < frames) return CTN_EINVAL;

@@ -217,7 +217,7 @@ extern "C" size_t ctn_sisdr_pit_scratch_bytes(int B, int S) { return sizeof(doub
 extern "C" int ctn_sisdr_pit_fwd(const float* est, const float* tgt, int B, int S, int T, float eps, float* loss_b,
                                  int64_t* perm, float* loss_mean, float* pair_sisdr, double* scratch,
                                  ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(est);
   if (!est || !tgt || !loss_b || !perm || !scratch || B <= 0 || T <= 0) return CTN_EINVAL;
   if (S < 1 || S > CTN_MAX_S) return CTN_EUNSUPPORTED;
   if ((((uintptr_t)est) | ((uintptr_t)tgt)) & 15) return CTN_EALIGN;
@@ -262,7 +262,7 @@ __global__ void k_sisdr_finalize(const double* __restrict__ scratch, int rows, f
 // plain sisdr(est[r], tgt[r]) per row: reuse the S=1 kernels with B=rows
 extern "C" int ctn_sisdr_fwd(const float* est, const float* tgt, int rows, int T, float eps, float* out, double* scratch,
                              ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(est);
   if (!est || !tgt || !out || !scratch || rows <= 0 || T <= 0) return CTN_EINVAL;
   if (((((uintptr_t)est) | ((uintptr_t)tgt)) & 15) || (T % 4 != 0 && 0)) return CTN_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_sisdr_pit_bwd(const float* __restrict__
 extern "C" int ctn_sisdr_pit_bwd(const float* est, const float* tgt, const int64_t* perm, int B, int S, int T, float eps,
                                  const double* fwd_scratch, const float* grad_loss_b, float coef, float* d_est,
                                  ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(est);
   if (!est || !tgt || !perm || !fwd_scratch || !d_est || B <= 0 || T <= 0) return CTN_EINVAL;
   if (S < 1 || S > CTN_MAX_S) return CTN_EUNSUPPORTED;
   int gx = (T + 1023) / 1024;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_gln_apply(const float* __restrict__ x, 
 
 extern "C" int ctn_gln_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T,
                            float eps, double* scratch, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   if (!x || !gamma || !beta || !y || !scratch || B <= 0 || C <= 0 || T <= 0) return CTN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, st);
@@ -153,7 +153,7 @@ int ctn_cln_pitch_fwd(const float* x, const float* gamma, const float* beta, flo
 
 extern "C" int ctn_cln_fwd(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T,
                            float eps, double* scratch, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   if (!x || !gamma || !beta || !y || !scratch || B <= 0 || C <= 0 || T <= 0) return CTN_EINVAL;
   return ctn_cln_pitch_fwd(x, gamma, beta, y, B, C, T, T, eps, scratch, (cudaStream_t)stream);
 }

@@ -857,7 +857,7 @@ extern "C" int ctn_train_workspace_bytes(const ctn_config_t* cfg, int batch, int
 
 extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_t* p, const float* x, int B, int T, float* out,
                                         void* train_ws, size_t train_ws_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   CTN_TRY(check_train_cfg(c));
   if (!p || !p->blocks || !x || !out || !train_ws || B <= 0 || T <= 0) return CTN_EINVAL;
   if (((uintptr_t)train_ws) & 255) return CTN_EALIGN;
@@ -957,7 +957,7 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
 // grads: same layout as params; every tensor must be ZERO on entry (the kernels accumulate with atomics)
 extern "C" int ctn_convtasnet_bwd(const ctn_config_t* c, const ctn_params_t* p, const ctn_params_t* grads, const float* x,
                                   const float* d_out, int B, int T, void* train_ws, size_t train_ws_bytes, ctn_stream_t stream) {
-  LaunchScope scope;
+  LaunchScope scope(x);
   CTN_TRY(check_train_cfg(c));
   if (!p || !p->blocks || !grads || !grads->blocks || !x || !d_out || !train_ws || B <= 0 || T <= 0) return CTN_EINVAL;
   if (((uintptr_t)train_ws) & 255) return CTN_EALIGN;

@@ -791,25 +791,25 @@ int pick_n_tile(int M) {
   return ((M + 15) / 16) * 16;
 }
 
-int g_num_sms = 0;
+int g_num_sms[CTN_MAX_DEVICES] = {0};  // per device ordinal
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  const int dev = ctn_current_device();
+  if (g_num_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 template <int PRO, int EPI, int NPASS, bool PAIR, bool F16>
 int launch(const UmmaArgs& g, size_t smem, int grid, cudaStream_t st) {
   constexpr int NT = Roles<PRO>::THREADS;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[CTN_MAX_DEVICES] = {false};  // the opt-in is per device (context)
+  const int dev = ctn_current_device();
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_pw_umma<PRO, EPI, NPASS, PAIR, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (PAIR) {
     cudaLaunchConfig_t cfg;

@@ -227,24 +227,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_umma(const WgArgs g) {
   if (warp == 4) ptx::tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
-int g_sms = 0;
+int g_sms[CTN_MAX_DEVICES] = {0};  // per device ordinal
 int sms() {
-  if (g_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms <= 0) g_sms = 148;
+  const int dev = ctn_current_device();
+  if (g_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms[dev] <= 0) g_sms[dev] = 148;
   }
-  return g_sms;
+  return g_sms[dev];
 }
 
 template <int NPASS>
 int launch_wg(const WgArgs& g, size_t smem, int grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[CTN_MAX_DEVICES] = {false};  // the opt-in is per device (context)
+  const int dev = ctn_current_device();
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_umma<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   k_wgrad_umma<NPASS><<<grid, WG_THREADS, smem, st>>>(g);
   CTN_COUNT_LAUNCH();

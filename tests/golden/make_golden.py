@@ -90,6 +90,32 @@ def model_case(name, cfg: O.OracleConfig, batch, T, wseed, xseed, subsample=None
           f"perm {perm.tolist()} fp32-vs-fp64 {rec['fp32_vs_fp64_maxabs']:.2e} -> {os.path.getsize(path)} B")
 
 
+def grad_case(name, cfg: O.OracleConfig, batch, T, wseed, xseed, stride=97):
+    """Reference-side TRAINING golden: ``loss.backward()`` of the unmodified reference through PIT1d(NegSISDR)
+    (egs/wsj0-mix/common/src/driver.py:146-150).  Stores, per parameter tensor, fp64 (sum, sumsq, absmax) of the gradient
+    and every ``stride``-th element of its flattened values (the full set is 20 MB at the paper size)."""
+    ref = build_reference(cfg)
+    sd = O.synth_state_dict(cfg, seed=wseed)
+    ref.load_state_dict(sd, strict=True)
+    ref.train()
+    mixture, sources = O.synth_batch(batch, cfg.n_sources, T, seed=xseed)
+    crit = PIT1d(NegSISDR(), n_sources=cfg.n_sources)
+    out = ref(mixture)
+    loss, perm = crit(out, sources)
+    loss.backward()
+    grads = {}
+    for k, p in ref.named_parameters():
+        g = p.grad.detach()
+        grads[k] = {"sum": float(g.double().sum()), "sumsq": float((g.double() ** 2).sum()), "absmax": float(g.abs().max()),
+                    "sample": g.flatten()[::stride].clone(), "shape": tuple(g.shape)}
+    rec = {"name": name, "cfg": cfg.to_dict(), "batch": batch, "T": T, "wseed": wseed, "xseed": xseed, "stride": stride,
+           "loss": loss.detach().clone(), "perm": perm.clone(), "grads": grads,
+           "out_absmax": float(out.detach().abs().max())}
+    path = os.path.join(HERE, name + ".pt")
+    torch.save(rec, path)
+    print(f"{name}: loss {float(loss):.6f} perm {perm.tolist()} {len(grads)} gradient tensors -> {os.path.getsize(path)} B")
+
+
 def module_cases():
     rec = {}
     # gLN / cLN: the reference's own self-test input (src/modules/norm.py:107-116) + a random one
@@ -168,6 +194,11 @@ def module_cases():
 
 
 def main():
+    paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
+                 sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
+    if len(sys.argv) > 1 and sys.argv[1] == "grad":   # mint only the training golden (the forward fixtures are unchanged)
+        grad_case("paper_3spk_grad", O.OracleConfig(**paper, causal=False, n_sources=3), batch=2, T=8000, wseed=113, xseed=113)
+        return
     tiny = dict(n_basis=16, kernel_size=4, sep_hidden_channels=16, sep_bottleneck_channels=8, sep_skip_channels=8,
                 sep_num_blocks=2, sep_num_layers=3)
     model_case("tiny_gln", O.OracleConfig(**tiny, causal=False), batch=2, T=203, wseed=11, xseed=21)
@@ -183,6 +214,7 @@ def main():
     model_case("paper_3spk_short", O.OracleConfig(**paper, causal=False, n_sources=3), batch=1, T=8000, wseed=112,
                xseed=112, subsample=17)
     module_cases()
+    grad_case("paper_3spk_grad", O.OracleConfig(**paper, causal=False, n_sources=3), batch=2, T=8000, wseed=113, xseed=113)
 
 
 if __name__ == "__main__":

@@ -96,3 +96,25 @@ def test_pit_sisdr(golden_dir):
     l, p = O.pit_neg_sisdr(r["input"], r["target"], batch_mean=False)
     assert torch.equal(p, r["pattern"])
     torch.testing.assert_close(l, r["loss_b"], rtol=1e-6, atol=1e-5)
+
+
+def test_autograd_over_the_oracle_matches_reference_backward(golden_dir):
+    """The training checker (torch autograd over the oracle) is pinned to the reference's own ``loss.backward()``
+    (tests/golden/make_golden.py: grad_case, paper hyper-parameters, 3 speakers, batch 2, T = 8000): loss, permutation and
+    all 343 gradient tensors (fp64 sums + every 97th element)."""
+    rec = _load(golden_dir, "paper_3spk_grad")
+    cfg = O.OracleConfig(**rec["cfg"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(cfg, seed=rec["wseed"]).items()}
+    mixture, sources = O.synth_batch(rec["batch"], cfg.n_sources, rec["T"], seed=rec["xseed"])
+    out, _ = O.conv_tasnet_fwd(mixture, sd, cfg)
+    loss, perm = O.pit_neg_sisdr(out, sources)
+    loss.backward()
+    assert torch.equal(perm, rec["perm"])
+    torch.testing.assert_close(loss.detach(), rec["loss"], rtol=0, atol=1e-4)
+    assert len(rec["grads"]) == 343
+    for k, g in rec["grads"].items():
+        mine = sd[k].grad
+        assert tuple(mine.shape) == g["shape"], k
+        tol = 2e-4 * g["absmax"] + 1e-12
+        assert float((mine.flatten()[::rec["stride"]] - g["sample"]).abs().max()) <= tol, k
+        assert abs(float(mine.double().sum()) - g["sum"]) <= 2e-4 * (g["sumsq"] * mine.numel()) ** 0.5 + 1e-9, k

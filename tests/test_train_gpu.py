@@ -121,3 +121,54 @@ def test_training_step_decreases_loss():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+PAPER = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128, sep_skip_channels=128,
+             sep_num_blocks=3, sep_num_layers=8)
+
+
+@pytest.mark.parametrize("mode", [m for m in MODES if m != "fp32"])
+@pytest.mark.parametrize("S", [2, 3])
+def test_paper_size_gradients_vs_oracle_autograd(mode, S):
+    """BASELINE hyper-parameters (N=512 L=16 B=128 H=512 Sc=128 X=8 R=3; cfg2 = 2 speakers, cfg3 = 3 speakers), batch 2,
+    T = 8000: the tcgen05 weight-gradient kernel runs its 4 M-tiles / K = 512 shapes and the split-K red.add path.  All 343
+    gradient tensors against torch autograd over the oracle (egs/wsj0-mix/common/src/driver.py:146-150)."""
+    cfg = O.OracleConfig(causal=False, n_sources=S, **PAPER)
+    sd = O.synth_state_dict(cfg, seed=113)
+    mixture, sources = O.synth_batch(2, S, 8000, seed=113)
+    ref_out, ref_loss, ref_perm, ref_grads = _oracle_grads(cfg, sd, mixture, sources)
+    model = build_model(cfg, sd, math=mode).train()
+    out = model(mixture.cuda())
+    torch.testing.assert_close(out.detach().cpu(), ref_out, rtol=1e-4, atol=2e-5)
+    loss, perm = PIT1d(NegSISDR(), S)(out, sources.cuda())
+    assert torch.equal(perm.cpu(), ref_perm)
+    torch.testing.assert_close(loss.detach().cpu(), ref_loss, rtol=0, atol=1e-4)
+    loss.backward()
+    assert len(ref_grads) == 343
+    worst = _check_grads(model, ref_grads)
+    print("paper-size worst relative gradient error", worst)
+
+
+def test_paper_size_gradients_vs_reference_golden(golden_dir):
+    """Same shape against the fixture minted from the UNMODIFIED reference's loss.backward() (tests/golden/make_golden.py
+    grad_case): loss, permutation, and every 97th element + fp64 sum of each of the 343 gradient tensors."""
+    import os
+    rec = torch.load(os.path.join(golden_dir, "paper_3spk_grad.pt"), weights_only=False)
+    cfg = O.OracleConfig(**rec["cfg"])
+    sd = O.synth_state_dict(cfg, seed=rec["wseed"])
+    mixture, sources = O.synth_batch(rec["batch"], cfg.n_sources, rec["T"], seed=rec["xseed"])
+    model = build_model(cfg, sd).train()
+    loss, perm = PIT1d(NegSISDR(), cfg.n_sources)(model(mixture.cuda()), sources.cuda())
+    loss.backward()
+    assert torch.equal(perm.cpu(), rec["perm"])
+    torch.testing.assert_close(loss.detach().cpu(), rec["loss"], rtol=0, atol=1e-4)
+    n = 0
+    for k, p in model.named_parameters():
+        g = rec["grads"][k]
+        mine = p.grad.detach().cpu()
+        assert tuple(mine.shape) == g["shape"], k
+        tol = GRAD_RTOL * g["absmax"] + GRAD_ATOL
+        assert float((mine.flatten()[::rec["stride"]] - g["sample"]).abs().max()) <= tol, k
+        assert abs(float(mine.double().sum()) - g["sum"]) <= GRAD_RTOL * (g["sumsq"] * mine.numel()) ** 0.5 + 1e-9, k
+        n += 1
+    assert n == 343
