@@ -106,6 +106,12 @@ struct TcnWs {
   float *x, *skip, *h, *u, *outraw;
   void* causal_ws;  // causal (cLN) models: scratch of the un-fused pipeline (ctn_causal.cu)
   float* xalt;  // second residual-stream buffer (tcgen05 modes ping-pong x between blocks: the update is fused into pw1)
+  // fp16-piece mode: activation envelope (ctn_act_scales)
+  std::vector<float*> dwp;  // per block: packed depthwise parameters [ceil16(H)][8]
+  float* scales;            // [2*RX + 1] power-of-two operand scales (+ 3*RX floats of scratch)
+  float* x0_bound;          // [x0_n] candidates bounding |x_0|: the head's per-row bounds, or the measured max |x| (ctn_tcn_fwd)
+  int x0_n;
+  const float* mask_slope;  // separator.prelu (nullable)
   size_t stats_bytes;
 };
 
@@ -130,11 +136,18 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
     ws->folds[i].Wf = cv.take<float>((size_t)Mt * c->hidden);
     ws->folds[i].v1 = cv.take<float>(Mt);
     ws->folds[i].v2 = cv.take<float>(Mt);
+    ws->folds[i].vb = cv.take<float>(Mt);
     if (c->math != CTN_MATH_FP32) {
       ws->wimg1[i] = cv.take<float>(ctn_umma_wimg_bytes(c->hidden, c->bottleneck, c->math) / sizeof(float));
       ws->wimg2[i] = cv.take<float>(ctn_umma_wimg_bytes(Mt, c->hidden, c->math) / sizeof(float));
     }
   }
+  ws->dwp.assign(RX, nullptr);
+  for (int i = 0; i < RX; ++i) ws->dwp[i] = cv.take<float>((size_t)ctn_round_up(c->hidden, 16) * 8);
+  ws->scales = cv.take<float>((size_t)5 * RX + 8);
+  ws->x0_bound = cv.take<float>(64);  // ctn_tcn_fwd: measured max |x|; the model path points x0_bound at the head's row bounds
+  ws->x0_n = 1;
+  ws->mask_slope = nullptr;
   const size_t bp = (size_t)B * pitch;
   ws->x = cv.take<float>(bp * c->bottleneck);
   ws->xalt = cv.take<float>(bp * c->bottleneck);
@@ -153,6 +166,7 @@ static void carve_tcn(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs
 
 static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t st) {
   if (math == CTN_MATH_FP32) return ctn_pw_simt(a, pro, epi, st);
+  if (math == CTN_MATH_F16X3 && ctn_pw_tma_supported(a, pro, epi)) return ctn_pw_tma(a, pro, epi, st);
   return ctn_pw_umma(a, pro, epi, math, st);
 }
 
@@ -167,20 +181,32 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
     StageTimer tm(CTN_ST_PREP, st);
     std::vector<FoldJob> fj;
     std::vector<WimgJob> wj;
+    const float Rh = sqrtf((float)H * (float)frames) * 1.0001f;  // >= max |normalised value| of a gLN group of H*frames elements
+    ScaleJobs* sj = new ScaleJobs;
+    memset(sj, 0, sizeof(*sj));
     for (int i = 0; i < R * X; ++i) {
       const ctn_block_params_t& p = blocks[i];
       const bool has_out = p.out_w != nullptr;
       const FoldedConv& f = ws->folds[i];
-      if (has_out) fj.push_back(FoldJob{p.out_w, p.out_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Bc, H, 0});
-      fj.push_back(FoldJob{p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Sc, H, has_out ? Bc : 0});
+      if (has_out) fj.push_back(FoldJob{p.out_w, p.out_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Bc, H, 0, f.vb, Rh});
+      fj.push_back(FoldJob{p.skip_w, p.skip_b, p.norm2_g, p.norm2_b, f.Wf, f.v1, f.v2, Sc, H, has_out ? Bc : 0, f.vb, Rh});
+      sj->j[i] = ScaleJob{f.vb, p.norm1_g, p.norm1_b, p.dw_w, p.dw_b, p.prelu2, ws->dwp[i], has_out ? 1 : 0};
       if (c->math != CTN_MATH_FP32) {
         wj.push_back(WimgJob{p.bottleneck_w, ws->wimg1[i], H, Bc});
         wj.push_back(WimgJob{f.Wf, ws->wimg2[i], has_out ? Bc + Sc : Sc, H});
       }
     }
-    CTN_TRY(ctn_fold_batch(fj.data(), (int)fj.size(), st));
-    if (!wj.empty()) CTN_TRY(ctn_umma_build_wimg_batch(wj.data(), (int)wj.size(), c->math, st));
+    int rc = ctn_fold_batch(fj.data(), (int)fj.size(), st);
+    if (rc == CTN_OK && !wj.empty()) rc = ctn_umma_build_wimg_batch(wj.data(), (int)wj.size(), c->math, st);
+    if (rc == CTN_OK && c->math == CTN_MATH_F16X3) {
+      sj->n = R * X; sj->Bc = Bc; sj->Sc = Sc; sj->H = H; sj->P = c->sep_kernel; sj->R = Rh;
+      sj->x0_bound = ws->x0_bound; sj->x0_n = ws->x0_n; sj->mask_slope = ws->mask_slope; sj->scales = ws->scales;
+      rc = ctn_act_scales(*sj, st);
+    }
+    delete sj;
+    CTN_TRY(rc);
   }
+  const bool scaled = c->math == CTN_MATH_F16X3;
   for (int r = 0; r < R; ++r) {
     for (int l = 0; l < X; ++l) {
       const int i = r * X + l;
@@ -201,6 +227,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       if (fuse_res && i == 0) a.A = ws->x;
       a.W = p.bottleneck_w; a.D = ws->h; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
       a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1; a.wimg = ws->wimg1[i];
+      if (scaled) a.act_scale = ws->scales + 2 * i;
       int pro1 = PRO_NONE;
       if (fuse_res && i > 0) {
         // x_{i} = x_{i-1} + deferred gLN2 of block i-1;  x_{i-1} lives in xbuf[(i-1)&1], x_i goes to xbuf[i&1]
@@ -223,6 +250,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
         a.wimg = ws->wimg2[i];
         a.pro_slope = p.prelu2; a.dw_norm_g = p.norm1_g; a.dw_norm_b = p.norm1_b; a.dw_w = p.dw_w; a.dw_b = p.dw_b;
         a.dw_stats_in = st1; a.dw_stats_out = st2; a.dw_dilation = dilation; a.dw_pad_left = pad_left; a.dw_eps = c->eps_tcn;
+        if (scaled) { a.act_scale = ws->scales + 2 * i + 1; a.dw_params = ws->dwp[i]; }
         CTN_TRY(pw_dispatch(a, PRO_DW, EPI_RAW, c->math, st));
       } else {
         // K_B: u = PReLU(dwconv(gLN1(h))), stats2
@@ -233,6 +261,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
         memset(&a, 0, sizeof(a));
         a.A = ws->u; a.W = ws->folds[i].Wf; a.D = ws->rblk[i]; a.B = B; a.M = Mt; a.K = H; a.frames = frames; a.pitch = pitch;
         a.wimg = ws->wimg2[i];
+        if (scaled) a.act_scale = ws->scales + 2 * i + 1;
         { StageTimer tm(CTN_ST_PW2, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_RAW, c->math, st)); }
       }
       // K_F: residual update with the deferred gLN2 (x += rstd2*r[:Bc] + c); the skip rows are reduced once at the end
@@ -284,6 +313,11 @@ extern "C" int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* bl
   cudaError_t e = cudaMemsetAsync(ws.stats, 0, ws.stats_bytes, st);
   if (e != cudaSuccess) return (int)e;
   CTN_TRY(ctn_copy_to_pitch(x, ws.x, B * cfg->bottleneck, frames, pitch, st));
+  if (cfg->math == CTN_MATH_F16X3 && !cfg->causal) {  // stand-alone TCN: |x_0| is whatever the caller passes -- measure it
+    e = cudaMemsetAsync(ws.x0_bound, 0, sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    CTN_TRY(ctn_absmax_pitch(ws.x, B * cfg->bottleneck, frames, pitch, ws.x0_bound, st));
+  }
   CTN_TRY(run_tcn(cfg, blocks, &ws, B, frames, pitch, st));
   CTN_TRY(ctn_copy_from_pitch(ws.skip, skip_out, B * cfg->skip, frames, pitch, st));
   return CTN_OK;
@@ -314,6 +348,7 @@ static void carve_model(Carver& cv, const ctn_config_t* c, int B, int pitch, Mod
   ws->head.Wf = cv.take<float>((size_t)c->bottleneck * c->n_basis);
   ws->head.v1 = cv.take<float>(c->bottleneck);
   ws->head.v2 = cv.take<float>(c->bottleneck);
+  ws->head.vb = cv.take<float>(c->bottleneck);
   ws->wimg_head = ws->wimg_mask = nullptr;
   if (c->math != CTN_MATH_FP32) {
     ws->wimg_head = cv.take<float>(ctn_umma_wimg_bytes(c->bottleneck, c->n_basis, c->math) / sizeof(float));
@@ -346,14 +381,14 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
     CTN_TRY(ctn_causal_head(c, p, ws->w, ws->what, ws->tcn.x, B, frames, pitch, ws->tcn.causal_ws, st));
     if (c->math != CTN_MATH_FP32) {
       StageTimer tm(CTN_ST_PREP, st);
-      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
+      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math, ws->wimg_mask, st));
     }
   } else {
     // head: gLN0 folded into the bottleneck 1x1 (conv_tasnet.py:370-371).  Its operand is the un-normalised encoder output
     // (any input scale), so the fp16-piece mode falls back to the tf32 pieces here (0.14 ms of the step).
     const int head_math = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
     { StageTimer tm(CTN_ST_PREP, st);
-      CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st));
+      CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws->head, 0, st, sqrtf((float)N * (float)frames) * 1.0001f));
       if (c->math != CTN_MATH_FP32) {
         CTN_TRY(ctn_umma_build_wimg(ws->head.Wf, Bc, N, head_math, ws->wimg_head, st));
         CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws->wimg_mask, st));
@@ -366,14 +401,18 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
     a.wimg = ws->wimg_head;
     { StageTimer tm(CTN_ST_HEAD, st); CTN_TRY(pw_dispatch(a, PRO_NONE, EPI_HEAD, head_math, st)); }
   }
-  // TCN (conv_tasnet.py:372)
+  // TCN (conv_tasnet.py:372).  fp16-piece mode: |x_0| <= max_n of the head's row bounds; the mask operand is PReLU(skip sum)
+  ws->tcn.x0_bound = ws->head.vb; ws->tcn.x0_n = Bc; ws->tcn.mask_slope = p->prelu_out;
   CTN_TRY(run_tcn(c, p->blocks, &ws->tcn, B, frames, pitch, st));
   // tail: PReLU -> mask 1x1 -> sigmoid -> * w  (conv_tasnet.py:373-376, 159-160)
   PwArgs a;
   memset(&a, 0, sizeof(a));
   a.A = ws->tcn.skip; a.W = p->mask_w; a.D = ws->what; a.B = B; a.M = S * N; a.K = Sc; a.frames = frames; a.pitch = pitch;
   a.pro_slope = p->prelu_out; a.bias = p->mask_b; a.wenc = ws->w; a.Nb = N; a.mask_out = mask_out; a.wimg = ws->wimg_mask;
-  { StageTimer tm(CTN_ST_MASK, st); CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, c->math, st)); }
+  if (c->math == CTN_MATH_F16X3 && !c->causal) a.act_scale = ws->tcn.scales + 2 * c->num_blocks * c->num_layers;
+  // causal models: no operand scales (un-fused pipeline) -> the mask contraction stays on the tf32 pieces
+  const int mask_math = (c->causal && c->math == CTN_MATH_F16X3) ? CTN_MATH_TF32X3 : c->math;
+  { StageTimer tm(CTN_ST_MASK, st); CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, mask_math, st)); }
   return CTN_OK;
 }
 

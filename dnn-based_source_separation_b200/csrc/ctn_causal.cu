@@ -108,9 +108,11 @@ inline dim3 grid_cb(int C, int B) { return dim3(C < 1024 ? C : 1024, B); }
 
 int pw(const ctn_config_t* c, CausalWs& ws, PwArgs& a, int pro, int epi, cudaStream_t st) {
   if (c->math == CTN_MATH_FP32) return ctn_pw_simt(a, pro, epi, st);
-  CTN_TRY(ctn_umma_build_wimg(a.W, a.M, a.K, c->math, ws.wimg, st));
+  // causal models: operands are materialised tensors without operand scales -> tf32 pieces in the fp16-piece mode
+  const int math = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
+  CTN_TRY(ctn_umma_build_wimg(a.W, a.M, a.K, math, ws.wimg, st));
   a.wimg = ws.wimg;
-  return ctn_pw_umma(a, pro, epi, c->math, st);
+  return ctn_pw_umma(a, pro, epi, math, st);
 }
 
 }  // namespace

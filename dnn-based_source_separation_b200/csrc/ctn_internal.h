@@ -9,8 +9,11 @@ struct FoldedConv {
   float* Wf;  // (M, K)
   float* v1;  // (M)
   float* v2;  // (M)
+  float* vb;  // (M) nullable: bound of |W gLN(u) + b| per row = sum_k |W[m][k]| (|gamma_k| R + |beta_k|) + |b_m|, R = sqrt(#elements
+              // of the gLN group) >= max |normalised value|  (activation envelope of the fp16-piece mode)
 };
 
+#define CTN_MAX_BLOCKS 64
 // epilogue / prologue selectors of the pointwise (1x1) contraction kernels
 enum { PRO_NONE = 0, PRO_PRELU = 1, PRO_DW = 2, PRO_RES = 3 };
 enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3 };
@@ -56,6 +59,10 @@ struct PwArgs {
   float* res_x_out;         // (B, K, pitch)
   // tcgen05 path only
   const float* wimg;       // pre-swizzled hi/lo weight images (ctn_umma_build_wimg)
+  // fp16-piece mode: power-of-two scale of the activation operand (device scalar, nullable = 1), chosen per forward from a
+  // bound on |operand| derived from the weights alone (ctn_act_scales) so that fp16 can never saturate; undone in the epilogue
+  const float* act_scale;
+  const float* dw_params;  // PRO_DW, TMA-fed kernel: packed per-channel parameters [ceil16(K)][8] (ctn_act_scales)
   uint32_t dbg_idesc, dbg_lbo_a, dbg_sbo_a, dbg_sbo_w;  // 0 = defaults (descriptor probing from the debug entry)
 };
 
@@ -72,14 +79,37 @@ int ctn_wgrad_umma(const float* dy, size_t dy_bs, const float* x, size_t x_bs, f
                    int K, int B, int frames, int pitch, int math, cudaStream_t st);
 
 int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
-                  int row_offset, cudaStream_t st);
+                  int row_offset, cudaStream_t st, float R = 0.f);
 
 // batched variants: all weight preparation of a forward in two launches (jobs travel in the kernel parameter block)
-struct FoldJob { const float *W, *bias, *gamma, *beta; float *Wf, *v1, *v2; int M, K, row_offset; };
+struct FoldJob { const float *W, *bias, *gamma, *beta; float *Wf, *v1, *v2; int M, K, row_offset; float* vb; float R; };
 struct WimgJob { const float* W; float* wimg; int M, K; };
 #define CTN_MAX_JOBS 48
 int ctn_fold_batch(const FoldJob* jobs, int n, cudaStream_t st);
 int ctn_umma_build_wimg_batch(const WimgJob* jobs, int n, int math, cudaStream_t st);
+
+// TMA-fed tcgen05 kernels of the fp16-piece mode (ctn_pwtma.cu): pw1 (PRO_RES / PRO_NONE + EPI_H) and pw2 (PRO_DW + EPI_RAW)
+int ctn_pw_tma_supported(const PwArgs& a, int pro, int epi);
+int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st);
+
+// Activation envelope of the fp16-piece mode.  Per residual block i the two operands that meet the tensor core as fp16
+// pieces are x_i (pw1) and u_i (fused depthwise output, pw2); the mask contraction sees PReLU(skip sum).  From the weights
+// alone:  |gLN(.)| <= |gamma| R + |beta| with R = sqrt(#elements of the group);  |u_c| <= max(1,|a2|) ((|g1_c| R + |b1_c|) sum_k |wd_ck| + |bd_c|);
+// |x_{i+1}| <= |x_i| + max_n vb_out_i[n];  |skip| <= sum_i max_n vb_skip_i[n].  scales[2i] / [2i+1] / [2n] receive the powers of two
+// that map those bounds to <= 2^15; dwp_i receives the packed depthwise parameters {g1, b1, w0, w1, w2, bd, 0, 0} per channel.
+struct ScaleJob { const float *vb, *g1, *b1, *dw_w, *dw_b, *slope2; float* dwp; int has_out; };
+struct ScaleJobs {
+  ScaleJob j[CTN_MAX_BLOCKS];
+  int n, Bc, Sc, H, P;
+  const float* x0_bound;  // device: x0_n candidates whose max bounds |x_0|
+  int x0_n;
+  const float* mask_slope;  // nullable
+  float R;
+  float* scales;  // [2n + 1]
+};
+int ctn_act_scales(const ScaleJobs& jobs, cudaStream_t st);
+// max |x| over rows x frames of a pitched tensor -> *out (float, must be zeroed by the caller)
+int ctn_absmax_pitch(const float* x, int rows, int frames, int pitch, float* out, cudaStream_t st);
 
 // depthwise stage: u = PReLU(dwconv(gLN1(h))) (+ stats2), all (B,H,pitch)
 int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_b, const float* dw_w, const float* dw_b,
@@ -92,7 +122,6 @@ int ctn_finish_fwd(const float* outraw, const FoldedConv f, const double* stats2
 
 // deferred skip reduction: skip[b][m][t] = sum_i ( rstd2_i[b] * r_i[b][off_i + m][t] + (v1_i[off_i+m] - mean_i rstd_i v2_i[off_i+m]) )
 // over all residual blocks i -- reads every block's skip rows ONCE instead of read-modify-writing the accumulator per block
-#define CTN_MAX_BLOCKS 64
 struct SkipJob { const float* r; const float* v1; const float* v2; const double* stats2; int off; int Mt; };
 struct SkipJobs { SkipJob j[CTN_MAX_BLOCKS]; int n; };
 int ctn_skip_reduce(const SkipJobs& jobs, double n2, float eps, float* skip, int B, int Sc, int frames, int pitch, cudaStream_t st);

@@ -14,28 +14,31 @@
 __global__ void __launch_bounds__(128) k_fold(const float* __restrict__ W, const float* __restrict__ bias,
                                               const float* __restrict__ gamma, const float* __restrict__ beta, int M, int K,
                                               float* __restrict__ Wf, float* __restrict__ v1, float* __restrict__ v2,
-                                              int row_offset) {
+                                              int row_offset, float* __restrict__ vb, float R) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = W[(size_t)row * K + k];
     const float wf = w * gamma[k];
     Wf[(size_t)(row + row_offset) * K + k] = wf;
     s1 = fmaf(w, beta[k], s1);
     s2 += wf;
+    s3 = fmaf(fabsf(w), fmaf(fabsf(gamma[k]), R, fabsf(beta[k])), s3);
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
+  s3 = warp_sum(s3);
   if (lane == 0) {
     v1[row + row_offset] = s1 + (bias ? bias[row] : 0.f);
     v2[row + row_offset] = s2;
+    if (vb) vb[row + row_offset] = s3 + (bias ? fabsf(bias[row]) : 0.f);
   }
 }
 
 int ctn_fold_conv(const float* W, const float* bias, const float* gamma, const float* beta, int M, int K, FoldedConv out,
-                  int row_offset, cudaStream_t st) {
-  k_fold<<<(M + 3) / 4, 128, 0, st>>>(W, bias, gamma, beta, M, K, out.Wf, out.v1, out.v2, row_offset);
+                  int row_offset, cudaStream_t st, float R) {
+  k_fold<<<(M + 3) / 4, 128, 0, st>>>(W, bias, gamma, beta, M, K, out.Wf, out.v1, out.v2, row_offset, out.vb, R);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
@@ -46,19 +49,22 @@ __global__ void __launch_bounds__(128) k_fold_batch(const FoldJobs jobs) {
   const FoldJob& jb = jobs.j[blockIdx.y];
   for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < jb.M; row += gridDim.x * 4) {
     const int lane = threadIdx.x & 31;
-    float s1 = 0.f, s2 = 0.f;
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
     for (int k = lane; k < jb.K; k += 32) {
       const float w = jb.W[(size_t)row * jb.K + k];
       const float wf = w * jb.gamma[k];
       jb.Wf[(size_t)(row + jb.row_offset) * jb.K + k] = wf;
       s1 = fmaf(w, jb.beta[k], s1);
       s2 += wf;
+      s3 = fmaf(fabsf(w), fmaf(fabsf(jb.gamma[k]), jb.R, fabsf(jb.beta[k])), s3);
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
+    s3 = warp_sum(s3);
     if (lane == 0) {
       jb.v1[row + jb.row_offset] = s1 + (jb.bias ? jb.bias[row] : 0.f);
       jb.v2[row + jb.row_offset] = s2;
+      if (jb.vb) jb.vb[row + jb.row_offset] = s3 + (jb.bias ? fabsf(jb.bias[row]) : 0.f);
     }
   }
 }
@@ -72,6 +78,100 @@ int ctn_fold_batch(const FoldJob* jobs, int n, cudaStream_t st) {
     k_fold_batch<<<dim3((maxM + 3) / 4, m), 128, 0, st>>>(fj);
     CTN_COUNT_LAUNCH();
   }
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation envelope of the fp16-piece mode (see ctn_internal.h: ScaleJobs)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_scale_for(float bound) {
+  // largest power of two s with bound * s <= 2^15 (fp16 max 65504); 1 for a zero / non-finite bound
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);  // bound = m 2^e, m in [0.5, 1)  =>  bound <= 2^e
+  e = 15 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.f, e);
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) v = fmaxf(v, red[i]);
+  return v;
+}
+// grid = number of residual blocks: block i packs dwp_i and writes its three partial bounds (U_i, D_out_i, D_skip_i)
+__global__ void __launch_bounds__(256) k_scale_partials(const ScaleJobs jobs, float* __restrict__ part) {
+  __shared__ float red[8];
+  const ScaleJob& jb = jobs.j[blockIdx.x];
+  const int H = jobs.H, P = jobs.P;
+  const float a2 = fmaxf(1.f, fabsf(jb.slope2[0]));
+  float u = 0.f;
+  const int Hp = (H + 15) & ~15;
+  for (int c = threadIdx.x; c < Hp; c += blockDim.x) {
+    float g = 0.f, b = 0.f, bd = 0.f, w[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+    if (c < H) {
+      g = jb.g1[c]; b = jb.b1[c]; bd = jb.dw_b[c];
+      for (int k = 0; k < P; ++k) { const float wk = jb.dw_w[c * P + k]; wsum += fabsf(wk); if (k < 3) w[k] = wk; }
+      u = fmaxf(u, a2 * fmaf(fmaf(fabsf(g), jobs.R, fabsf(b)), wsum, fabsf(bd)));
+    }
+    if (jb.dwp && P == 3) {
+      float4* d = reinterpret_cast<float4*>(jb.dwp + (size_t)c * 8);
+      d[0] = make_float4(g, b, w[0], w[1]);
+      d[1] = make_float4(w[2], bd, 0.f, 0.f);
+    }
+  }
+  u = block_max(u, red);
+  float dout = 0.f, dskip = 0.f;
+  const int Mt = jb.has_out ? jobs.Bc + jobs.Sc : jobs.Sc;
+  for (int n = threadIdx.x; n < Mt; n += blockDim.x) {
+    const float v = jb.vb[n];
+    if (jb.has_out && n < jobs.Bc) dout = fmaxf(dout, v); else dskip = fmaxf(dskip, v);
+  }
+  dout = block_max(dout, red);
+  dskip = block_max(dskip, red);
+  if (threadIdx.x == 0) { part[3 * blockIdx.x] = u; part[3 * blockIdx.x + 1] = dout; part[3 * blockIdx.x + 2] = dskip; }
+}
+__global__ void __launch_bounds__(32) k_scale_chain(const ScaleJobs jobs, const float* __restrict__ part) {
+  if (threadIdx.x != 0) return;
+  float X = 0.f;
+  for (int i = 0; i < jobs.x0_n; ++i) X = fmaxf(X, fabsf(jobs.x0_bound[i]));
+  float S = 0.f;
+  for (int i = 0; i < jobs.n; ++i) {
+    jobs.scales[2 * i] = pow2_scale_for(X);
+    jobs.scales[2 * i + 1] = pow2_scale_for(part[3 * i]);
+    X += part[3 * i + 1];
+    S += part[3 * i + 2];
+  }
+  const float am = jobs.mask_slope ? fmaxf(1.f, fabsf(jobs.mask_slope[0])) : 1.f;
+  jobs.scales[2 * jobs.n] = pow2_scale_for(am * S);
+}
+int ctn_act_scales(const ScaleJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0 || jobs.n > CTN_MAX_BLOCKS) return CTN_EINVAL;
+  float* part = jobs.scales + 2 * jobs.n + 1;  // scratch behind the scales: 3 floats per block
+  k_scale_partials<<<jobs.n, 256, 0, st>>>(jobs, part);
+  CTN_COUNT_LAUNCH();
+  k_scale_chain<<<1, 32, 0, st>>>(jobs, part);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+__global__ void __launch_bounds__(256) k_absmax_pitch(const float* __restrict__ x, int rows, int frames, int pitch, float* __restrict__ out) {
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int t = threadIdx.x; t < frames; t += blockDim.x) m = fmaxf(m, fabsf(x[(size_t)r * pitch + t]));
+  m = block_max(m, red);
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));  // non-negative floats order like uints
+}
+int ctn_absmax_pitch(const float* x, int rows, int frames, int pitch, float* out, cudaStream_t st) {
+  k_absmax_pitch<<<rows < 1024 ? rows : 1024, 256, 0, st>>>(x, rows, frames, pitch, out);
+  CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
 }

@@ -726,6 +726,7 @@ void carve_train(Carver& cv, const ctn_config_t* c, int B, int pitch, TrainWs* w
   ws->head.Wf = cv.take<float>((size_t)Bc * N);
   ws->head.v1 = cv.take<float>(Bc);
   ws->head.v2 = cv.take<float>(Bc);
+  ws->head.vb = nullptr;
   ws->wimg = cv.take<float>(max_wimg_bytes(c) / sizeof(float));
   size_t wmax = (size_t)(Bc + Sc) * H;
   if ((size_t)S * N * Sc > wmax) wmax = (size_t)S * N * Sc;
@@ -769,7 +770,10 @@ int gemm_raw(const ctn_config_t* c, TrainWs& ws, const float* W, int M, int K, c
   memset(&a, 0, sizeof(a));
   a.A = A; a.W = W; a.D = D; a.B = B; a.M = M; a.K = K; a.frames = frames; a.pitch = pitch;
   if (c->math == CTN_MATH_FP32) return ctn_pw_simt(a, PRO_NONE, EPI_RAW, st);
-  const int math = (grad && c->math == CTN_MATH_F16X3) ? CTN_MATH_TF32X3 : c->math;
+  // the training path keeps every contraction on the tf32 pieces: its forward operands (x_i, gLN2 output, skip sum) are
+  // materialised tensors without the per-forward operand scales of the fused inference kernels (ctn_act_scales)
+  (void)grad;
+  const int math = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
   CTN_TRY(ctn_umma_build_wimg(W, M, K, math, ws.wimg, st));
   a.wimg = ws.wimg;
   return ctn_pw_umma(a, PRO_NONE, EPI_RAW, math, st);
@@ -896,6 +900,8 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
     }
   }
   const double nH = (double)H * (double)frames;
+  // un-normalised operands (x_i, skip sum) without operand scales: tf32 pieces (8-bit exponent) in the fp16-piece mode
+  const int fmath = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
   for (int i = 0; i < R * X; ++i) {
     const ctn_block_params_t& q = p->blocks[i];
     const bool has_out = q.out_w != nullptr;
@@ -914,9 +920,9 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
       memset(&a, 0, sizeof(a));
       a.A = ws.x[i]; a.W = q.bottleneck_w; a.D = ws.hpre[i]; a.B = B; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
       a.bias = q.bottleneck_b; a.slope = q.prelu1; a.stats_out = st1; a.store_pre = 1;
-      CTN_TRY(ctn_umma_build_wimg(q.bottleneck_w, H, Bc, c->math, ws.wimg, st));
+      CTN_TRY(ctn_umma_build_wimg(q.bottleneck_w, H, Bc, fmath, ws.wimg, st));
       a.wimg = ws.wimg;
-      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_H, c->math, st));
+      CTN_TRY(ctn_pw_umma(a, PRO_NONE, EPI_H, fmath, st));
     }
     // u_pre = dwconv(gLN1(PReLU(h_pre))) + bd ; stats2 of PReLU(u_pre)
     k_dw_train_fwd<<<grid_cb(H, B), 256, 0, st>>>(ws.hpre[i], ws.upre[i], q.norm1_g, q.norm1_b, q.dw_w, q.dw_b, q.prelu1, q.prelu2,
@@ -945,9 +951,9 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
     if (c->math == CTN_MATH_FP32) {
       CTN_TRY(ctn_pw_simt(a, PRO_PRELU, EPI_MASK, st));
     } else {
-      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, c->math, ws.wimg, st));
+      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, fmath, ws.wimg, st));
       a.wimg = ws.wimg;
-      CTN_TRY(ctn_pw_umma(a, PRO_PRELU, EPI_MASK, c->math, st));
+      CTN_TRY(ctn_pw_umma(a, PRO_PRELU, EPI_MASK, fmath, st));
     }
   }
   CTN_TRY(ctn_decoder_fwd(ws.what, p->dec_w, out, B * S, N, frames, pitch, c->kernel_size, c->stride, pl, T, stream));

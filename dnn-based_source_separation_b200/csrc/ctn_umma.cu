@@ -22,6 +22,7 @@
 // Pipelines: smem ring (full/empty mbarriers, tcgen05.commit frees a stage) and a 2-deep TMEM accumulator ring.
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
+#include "ctn_dw_math.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -86,58 +87,6 @@ struct __align__(8) SmemHeader {
   uint64_t tempty[2];
   uint32_t tmem_base;
 };
-
-// ---- depthwise producer math (PRO_DW) -------------------------------------------------------------------------
-// One channel, 4 consecutive time steps.  q0,q1,q2: the three aligned 128-bit loads (d >= 4: taps t-d, t, t+d;
-// d < 4: the window [t-4, t+8)).  DCLS in {1, 2, 4(=d>=4)} selects the tap positions at compile time.
-// INTERIOR tiles (every tap of every element inside [0, frames)) fold gLN1 into the taps: 3 FMA per output.
-template <int DCLS, bool INTERIOR>
-__device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, const float4 q2, float gsc, float gsh, float w0,
-                                             float w1, float w2, float bd, float slope, int first, int step, int tbase,
-                                             int frames, bool cvalid, float2& ls, float2& lss) {
-  const float win[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-  constexpr int i0 = DCLS == 4 ? 0 : (DCLS == 2 ? 2 : 3);
-  constexpr int i1 = 4;
-  constexpr int i2 = DCLS == 4 ? 8 : (DCLS == 2 ? 6 : 5);
-  float o[4];
-  if (INTERIOR) {
-    // packed fp32 (FFMA2): two time steps per instruction
-    const float a0 = gsc * w0, a1 = gsc * w1, a2 = gsc * w2;
-    const float cst = fmaf(gsh, (w0 + w1) + w2, bd);
-    const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), C = make_float2(cst, cst);
-#pragma unroll
-    for (int e = 0; e < 4; e += 2) {
-      float2 r = __ffma2_rn(A0, make_float2(win[i0 + e], win[i0 + e + 1]), C);
-      r = __ffma2_rn(A1, make_float2(win[i1 + e], win[i1 + e + 1]), r);
-      r = __ffma2_rn(A2, make_float2(win[i2 + e], win[i2 + e + 1]), r);
-      o[e] = r.x;
-      o[e + 1] = r.y;
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      // absolute time of the three taps of element e
-      const int t0 = DCLS == 4 ? first + e : first + i0 + e;
-      const int t1 = DCLS == 4 ? first + step + e : first + i1 + e;
-      const int t2 = DCLS == 4 ? first + 2 * step + e : first + i2 + e;
-      const float h0 = (t0 >= 0 && t0 < frames) ? fmaf(win[i0 + e], gsc, gsh) : 0.f;
-      const float h1 = (t1 >= 0 && t1 < frames) ? fmaf(win[i1 + e], gsc, gsh) : 0.f;
-      const float h2 = (t2 >= 0 && t2 < frames) ? fmaf(win[i2 + e], gsc, gsh) : 0.f;
-      o[e] = fmaf(w2, h2, fmaf(w1, h1, fmaf(w0, h0, bd)));
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float u = prelu_f(o[e], slope);
-    if (!INTERIOR && (tbase + e >= frames || !cvalid)) u = 0.f;
-    o[e] = u;
-  }
-  const float2 u01 = make_float2(o[0], o[1]), u23 = make_float2(o[2], o[3]);
-  ls = __fadd2_rn(ls, __fadd2_rn(u01, u23));
-  lss = __ffma2_rn(u01, u01, lss);
-  lss = __ffma2_rn(u23, u23, lss);
-  return make_float4(o[0], o[1], o[2], o[3]);
-}
 
 template <int DCLS, bool INTERIOR, int CPW>
 __device__ __forceinline__ void dw_slab(const PwArgs& a, int b, int ks, int pw, int tbase, float2 mr1, float pslope, bool skip_loads,
@@ -218,9 +167,14 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
     if constexpr (pair) ptx::tmem_alloc2(ptx::smem_u32(&hdr->tmem_base), 512);
     else ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
   }
+  // fp16 pieces: power-of-two scale of the activation operand (|operand| * act_s <= 2^15 by construction, ctn_act_scales),
+  // undone together with the weight-group scales in the epilogue
+  float act_s = 1.f;
   if constexpr (F16) {
+    if (a.act_scale) act_s = __ldg(a.act_scale);
+    const float inv = 1.f / act_s;
     float* ssc_all = reinterpret_cast<float*>(smem + SMEM_SCALES);
-    for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += blockDim.x) ssc_all[i] = __ldg(g.oscale + i);
+    for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += blockDim.x) ssc_all[i] = __ldg(g.oscale + i) * inv;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -384,6 +338,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
             x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
           }
           if constexpr (F16) {
+            x.x *= act_s; x.y *= act_s; x.z *= act_s; x.w *= act_s;
             // MN-major 16-bit SWIZZLE_128B: atoms of 64 time steps x 8 channels (1024 B): channel row r = kl & 7 at r*128 B,
             // 16-byte chunks (8 time steps) XOR r; time atoms 1024 B apart (LBO), 8-channel groups 2048 B apart (SBO)
             const uint32_t r8 = (uint32_t)(kl & 7);
