@@ -496,6 +496,83 @@ extern "C" int ctn_separator_fwd(const ctn_config_t* cfg, const ctn_params_t* pa
 }
 
 // ------------------------------------------------------------------------------------------------
+// separator stages on the pitched layout (used by the DPRNN-TasNet path, whose dual-path blocks run between them)
+// ------------------------------------------------------------------------------------------------
+struct StageWs { FoldedConv head; float* wimg; };
+static void carve_stage(Carver& cv, int M, int K, int math, StageWs* ws) {
+  ws->head.Wf = cv.take<float>((size_t)M * K);
+  ws->head.v1 = cv.take<float>(M);
+  ws->head.v2 = cv.take<float>(M);
+  ws->head.vb = nullptr;
+  ws->wimg = math != CTN_MATH_FP32 ? cv.take<float>(ctn_umma_wimg_bytes(M, K, math) / sizeof(float)) : nullptr;
+}
+extern "C" size_t ctn_stage_workspace_bytes(int M, int K) {
+  if (M <= 0 || K <= 0) return 0;
+  Carver cv(nullptr);
+  StageWs ws;
+  carve_stage(cv, M, K, CTN_MATH_TF32X3, &ws);
+  return cv.off + 512;
+}
+
+// Separator head (src/models/conv_tasnet.py:370-371 == src/models/dprnn_tasnet.py:335-336): x0 = Wb gLN(w) + bb with the gLN
+// folded into the contraction.  w (B, N, pitch) pitched, stats0 = double[B][2] (sum, sumsq) of w over its valid frames (as
+// ctn_encoder_fwd leaves them); x0 (B, Bc, pitch) pitched.  The operand is un-normalised: fp16-piece mode runs on tf32 pieces.
+extern "C" int ctn_sep_head_fwd(const float* w, const double* stats0, const float* norm_g, const float* norm_b, const float* bn_w,
+                                const float* bn_b, float* x0, int B, int N, int Bc, int frames, int pitch, float eps, int math,
+                                void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope(w);
+  if (!w || !stats0 || !norm_g || !norm_b || !bn_w || !x0 || !workspace || B <= 0 || N <= 0 || Bc <= 0 || frames <= 0) return CTN_EINVAL;
+  if (pitch < frames || pitch % CTN_TILE_T != 0 || (((uintptr_t)workspace) & 255)) return CTN_EALIGN;
+  if (workspace_bytes < ctn_stage_workspace_bytes(Bc, N)) return CTN_EWORKSPACE;
+  if (math == CTN_MATH_F16X3) math = CTN_MATH_TF32X3;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  StageWs ws;
+  carve_stage(cv, Bc, N, math, &ws);
+  CTN_TRY(ctn_fold_conv(bn_w, bn_b, norm_g, norm_b, Bc, N, ws.head, 0, st));
+  PwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = w; a.W = ws.head.Wf; a.D = x0; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
+  a.v1 = ws.head.v1; a.v2 = ws.head.v2; a.stats_in = stats0; a.n_in = (double)N * (double)frames; a.eps = eps;
+  if (math != CTN_MATH_FP32) {
+    CTN_TRY(ctn_umma_build_wimg(ws.head.Wf, Bc, N, math, ws.wimg, st));
+    a.wimg = ws.wimg;
+  }
+  return pw_dispatch(a, PRO_NONE, EPI_HEAD, math, st);
+}
+
+// Separator tail + decoder (conv_tasnet.py:373-376, 158-169 == dprnn_tasnet.py:348-350 + 141-153): PReLU -> mask 1x1 -> sigmoid ->
+// w * mask -> ConvTranspose1d -> crop.  y (B, Bc, pitch), w (B, N, pitch) pitched; out (B, S, T) contiguous; latent (nullable)
+// (B, S, N, frames) contiguous; what: (B, S*N, pitch) scratch for w_hat.
+extern "C" int ctn_sep_tail_fwd(const float* y, const float* w, const float* prelu, const float* mask_w, const float* mask_b,
+                                const float* dec_w, float* out, float* latent, float* what, int B, int N, int Bc, int S, int frames,
+                                int pitch, int L, int stride, int crop_left, int T, int math, void* workspace, size_t workspace_bytes,
+                                ctn_stream_t stream) {
+  LaunchScope scope(y);
+  if (!y || !w || !prelu || !mask_w || !mask_b || !dec_w || !out || !what || !workspace || B <= 0 || N <= 0 || Bc <= 0 || S <= 0 || frames <= 0)
+    return CTN_EINVAL;
+  if (pitch < frames || pitch % CTN_TILE_T != 0 || (((uintptr_t)workspace) & 255)) return CTN_EALIGN;
+  if (workspace_bytes < ctn_stage_workspace_bytes(S * N, Bc)) return CTN_EWORKSPACE;
+  if (math == CTN_MATH_F16X3) math = CTN_MATH_TF32X3;  // un-normalised operand without a static bound: tf32 pieces
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  StageWs ws;
+  carve_stage(cv, S * N, Bc, math, &ws);
+  PwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = y; a.W = mask_w; a.D = what; a.B = B; a.M = S * N; a.K = Bc; a.frames = frames; a.pitch = pitch;
+  a.pro_slope = prelu; a.bias = mask_b; a.wenc = w; a.Nb = N;
+  if (math != CTN_MATH_FP32) {
+    CTN_TRY(ctn_umma_build_wimg(mask_w, S * N, Bc, math, ws.wimg, st));
+    a.wimg = ws.wimg;
+  }
+  CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, math, st));
+  CTN_TRY(ctn_decoder_fwd(what, dec_w, out, B * S, N, frames, pitch, L, stride, crop_left, T, stream));
+  if (latent) CTN_TRY(ctn_copy_from_pitch(what, latent, B * S * N, frames, pitch, st));
+  return CTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // end-to-end with host buffers
 // ------------------------------------------------------------------------------------------------
 struct HostIo {

@@ -1,0 +1,120 @@
+"""Dual-path RNN blocks behind the reference's class API (src/models/dprnn.py:9-148).
+
+``DPRNN`` / ``DPRNNBlock`` / ``IntraChunkRNN`` / ``InterChunkRNN`` keep the reference's constructors, module tree and
+``state_dict`` keys (``rnn.weight_ih_l0`` ..., ``fc.weight/bias``, ``norm1d.norm.weight/bias``).
+
+What runs where: the dual-path state lives CHANNELS-LAST, (batch, D1, D2, features) -- already the batch_first tensor the
+path's LSTM consumes, so none of the reference's permute().contiguous() copies exist.  The bi-LSTM recurrence is cuDNN
+(``nn.LSTM``) and the 2H -> F projection a library GEMM (``F.linear``): sequential recurrences / plain GEMMs are the one
+place a library is the right tool.  Everything between them -- gLN statistics, normalisation,
+residual add and the intra <-> inter layout swap -- is ONE native call (ctn_dprnn_norm_res_fwd, csrc/ctn_dprnn.cu).
+Envelope: non-causal (gLN, bidirectional inter-chunk LSTM), rnn_type='lstm', norm=True; forward only.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F_
+
+from .. import _native as N
+from ..utils.tasnet import choose_layer_norm
+from .transform import ctn_dprnn_norm_res_fwd
+
+EPS = 1e-12
+
+
+def choose_rnn(name, **kwargs):
+    """src/utils/model.py:22-32"""
+    if name == 'rnn':
+        return nn.RNN(**kwargs)
+    if name == 'lstm':
+        return nn.LSTM(**kwargs)
+    if name == 'gru':
+        return nn.GRU(**kwargs)
+    raise NotImplementedError("Invalid RNN is specified. Choose 'rnn', 'lstm', or 'gru' instead of {}.".format(name))
+
+
+class _ChunkRNN(nn.Module):
+    def __init__(self, num_features, hidden_channels, causal_rnn, norm=True, rnn_type='lstm', eps=EPS):
+        super().__init__()
+        self.num_features, self.hidden_channels = num_features, hidden_channels
+        self.norm = norm
+        if rnn_type != 'lstm':
+            raise NotImplementedError("Not support {}.".format(rnn_type))
+        if causal_rnn:
+            raise NotImplementedError("causal DPRNN (uni-directional inter-chunk LSTM + cLN) is outside the sm_100a path")
+        self.rnn = choose_rnn(rnn_type, input_size=num_features, hidden_size=hidden_channels, batch_first=True, bidirectional=True)
+        self.fc = nn.Linear(2 * hidden_channels, num_features)
+        if not norm:
+            raise NotImplementedError("norm=False is outside the sm_100a path")
+        self.norm1d = choose_layer_norm('gLN', num_features, causal=False, eps=eps)
+        self.eps = eps
+
+    def _step(self, z, swap):
+        """z (B, D1, D2, F) channels-last -> gLN(fc(rnn(z))) + z, stored as (B, D2, D1, F) when swap."""
+        B, D1, D2, F = z.shape
+        dev = N.require_cuda(z)
+        self.rnn.flatten_parameters()
+        y, _ = self.rnn(z.view(B * D1, D2, F))                  # cuDNN bi-LSTM over D2
+        y = F_.linear(y, self.fc.weight, self.fc.bias)           # (B*D1, D2, F)
+        out = torch.empty((B, D2, D1, F) if swap else (B, D1, D2, F), dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * B, dtype=torch.float64, device=dev)
+        g, b = self.norm1d.norm.weight, self.norm1d.norm.bias
+        N.check(ctn_dprnn_norm_res_fwd(y.data_ptr(), z.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), B, D1, D2, F,
+                                       float(self.eps), int(swap), scratch.data_ptr(), N.stream_ptr(dev)), "ctn_dprnn_norm_res_fwd")
+        return out
+
+
+class IntraChunkRNN(_ChunkRNN):
+    def __init__(self, num_features, hidden_channels, norm=True, rnn_type='lstm', eps=EPS):
+        super().__init__(num_features, hidden_channels, causal_rnn=False, norm=norm, rnn_type=rnn_type, eps=eps)
+
+    def forward(self, input):
+        """input, output (batch_size, num_features, S, chunk_size) -- the reference layout (dprnn.py:70-94)"""
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("the DPRNN path is forward-only: call under torch.no_grad()")
+        z = input.permute(0, 2, 3, 1).contiguous()
+        return self._step(z, swap=False).permute(0, 3, 1, 2).contiguous()
+
+
+class InterChunkRNN(_ChunkRNN):
+    def __init__(self, num_features, hidden_channels, causal, norm=True, rnn_type='lstm', eps=EPS):
+        super().__init__(num_features, hidden_channels, causal_rnn=causal, norm=norm, rnn_type=rnn_type, eps=eps)
+
+    def forward(self, input):
+        """input, output (batch_size, num_features, S, chunk_size) (dprnn.py:122-148)"""
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("the DPRNN path is forward-only: call under torch.no_grad()")
+        z = input.permute(0, 3, 2, 1).contiguous()             # (B, K, S, F)
+        return self._step(z, swap=False).permute(0, 3, 2, 1).contiguous()
+
+
+class DPRNNBlock(nn.Module):
+    def __init__(self, num_features, hidden_channels, causal, norm=True, rnn_type='lstm', eps=EPS):
+        super().__init__()
+        self.intra_chunk_block = IntraChunkRNN(num_features, hidden_channels, norm=norm, rnn_type=rnn_type, eps=eps)
+        self.inter_chunk_block = InterChunkRNN(num_features, hidden_channels, norm=norm, causal=causal, rnn_type=rnn_type, eps=eps)
+
+    def forward(self, input):
+        return self.inter_chunk_block(self.intra_chunk_block(input))
+
+    def forward_channels_last(self, z):
+        """z (B, S, K, F) -> (B, S, K, F): intra (swap to (B, K, S, F)), inter (swap back)"""
+        return self.inter_chunk_block._step(self.intra_chunk_block._step(z, swap=True), swap=True)
+
+
+class DPRNN(nn.Module):
+    def __init__(self, num_features, hidden_channels, num_blocks=6, norm=True, causal=False, rnn_type='lstm', eps=EPS):
+        super().__init__()
+        self.net = nn.Sequential(*[DPRNNBlock(num_features, hidden_channels, norm=norm, causal=causal, rnn_type=rnn_type, eps=eps)
+                                   for _ in range(num_blocks)])
+
+    def forward(self, input):
+        """input, output (batch_size, num_features, S, chunk_size)"""
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("the DPRNN path is forward-only: call under torch.no_grad()")
+        z = input.permute(0, 2, 3, 1).contiguous()
+        return self.forward_channels_last(z).permute(0, 3, 1, 2).contiguous()
+
+    def forward_channels_last(self, z):
+        for blk in self.net:
+            z = blk.forward_channels_last(z)
+        return z

@@ -116,6 +116,52 @@ def grad_case(name, cfg: O.OracleConfig, batch, T, wseed, xseed, stride=97):
     print(f"{name}: loss {float(loss):.6f} perm {perm.tolist()} {len(grads)} gradient tensors -> {os.path.getsize(path)} B")
 
 
+def dprnn_cases():
+    """DPRNN-TasNet (BASELINE cfg4) goldens from the unmodified reference: transform.py modules, one tiny model, and the cfg4
+    hyper-parameters (N=64 L=2 F=64 H=128 K=250 P=125 B=6) on a short batch (strided subsample + fp64 checksums)."""
+    from models.dprnn_tasnet import DPRNNTasNet  # reference
+    from models.transform import Segment1d, OverlapAdd1d
+    import dprnn_oracle as DO
+    rec = {}
+    g = torch.Generator().manual_seed(17)
+    for (B, Fc, T, K, P) in [(2, 3, 5, 3, 2), (2, 6, 103, 10, 5), (1, 4, 40, 7, 3)]:
+        x = torch.randn(B, Fc, T, generator=g)
+        seg = Segment1d(K, P)(x)
+        rec[f"segment_{B}_{Fc}_{T}_{K}_{P}"] = {"x": x, "seg": seg, "ola": OverlapAdd1d(K, P)(seg)}
+    torch.save(rec, os.path.join(HERE, "dprnn_modules.pt"))
+    for name, cfg, batch, T, sub in [
+        ("dprnn_tiny", DO.DPRNNConfig(n_basis=16, kernel_size=4, sep_hidden_channels=12, sep_bottleneck_channels=8, sep_chunk_size=10,
+                                      sep_hop_size=5, sep_num_blocks=2, n_sources=2), 2, 203, None),
+        ("dprnn_cfg4_short", DO.DPRNNConfig(n_basis=64, kernel_size=2, sep_hidden_channels=128, sep_bottleneck_channels=64,
+                                            sep_chunk_size=250, sep_hop_size=125, sep_num_blocks=6, n_sources=2), 2, 4000, 13),
+    ]:
+        ref = DPRNNTasNet(cfg.n_basis, cfg.kernel_size, stride=cfg.stride, enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
+                          sep_hidden_channels=cfg.sep_hidden_channels, sep_bottleneck_channels=cfg.sep_bottleneck_channels,
+                          sep_chunk_size=cfg.sep_chunk_size, sep_hop_size=cfg.sep_hop_size, sep_num_blocks=cfg.sep_num_blocks,
+                          sep_norm=True, mask_nonlinear="sigmoid", causal=False, rnn_type="lstm", n_sources=cfg.n_sources, eps=cfg.eps)
+        ref_keys = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+        assert ref_keys == [(k, tuple(sh)) for k, sh in DO.state_dict_spec(cfg)], "dprnn state_dict_spec does not match the reference"
+        sd = DO.synth_state_dict(cfg, seed=31)
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        mixture, sources = O.synth_batch(batch, cfg.n_sources, T, seed=32)
+        with torch.no_grad():
+            out, latent = ref.extract_latent(mixture)
+            loss, perm = PIT1d(NegSISDR(), n_sources=cfg.n_sources)(out, sources)
+        r = {"name": name, "cfg": cfg.to_dict(), "batch": batch, "T": T, "wseed": 31, "xseed": 32, "loss": loss.clone(), "perm": perm.clone(),
+             "out_sum": float(out.double().sum()), "out_sumsq": float((out.double() ** 2).sum()), "out_absmax": float(out.abs().max())}
+        if sub is None:
+            r["out"], r["latent"] = out.clone(), latent.clone()
+        else:
+            r["out_stride"] = sub
+            r["out"] = out[..., ::sub].clone()
+            r["latent_stride"] = (7, 29)
+            r["latent"] = latent[:, :, ::7, ::29].clone()
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(r, path)
+        print(f"{name}: out {tuple(out.shape)} absmax {r['out_absmax']:.4f} loss {float(loss):.6f} perm {perm.tolist()} -> {os.path.getsize(path)} B")
+
+
 def module_cases():
     rec = {}
     # gLN / cLN: the reference's own self-test input (src/modules/norm.py:107-116) + a random one
@@ -196,6 +242,9 @@ def module_cases():
 def main():
     paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
                  sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
+    if len(sys.argv) > 1 and sys.argv[1] == "dprnn":
+        dprnn_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "grad":   # mint only the training golden (the forward fixtures are unchanged)
         grad_case("paper_3spk_grad", O.OracleConfig(**paper, causal=False, n_sources=3), batch=2, T=8000, wseed=113, xseed=113)
         return
@@ -215,6 +264,7 @@ def main():
                xseed=112, subsample=17)
     module_cases()
     grad_case("paper_3spk_grad", O.OracleConfig(**paper, causal=False, n_sources=3), batch=2, T=8000, wseed=113, xseed=113)
+    dprnn_cases()
 
 
 if __name__ == "__main__":
