@@ -85,6 +85,14 @@ ctn_last_launch_count = _sig("ctn_last_launch_count", _i)
 ctn_debug_pointwise = _sig("ctn_debug_pointwise", _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _i,
                            C.POINTER(C.c_uint32), _fp, _sz, _fp)
 ctn_debug_timeline = _sig("ctn_debug_timeline", _i, C.POINTER(C.c_ulonglong), _i)
+# DPRNN-TasNet path (cfg4) + separator stages on the pitched layout
+ctn_segment_fwd = _sig("ctn_segment_fwd", _i, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp)
+ctn_overlap_add_fwd = _sig("ctn_overlap_add_fwd", _i, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp)
+ctn_dprnn_norm_res_fwd = _sig("ctn_dprnn_norm_res_fwd", _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _i, _fp, _fp)
+ctn_stage_workspace_bytes = _sig("ctn_stage_workspace_bytes", _sz, _i, _i)
+ctn_sep_head_fwd = _sig("ctn_sep_head_fwd", _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _i, _fp, _sz, _fp)
+ctn_sep_tail_fwd = _sig("ctn_sep_tail_fwd", _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                        _fp, _sz, _fp)
 ctn_profile_enable = _sig("ctn_profile_enable", _i, _i)
 ctn_profile_read = _sig("ctn_profile_read", _i, C.POINTER(C.c_double), C.POINTER(_i))
 STAGES = ("prep", "enc", "head", "pw1", "dw", "pw2", "fin", "mask", "dec", "loss")
@@ -96,6 +104,7 @@ EXPORTED = [
     "ctn_convtasnet_loss_host", "ctn_train_workspace_bytes", "ctn_convtasnet_fwd_train", "ctn_convtasnet_bwd",
     "ctn_sisdr_pit_bwd", "ctn_last_launch_count", "ctn_profile_enable", "ctn_profile_read",
     "ctn_debug_pointwise", "ctn_debug_timeline",
+    "ctn_segment_fwd", "ctn_overlap_add_fwd", "ctn_dprnn_norm_res_fwd", "ctn_stage_workspace_bytes", "ctn_sep_head_fwd", "ctn_sep_tail_fwd",
 ]
 
 

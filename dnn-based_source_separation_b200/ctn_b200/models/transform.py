@@ -5,32 +5,13 @@ Mirrors src/models/transform.py:6-65 of the reference (same constructors, same s
 ``OverlapAdd1d`` sums the overlapping chunks back into (batch, features, (S - 1) * hop_size + chunk_size).
 The DPRNN separator uses the same kernels with ``channels_last=1`` and the padding / crop fused in.
 """
-import ctypes as C
-
 import torch
 import torch.nn as nn
 
 from .. import _native as N
 
-_i, _fp = C.c_int, C.c_void_p
-
-
-def _bind(name, *argtypes):
-    fn = getattr(N.lib, name)
-    fn.restype = C.c_int
-    fn.argtypes = list(argtypes)
-    return fn
-
-
-ctn_segment_fwd = _bind("ctn_segment_fwd", _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp)
-ctn_overlap_add_fwd = _bind("ctn_overlap_add_fwd", _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp)
-ctn_dprnn_norm_res_fwd = _bind("ctn_dprnn_norm_res_fwd", _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, C.c_float, _i, _fp, _fp)
-ctn_stage_workspace_bytes = getattr(N.lib, "ctn_stage_workspace_bytes")
-ctn_stage_workspace_bytes.restype = C.c_size_t
-ctn_stage_workspace_bytes.argtypes = [_i, _i]
-ctn_sep_head_fwd = _bind("ctn_sep_head_fwd", _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _i, _fp, C.c_size_t, _fp)
-ctn_sep_tail_fwd = _bind("ctn_sep_tail_fwd", _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp,
-                         C.c_size_t, _fp)
+ctn_segment_fwd, ctn_overlap_add_fwd, ctn_dprnn_norm_res_fwd = N.ctn_segment_fwd, N.ctn_overlap_add_fwd, N.ctn_dprnn_norm_res_fwd
+ctn_stage_workspace_bytes, ctn_sep_head_fwd, ctn_sep_tail_fwd = N.ctn_stage_workspace_bytes, N.ctn_sep_head_fwd, N.ctn_sep_tail_fwd
 
 
 class Segment1d(nn.Module):
