@@ -3,12 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one process per GPU under torchrun)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py --config cfg4                            # DPRNN-TasNet (segment / overlap-add path), its own line
+    python bench.py --train [--n-sources 3 --batch 8]        # the training step alone, its own line
 
 Workload (BASELINE.json configs[1], "cfg2"): Conv-TasNet N=512 L=16 B=128 H=512 Sc=128 P=3 X=8 R=3, gLN, 2 speakers,
 batch 32 x 4 s @ 8 kHz per GPU (weak scaling: every rank gets its own batch of 32; no data-path collective).
 A "step" = one pass of the hot path (model forward + PIT(NegSISDR) loss) over one batch of synthetic mixtures.
-Prints ONE JSON line on rank 0.  value = device-resident throughput; e2e = through the public module API with pinned
-host inputs, H2D copies and the D2H loss/permutation read inside the timed region.
+Prints ONE JSON line on rank 0:
+  value  = device-resident throughput (stage timers OFF), max over ranks, CUDA events;
+  e2e    = the same through the C-ABI host-buffer call (ctn_convtasnet_loss_host via ConvTasNet.separate_host): pinned host
+           mixture + sources -> H2D -> forward + PIT -> D2H of the separated estimates, loss and permutation, every step;
+  stages = per-kernel-group CUDA-event times from a SEPARATE short pass with the library's stage timers on;
+  train  = the data-parallel TRAINING step at the cfg3 per-GPU shape (3 speakers, batch 8 per GPU): fwd + PIT + backward +
+           ONE gradient all-reduce (timed on its own) + native clip/Adam -- the path that has a collective, at every N;
+  ddp_check (N > 1) = all-reduced shard gradients vs the same global batch on one GPU (small model), worst relative error.
 """
 import argparse
 import json
@@ -21,10 +29,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dnn-based_source_separation_b200"))
 
-SR = 8000
 PAPER = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128, sep_skip_channels=128,
              sep_kernel_size=3, sep_num_blocks=3, sep_num_layers=8)
+CFG4 = dict(n_basis=64, kernel_size=2, sep_hidden_channels=128, sep_bottleneck_channels=64, sep_chunk_size=250, sep_hop_size=125,
+            sep_num_blocks=6)
 METRIC = "audio-sec/s Conv-TasNet 2spk 4s@8kHz fwd+SI-SDR-PIT"
+CPU_THREADS = 32  # fixed team size of the CPU arm (torch's intra-op pool stops scaling around here on these tensor sizes)
 
 
 def parse():
@@ -33,16 +43,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
-    ap.add_argument("--seconds", type=float, default=4.0)
-    ap.add_argument("--sample-rate", type=int, default=8000, help="Hz; cfg5 of BASELINE.json is 8 s @ 16 kHz")
-    ap.add_argument("--n-sources", type=int, default=2)
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 (default, the headline), cfg3 = 3 speakers batch 8 per GPU, cfg5 = 4 speakers 8 s @ 16 kHz batch 16 per GPU, "
+                         "cfg4 = DPRNN-TasNet batch 16")
+    ap.add_argument("--batch", type=int, default=None, help="mixtures per GPU per step")
+    ap.add_argument("--seconds", type=float, default=None)
+    ap.add_argument("--sample-rate", type=int, default=None)
+    ap.add_argument("--n-sources", type=int, default=None)
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32", "f16x3"])
-    ap.add_argument("--cpu-batch", type=int, default=4, help="mixtures per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=None, help="mixtures per CPU-arm step (default: the full per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--train", action="store_true",
-                    help="time the TRAINING step instead (fwd + PIT + backward + gradient all-reduce + clip + Adam); prints its own line")
-    return ap.parse_args()
+    ap.add_argument("--no-train-block", action="store_true")
+    ap.add_argument("--train", action="store_true", help="time the TRAINING step only; prints its own line")
+    a = ap.parse_args()
+    d = {"cfg2": (32, 4.0, 8000, 2), "cfg3": (8, 4.0, 8000, 3), "cfg4": (16, 4.0, 8000, 2), "cfg5": (16, 8.0, 16000, 4)}[a.config]
+    a.batch = a.batch if a.batch is not None else d[0]
+    a.seconds = a.seconds if a.seconds is not None else d[1]
+    a.sample_rate = a.sample_rate if a.sample_rate is not None else d[2]
+    a.n_sources = a.n_sources if a.n_sources is not None else d[3]
+    return a
 
 
 def peaks():
@@ -97,68 +116,182 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(args, world):
+    """The `config` object of BOTH arms (ours and --impl reference): same keys, same values => same_config."""
+    B, S = args.batch, args.n_sources
+    if args.config == "cfg4":
+        wl = (f"cfg4: DPRNN-TasNet {S}spk N64 L2 F64 H128 K250 P125 B6 gLN sigmoid, batch {B} x {args.seconds:g}s@{args.sample_rate // 1000}kHz per GPU, "
+              "fwd + PIT(NegSISDR)")
+    else:
+        wl = (f"{args.config}: Conv-TasNet {S}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN sigmoid, batch {B} x {args.seconds:g}s@"
+              f"{args.sample_rate // 1000}kHz per GPU, fwd + PIT(NegSISDR)")
+    return {"workload": wl, "global_batch": world * B,
+            "l2": "per-step activation traffic (> 2 GB) exceeds the 126 MB L2 many times over; no explicit flush"}
+
+
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_leg(args, steps, warmup):
-    """The reference algorithm (oracle port, plain PyTorch CPU ops = what the reference executes) on all host cores,
-    on a bounded sample of the workload: cpu-batch mixtures of the same 4 s @ 8 kHz shape per step."""
+def cpu_reference_leg(args, steps, warmup, cpu_batch):
+    """The reference algorithm (oracle port, plain PyTorch CPU ops = the ATen ops the reference dispatches to) on the host cores,
+    fixed team of CPU_THREADS torch threads, `cpu_batch` mixtures of the workload's shape per step."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import convtasnet_oracle as O
     cores = os.cpu_count() or 1
-    cfg = O.OracleConfig(**PAPER, causal=False, n_sources=args.n_sources)
-    sd = O.synth_state_dict(cfg, seed=111)
+    thr = min(CPU_THREADS, cores)
+    torch.set_num_threads(thr)
     T = int(args.seconds * args.sample_rate)
-    mixture, sources = O.synth_batch(args.cpu_batch, args.n_sources, T, seed=111)
-    # "all the host threads it can use": torch's intra-op pool saturates well below 128 threads on these tensor sizes and
-    # gets SLOWER beyond that, so sweep a few team sizes on one sample and keep the fastest (reported as `cores`).
-    best_thr, best_t = cores, float("inf")
-    sweep = sorted({t for t in (8, 16, 32, 64, cores) if t <= cores})
-    with torch.no_grad():
-        for thr in sweep:
-            torch.set_num_threads(thr)
-            O.conv_tasnet_fwd(mixture[:1], sd, cfg)
-            t0 = time.perf_counter()
-            O.conv_tasnet_fwd(mixture[:1], sd, cfg)
-            dt = time.perf_counter() - t0
-            if dt < best_t:
-                best_thr, best_t = thr, dt
-    torch.set_num_threads(best_thr)
+    if args.config == "cfg4":
+        import dprnn_oracle as DO
+        cfg = DO.DPRNNConfig(**CFG4, n_sources=args.n_sources)
+        sd = DO.synth_state_dict(cfg, seed=111)
+        fwd = lambda m: DO.dprnn_tasnet_fwd(m, sd, cfg)
+    else:
+        cfg = O.OracleConfig(**PAPER, causal=False, n_sources=args.n_sources)
+        sd = O.synth_state_dict(cfg, seed=111)
+        fwd = lambda m: O.conv_tasnet_fwd(m, sd, cfg)
+    mixture, sources = O.synth_batch(cpu_batch, args.n_sources, T, seed=111)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out, _ = O.conv_tasnet_fwd(mixture, sd, cfg)
+            out, _ = fwd(mixture)
             loss, perm = O.pit_neg_sisdr(out, sources)
             float(loss)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = args.cpu_batch * args.seconds * len(times) / total
-    return dict(value=value, unit="audio-sec/s", cores=best_thr, threads=torch.get_num_threads(), kind="port",
-                sample=f"{args.cpu_batch} x {args.seconds:g} s @ {args.sample_rate} Hz per step, {len(times)} steps (+{warmup} warm-up), "
-                       f"oracle/convtasnet_oracle.py fwd+PIT under no_grad, {best_thr} torch threads (fastest of {sweep}) on "
-                       f"{cores} logical cores",
+    value = cpu_batch * args.seconds * len(times) / total
+    return dict(value=value, unit="audio-sec/s", cores=thr, kind="port",
+                sample=f"{cpu_batch} x {args.seconds:g} s @ {args.sample_rate} Hz per step, {len(times)} steps (+{warmup} warm-up), "
+                       f"oracle/ port of the reference forward + PIT under no_grad, {thr} torch threads on {cores} logical cores",
                 ms_per_step=1e3 * total / len(times))
 
 
 def stage_model(args, B, frames, T):
-    """Algorithmic (bytes, flops) per LAUNCH of each stage."""
+    """Algorithmic (bytes, flops) per kernel GROUP of each stage: one group = one launch, except `prep`."""
     N, Bc, H, Sc, S = PAPER["n_basis"], PAPER["sep_bottleneck_channels"], PAPER["sep_hidden_channels"], PAPER["sep_skip_channels"], args.n_sources
     L = PAPER["kernel_size"]
+    RX = PAPER["sep_num_blocks"] * PAPER["sep_num_layers"]
     f = frames * B * 4.0
     Mt = Bc + Sc
     return {
         "enc": (B * T * 4.0 + N * f, 2.0 * N * L * frames * B, "hbm"),
         "head": ((N + Bc) * f, 2.0 * N * Bc * frames * B, "tensor"),
-        "pw1": ((Bc + H) * f, 2.0 * Bc * H * frames * B, "tensor"),
+        # pw1 reads x_prev and the previous block's r[:Bc], writes x and h
+        "pw1": ((3 * Bc + H) * f, 2.0 * Bc * H * frames * B, "tensor"),
         "dw": (2.0 * H * f, 2.0 * 3 * H * frames * B, "hbm"),
         "pw2": ((H + Mt) * f, 2.0 * H * Mt * frames * B, "tensor"),
-        "fin": (3.0 * Mt * f, 2.0 * Mt * frames * B, "hbm"),
+        # ONE launch: reads the skip rows of all RX blocks, writes the skip sum
+        "fin": ((RX * Sc + Sc) * f, 2.0 * RX * Sc * frames * B, "hbm"),
         "mask": ((Sc + N + S * N) * f, 2.0 * Sc * S * N * frames * B, "tensor"),
         "dec": (S * N * f + S * B * T * 4.0, 2.0 * S * N * L * frames * B, "hbm"),
         "loss": (2 * 2.0 * S * B * T * 4.0 / 3.0, 0.0, "hbm"),   # 3 launches share two passes over est+tgt
         "prep": (0.0, 0.0, "hbm"),
     }
+
+
+def cuda_time(fn, steps, torch, D, dev, sampler=None):
+    """barrier + synchronize, EXACTLY `steps` calls between two CUDA events, synchronize + barrier; max over ranks (ms)."""
+    D.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ret = None
+    for _ in range(steps):
+        ret = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms_local = e0.elapsed_time(e1)
+    return D.max_over_ranks(ms_local, dev), ms_local, ret
+
+
+def build_convtasnet(args, dev, torch, S):
+    from ctn_b200.models.conv_tasnet import ConvTasNet
+    torch.manual_seed(111)  # reference default seed (train.sh:59); default init = the reference's default init
+    m = ConvTasNet(PAPER["n_basis"], PAPER["kernel_size"], enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
+                   sep_hidden_channels=PAPER["sep_hidden_channels"], sep_bottleneck_channels=PAPER["sep_bottleneck_channels"],
+                   sep_skip_channels=PAPER["sep_skip_channels"], sep_kernel_size=3, sep_num_blocks=3, sep_num_layers=8,
+                   causal=False, n_sources=S).to(dev)
+    m.math = args.math
+    return m
+
+
+def train_leg(args, torch, N, D, dev, rank, world, S, B, steps, warmup):
+    """Data-parallel training step (egs/wsj0-mix/common/src/driver.py:146-157): fwd_train + PIT + native backward + ONE gradient
+    all-reduce + native global-norm clip + Adam.  Returns the `train` block."""
+    from ctn_b200.criterion.sdr import NegSISDR
+    from ctn_b200.criterion.pit import PIT1d
+    from ctn_b200.optim import FlatClipAdam
+    T = int(args.seconds * args.sample_rate)
+    model = build_convtasnet(args, dev, torch, S).train()
+    crit = PIT1d(NegSISDR(), S)
+    g = torch.Generator().manual_seed(211 + rank)
+    sources = (0.1 * torch.randn(B, S, T, generator=g)).to(dev)
+    mixture = sources.sum(dim=1, keepdim=True)
+    opt = FlatClipAdam(model, lr=1e-3, max_norm=5.0)
+    ar_ev = []
+
+    def step():
+        opt.zero_grad()
+        loss, _ = crit(model(mixture), sources)
+        loss.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nel = D.allreduce_gradients(model)
+        e1.record()
+        ar_ev.append((e0, e1))
+        opt.step()
+        return loss, nel
+
+    for _ in range(max(warmup, 2)):
+        loss, nel = step()
+    launches = model.last_launches + model.last_bwd_launches + opt.launches_per_step
+    ar_ev.clear()
+    ms, _, (loss, nel) = cuda_time(step, steps, torch, D, dev)
+    ar_ms = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in ar_ev) / max(1, len(ar_ev)), dev)
+    return {"workload": f"cfg3 per-GPU shape: Conv-TasNet {S}spk paper hparams, batch {B} x {args.seconds:g}s@{args.sample_rate // 1000}kHz per GPU, "
+                        "fwd_train + PIT + backward + all-reduce + clip(5.0) + Adam(1e-3)", "global_batch": world * B,
+            "ms_per_step": ms / steps, "allreduce_ms": ar_ms, "allreduce_elems": nel, "audio_s_per_s": world * B * args.seconds * steps / (ms * 1e-3),
+            "steps": steps, "gpu_launches_per_step": launches, "optimizer": "native flat clip + Adam (ctn_clip_adam_step)",
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "last_loss": float(loss)}
+
+
+def ddp_check(torch, D, dev, rank, world):
+    """All-reduced shard gradients == gradients of the same GLOBAL batch on one GPU (small model; tests/test_dist_gpu.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import convtasnet_oracle as O
+    from ctn_b200.models.conv_tasnet import ConvTasNet
+    from ctn_b200.criterion.sdr import NegSISDR
+    from ctn_b200.criterion.pit import PIT1d
+    cfg = O.OracleConfig(n_basis=32, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=2, sep_num_layers=2, causal=False, n_sources=2)
+    sd = O.synth_state_dict(cfg, seed=7)
+    G = 3 * world
+    mixture, sources = O.synth_batch(G, 2, 2000, seed=9)
+    crit = PIT1d(NegSISDR(), 2)
+
+    def grads(lo, hi):
+        m = ConvTasNet(cfg.n_basis, cfg.kernel_size, enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
+                       sep_hidden_channels=cfg.sep_hidden_channels, sep_bottleneck_channels=cfg.sep_bottleneck_channels,
+                       sep_skip_channels=cfg.sep_skip_channels, sep_num_blocks=cfg.sep_num_blocks, sep_num_layers=cfg.sep_num_layers,
+                       causal=False, n_sources=2)
+        m.load_state_dict(sd)
+        m = m.to(dev).train()
+        loss, _ = crit(m(mixture[lo:hi].to(dev)), sources[lo:hi].to(dev))
+        loss.backward()
+        return m
+
+    lo, hi = D.shard_bounds(G, rank, world)
+    m = grads(lo, hi)
+    D.allreduce_gradients(m, local_batch=hi - lo, global_batch=G)
+    full = grads(0, G)
+    worst = 0.0
+    for (k, p), (_, q) in zip(m.named_parameters(), full.named_parameters()):
+        worst = max(worst, float((p.grad - q.grad).abs().max()) / (float(q.grad.abs().max()) + 1e-30))
+    worst = D.max_over_ranks(worst, dev)
+    return {"worst_rel": worst, "ok": bool(worst < 1e-4), "global_batch": G, "ranks": world,
+            "what": "NCCL all-reduced shard gradients vs the same global batch on one GPU, all parameter tensors"}
 
 
 def main():
@@ -167,12 +300,14 @@ def main():
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return
-        leg = cpu_reference_leg(args, args.steps, args.warmup)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        cpu_batch = args.cpu_batch or args.batch
+        leg = cpu_reference_leg(args, args.steps, args.warmup, cpu_batch)
+        cfgd = workload_config(args, max(world, args.gpus))
         line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "audio-sec/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"Conv-TasNet {args.n_sources}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN, {args.seconds:g}s@8kHz, "
-                                       f"fwd+SI-SDR-PIT; CPU step = {args.cpu_batch} mixtures (bounded sample of the batch-{args.batch} workload)"},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
+                "cpu_step": f"{cpu_batch} mixtures per CPU step" + ("" if cpu_batch == args.batch else f" (bounded sample of the batch-{args.batch} step)"),
                 "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": leg["value"], "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -182,7 +317,6 @@ def main():
     import torch
     from ctn_b200 import _native as N
     from ctn_b200 import dist as D
-    from ctn_b200.models.conv_tasnet import ConvTasNet
     from ctn_b200.criterion.sdr import NegSISDR
     from ctn_b200.criterion.pit import PIT1d
 
@@ -191,188 +325,180 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     S, B, T = args.n_sources, args.batch, int(args.seconds * args.sample_rate)
-
-    torch.manual_seed(111)  # reference default seed (train.sh:59); default init = the reference's default init
-    model = ConvTasNet(PAPER["n_basis"], PAPER["kernel_size"], enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
-                       sep_hidden_channels=PAPER["sep_hidden_channels"], sep_bottleneck_channels=PAPER["sep_bottleneck_channels"],
-                       sep_skip_channels=PAPER["sep_skip_channels"], sep_kernel_size=3, sep_num_blocks=3, sep_num_layers=8,
-                       causal=False, n_sources=S).to(dev).eval()
-    model.math = args.math
     math_name = args.math or ("f16x3" if N.ctn_has_tcgen05() else "fp32")
-    crit = PIT1d(NegSISDR(), S)
-    g = torch.Generator().manual_seed(111 + rank)
-    sources_h = (0.1 * torch.randn(B, S, T, generator=g)).pin_memory()
-    mixture_h = sources_h.sum(dim=1, keepdim=True).pin_memory()
-    mixture_d, sources_d = mixture_h.to(dev), sources_h.to(dev)
-    frames = N.frames_of(T, PAPER["kernel_size"], PAPER["kernel_size"] // 2)[0]
-
-    def step_resident():
-        out = model(mixture_d)
-        return crit(out, sources_d)
-
-    loss_pin = torch.empty(1).pin_memory()
-    perm_pin = torch.empty(B, S, dtype=torch.int64).pin_memory()
-
-    def step_e2e():
-        x = mixture_h.to(dev, non_blocking=True)
-        t = sources_h.to(dev, non_blocking=True)
-        out = model(x)
-        loss, perm = crit(out, t)
-        loss_pin.copy_(loss.reshape(1), non_blocking=True)
-        perm_pin.copy_(perm, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads loss / perm every step (driver.py:157 loss.item())
-        return float(loss_pin[0])
 
     if args.train:
-        # ---- training step (driver.py:146-157): fwd_train + PIT + native backward + ONE gradient all-reduce + clip + Adam ----
-        model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-        nelem = 0
-
-        def step_train():
-            nonlocal nelem
-            opt.zero_grad(set_to_none=True)
-            loss, _ = crit(model(mixture_d), sources_d)
-            loss.backward()
-            nelem = D.allreduce_gradients(model)
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-            opt.step()
-            return loss
-
-        for _ in range(max(args.warmup, 2)):
-            loss = step_train()
-        launches = model.last_launches + model.last_bwd_launches + 3
-        D.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            e0.record()
-            for _ in range(args.steps):
-                loss = step_train()
-            e1.record()
-            torch.cuda.synchronize()
-        D.barrier()
-        ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        blk = train_leg(args, torch, N, D, dev, rank, world, S, B, args.steps, args.warmup)
         if rank == 0:
-            print(json.dumps({
-                "mode": "train", "metric": "audio-sec/s Conv-TasNet %dspk %gs@8kHz TRAIN step (fwd+SI-SDR-PIT+bwd+allreduce+clip+Adam)" % (S, args.seconds),
-                "value": world * B * args.seconds * args.steps / (ms * 1e-3), "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "dtype": math_name, "data": "synthetic", "config": {"workload": f"cfg2/cfg3 shape, batch {B} per GPU", "global_batch": world * B,
-                "optimizer": "torch.optim.Adam(fused) + clip_grad_norm_ (torch; not part of the native path)"},
-                "gpu_launches": launches * args.steps, "allreduce_elems": nelem, "peak_mem_gb": peak_gb, "clocks": clk.summary(),
-                "last_loss": float(loss)}), flush=True)
+            print(json.dumps({"mode": "train", "metric": "audio-sec/s Conv-TasNet TRAIN step", "value": blk["audio_s_per_s"], "unit": "audio-sec/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": blk["ms_per_step"],
+                              "higher_is_better": True, "scaling": "weak", "dtype": math_name, "data": "synthetic", "config": {"workload": blk["workload"]},
+                              "train": blk}), flush=True)
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
         return
 
-    launches_per_step = 0
+    if args.config == "cfg4":
+        from ctn_b200.models.dprnn_tasnet import DPRNNTasNet
+        torch.manual_seed(111)
+        model = DPRNNTasNet(CFG4["n_basis"], CFG4["kernel_size"], enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
+                            sep_hidden_channels=CFG4["sep_hidden_channels"], sep_bottleneck_channels=CFG4["sep_bottleneck_channels"],
+                            sep_chunk_size=CFG4["sep_chunk_size"], sep_hop_size=CFG4["sep_hop_size"], sep_num_blocks=CFG4["sep_num_blocks"],
+                            causal=False, n_sources=S).to(dev).eval()
+        model.math = args.math
+    else:
+        model = build_convtasnet(args, dev, torch, S).eval()
+    crit = PIT1d(NegSISDR(), S)
+    g = torch.Generator().manual_seed(111 + rank)
+    sources_h = (0.1 * torch.randn(B, S, T, generator=g)).pin_memory()
+    mixture_h = sources_h.sum(dim=1, keepdim=True).pin_memory()
+    out_h = torch.empty(B, S, T).pin_memory()
+    mixture_d, sources_d = mixture_h.to(dev), sources_h.to(dev)
+
+    def step_resident():
+        out = model(mixture_d)
+        return crit(out, sources_d)
+
+    if args.config == "cfg4":
+        loss_pin = torch.empty(1).pin_memory()
+        perm_pin = torch.empty(B, S, dtype=torch.int64).pin_memory()
+
+        def step_e2e():
+            out = model(mixture_h.to(dev, non_blocking=True))
+            loss, perm = crit(out, sources_h.to(dev, non_blocking=True))
+            out_h.copy_(out, non_blocking=True)
+            loss_pin.copy_(loss.reshape(1), non_blocking=True)
+            perm_pin.copy_(perm, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(loss_pin[0])
+        e2e_api = "DPRNNTasNet.forward + PIT1d(NegSISDR).forward on pinned host tensors, estimates + loss + permutation copied back"
+    else:
+        def step_e2e():
+            loss, perm = model.separate_host(mixture_h, sources_h, out_host=out_h)
+            torch.cuda.current_stream().synchronize()   # the caller reads the estimates / loss every step (driver.py:157 loss.item())
+            return float(loss[0])
+        e2e_api = ("ConvTasNet.separate_host -> ctn_convtasnet_loss_host (C ABI, host buffers): H2D mixture + sources, forward + PIT, "
+                   "D2H estimates + loss + permutation")
+
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             loss, perm = step_resident()
-        launches_per_step = model.last_launches + N.ctn_last_launch_count()
+        launches_per_step = getattr(model, "last_launches", 0) + N.ctn_last_launch_count()
         torch.cuda.synchronize()
-
-        # ---- timed: device-resident ---------------------------------------------------------------------------
-        N.ctn_profile_enable(1)
-        N.profile_read()
-        D.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            e0.record()
-            for _ in range(args.steps):
-                loss, perm = step_resident()
-            e1.record()
-            torch.cuda.synchronize()
-        D.barrier()
-        ms_local = e0.elapsed_time(e1)
-        prof = N.profile_read()
+        # ---- timed: device-resident, stage timers OFF ---------------------------------------------------------
         N.ctn_profile_enable(0)
-        ms = D.max_over_ranks(ms_local, dev)
-
-        # ---- timed: end to end --------------------------------------------------------------------------------
+        with ClockSampler(local_rank) as clk:
+            ms, ms_local, _ = cuda_time(step_resident, args.steps, torch, D, dev)
+        # ---- timed: end to end ----------------------------------------------------------------------------------
         for _ in range(2):
             step_e2e()
-        D.barrier()
-        torch.cuda.synchronize()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        for _ in range(args.steps):
-            last_loss = step_e2e()
-        e3.record()
-        torch.cuda.synchronize()
-        D.barrier()
-        ms_e2e = D.max_over_ranks(e2.elapsed_time(e3), dev)
+        ms_e2e, _, last_loss = cuda_time(step_e2e, args.steps, torch, D, dev)
+        # ---- stage pass (separate, not part of `value`) ------------------------------------------------------------
+        prof, prof_steps, ms_prof = {}, min(args.steps, 5), 0.0
+        if args.config != "cfg4":
+            N.ctn_profile_enable(1)
+            N.profile_read()
+            _, ms_prof, _ = cuda_time(step_resident, prof_steps, torch, D, dev)
+            prof = N.profile_read()
+            N.ctn_profile_enable(0)
+
+    train_blk, ddp = None, None
+    if args.config == "cfg2" and not args.no_train_block:
+        torch.cuda.empty_cache()
+        N.release_workspaces()
+        try:
+            train_blk = train_leg(args, torch, N, D, dev, rank, world, 3, 8, steps=min(args.steps, 10), warmup=2)
+        except Exception as e:  # the forward line must survive a failure of the auxiliary block
+            train_blk = {"error": repr(e)[:300]}
+        if world > 1:
+            try:
+                ddp = ddp_check(torch, D, dev, rank, world)
+            except Exception as e:
+                ddp = {"error": repr(e)[:300], "ok": False}
 
     audio_per_step = world * B * args.seconds
     value = audio_per_step * args.steps / (ms * 1e-3)
     e2e_value = audio_per_step * args.steps / (ms_e2e * 1e-3)
-
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
         return
 
     pk = peaks()
-    model_bf = stage_model(args, B, frames, T)
-    # TF32 dense = 1/2 bf16 on tcgen05; fp16 operands (f16x3) run at the bf16 rate.  Sustained figure (kernel timed inside a long step)
+    frames = N.frames_of(T, model.kernel_size, model.stride)[0]
     tf32_peak = pk["bf16_sustained"] / (1.0 if math_name == "f16x3" else 2.0)
-    stages = {}
-    for name, (t_ms, n) in prof.items():
-        if n == 0:
-            continue
-        by, fl, bound = model_bf[name]
-        per_launch_ms = t_ms / n
-        groups = max(1, {"pw1": 24, "dw": 24, "pw2": 24, "fin": 24}.get(name, 1) * args.steps)
-        # stage records are per kernel group (one per block per step); bytes/flops above are per group
-        per_group_ms = t_ms / groups if name != "prep" else t_ms / args.steps
-        ent = {"ms_per_step": t_ms / args.steps, "launches_per_step": n / args.steps, "share": t_ms / (ms_local + 1e-9)}
-        if by > 0:
-            ent["GBps"] = by / (per_group_ms * 1e-3) / 1e9
-            ent["hbm_frac"] = ent["GBps"] / pk["hbm"]
-        if fl > 0 and bound == "tensor":
-            ent["TFLOPs"] = fl / (per_group_ms * 1e-3) / 1e12
-            ent["tf32_frac"] = ent["TFLOPs"] / tf32_peak
-        ent["bound"] = bound
-        ent["avg_launch_ms"] = per_launch_ms
-        stages[name] = ent
-    dom = max((k for k in stages if k != "prep"), key=lambda k: stages[k]["ms_per_step"])
-    d = stages[dom]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(math_name, {}).get(dom)
-    if d["bound"] == "tensor":
-        roof = {"kernel": dom, "bound": "tensor", "achieved": d["TFLOPs"], "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": d["TFLOPs"] / tf32_peak, "traffic": traffic,
-                "peak_note": (f"fp16 dense = bf16_tflops_sustained of {pk['source']}" if math_name == "f16x3" else
-                              f"TF32 dense = bf16_tflops_sustained/2 of {pk['source']}") +
-                             "; algorithmic 2*M*N*K flops (the 3-pass hi/lo split issues 3x that on the tensor pipe)"}
-        # the same kernel against the other roofline (algorithmic bytes / duration): with the fp16 pieces the two ideal times
-        # are within 15 % of each other, so both fractions are reported
-        if d.get("GBps") is not None:
-            roof["hbm_view"] = {"achieved": d.get("GBps"), "peak": pk["hbm"], "unit": "GB/s", "frac": d.get("hbm_frac")}
+    stages, roof = {}, None
+    if args.config != "cfg4":
+        model_bf = stage_model(args, B, frames, T)
+        for name, (t_ms, n) in prof.items():
+            if n == 0:
+                continue
+            by, fl, bound = model_bf[name]
+            groups = max(1, {"pw1": 24, "dw": 24, "pw2": 24}.get(name, 1) * prof_steps)
+            per_group_ms = t_ms / groups
+            ent = {"ms_per_step": t_ms / prof_steps, "launches_per_step": n / prof_steps, "share": t_ms / (ms_prof + 1e-9), "bound": bound,
+                   "avg_launch_ms": t_ms / n}
+            if by > 0:
+                ent["GBps"] = by / (per_group_ms * 1e-3) / 1e9
+                ent["hbm_frac"] = ent["GBps"] / pk["hbm"]
+            if fl > 0 and bound == "tensor":
+                ent["TFLOPs"] = fl / (per_group_ms * 1e-3) / 1e12
+                ent["tensor_frac"] = ent["TFLOPs"] / tf32_peak
+            stages[name] = ent
+        dom = max((k for k in stages if k != "prep"), key=lambda k: stages[k]["ms_per_step"])
+        d = stages[dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(math_name, {}).get(dom)
+        if d["bound"] == "tensor":
+            roof = {"kernel": dom, "bound": "tensor", "achieved": d["TFLOPs"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": d["TFLOPs"] / tf32_peak,
+                    "traffic": traffic,
+                    "peak_note": (f"fp16 dense = bf16_tflops_sustained of {pk['source']}" if math_name == "f16x3" else
+                                  f"TF32 dense = bf16_tflops_sustained/2 of {pk['source']}") +
+                                 "; algorithmic 2*M*N*K flops (the 3-pass hi/lo split issues 3x that on the tensor pipe)",
+                    "hbm_view": {"achieved": d.get("GBps"), "peak": pk["hbm"], "unit": "GB/s", "frac": d.get("hbm_frac")}}
+        else:
+            roof = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s", "frac": d["GBps"] / pk["hbm"],
+                    "traffic": traffic, "peak_note": f"hbm_gbs of {pk['source']}"}
+        # whole step against both roofs (234.3 MB and 39.28 GFLOP per 4-s 2-speaker sample, ideal fusion)
+        step_bytes = sum(model_bf[k][0] * {"pw1": 24, "pw2": 24}.get(k, 1) for k in ("enc", "head", "pw1", "pw2", "fin", "mask", "dec"))
+        roof["step"] = {"ms": ms / args.steps, "moved_bytes_model": step_bytes,
+                        "hbm_frac_on_moved_bytes": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]}
     else:
-        roof = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "peak_note": f"hbm_gbs of {pk['source']}"}
+        # cfg4: the segment / overlap-add / gLN glue kernels are HBM-bound; the LSTM recurrences (cuDNN) dominate the step
+        F_, K_, P_ = CFG4["sep_bottleneck_channels"], CFG4["sep_chunk_size"], CFG4["sep_hop_size"]
+        Sn = (frames + ((P_ - (frames - K_) % P_) % P_) - K_) // P_ + 1
+        state = B * Sn * K_ * F_ * 4.0
+        glue_bytes = 12 * 4 * state + 2 * state + 2 * B * F_ * frames * 4.0   # 12 x (stats read + Y,R read + out write) + segment + overlap-add
+        roof = {"kernel": "ctn_dprnn_norm_res_fwd (x12) + segment + overlap-add", "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": None, "traffic": None, "algorithmic_bytes_per_step": glue_bytes,
+                "ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
+                "note": "per-kernel durations in profiles/ (ncu launch list of this command); the cuDNN LSTM recurrences are library code"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC if args.config == "cfg2" else METRIC.replace("Conv-TasNet 2spk 4s@8kHz", workload_config(args, world)["workload"].split(",")[0]),
+        "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32x3": "f32 via 3xTF32 split on tcgen05, fp32 accumulate", "tf32": "tf32 (single pass), fp32 accumulate", "f16x3": "f32 via 3xFP16 split on tcgen05 (kind::f16), fp32 accumulate"}[math_name],
-        "data": "synthetic",
-        "config": {"workload": f"cfg2: Conv-TasNet {S}spk N512 L16 B128 H512 Sc128 P3 X8 R3 gLN sigmoid, batch {B} x {args.seconds:g}s@{args.sample_rate // 1000}kHz per GPU, "
-                               f"fwd + PIT(NegSISDR)", "global_batch": world * B, "math": math_name,
-                   "l2": "per-step activation traffic (>2 GB) exceeds the 126 MB L2 many times over; no explicit flush",
-                   "parallelism": f"batch shards x{world}, no data-path collective"},
-        "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": B * T * 4 * (1 + S), "d2h_bytes_per_step": 4 + B * S * 8,
-                "ms_per_step": ms_e2e / args.steps, "api": "ConvTasNet.forward + PIT1d(NegSISDR).forward on pinned host tensors"},
+        "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32x3": "f32 via 3xTF32 split on tcgen05, fp32 accumulate", "tf32": "tf32 (single pass), fp32 accumulate",
+                  "f16x3": "f32 via 3xFP16 split on tcgen05 (kind::f16), fp32 accumulate"}[math_name],
+        "data": "synthetic", "config": workload_config(args, world),
+        "detail": {"math": math_name, "parallelism": f"batch shards x{world}, no data-path collective in the forward",
+                   "value_timing": "CUDA events, stage timers off, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": B * T * 4 * (1 + S), "d2h_bytes_per_step": B * S * T * 4 + 4 + B * S * 8,
+                "ms_per_step": ms_e2e / args.steps, "api": e2e_api},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof, "stages": stages, "clocks": clk.summary(), "last_loss": last_loss,
     }
+    if train_blk is not None:
+        line["train"] = train_blk
+    if ddp is not None:
+        line["ddp_check"] = ddp
     if world == 1 and not args.no_cpu_baseline:
-        leg = cpu_reference_leg(args, steps=3, warmup=1)
+        # bounded sample: the full per-GPU batch, 1 warm-up + 2 timed steps (~ 20-30 s of CPU work at cfg2)
+        leg = cpu_reference_leg(args, steps=2, warmup=1, cpu_batch=args.cpu_batch or args.batch)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -601,11 +601,12 @@ extern "C" size_t ctn_host_io_bytes(const ctn_config_t* cfg, int B, int T) {
 
 extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params, const float* x_host,
                                         const float* tgt_host, int B, int T, float* out_host, float* loss_mean_host,
-                                        int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
-                                        ctn_stream_t stream) {
+                                        int64_t* perm_host, void* dev_io, size_t dev_io_bytes, void* workspace,
+                                        size_t workspace_bytes, float loss_eps, ctn_stream_t stream) {
   LaunchScope scope(dev_io);
-  if (!cfg || !x_host || !tgt_host || !loss_mean_host || !perm_host || !dev_io) return CTN_EINVAL;
+  if (!cfg || !x_host || !tgt_host || !loss_mean_host || !perm_host || !dev_io || B <= 0 || T <= 0) return CTN_EINVAL;
   if (((uintptr_t)dev_io) & 255) return CTN_EALIGN;
+  if (dev_io_bytes < ctn_host_io_bytes(cfg, B, T)) return CTN_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int S = cfg->n_sources;
   Carver cv(dev_io);
@@ -615,7 +616,7 @@ extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_param
   if ((e = cudaMemcpyAsync(io.x, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(io.tgt, tgt_host, sizeof(float) * (size_t)B * S * T, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
   CTN_TRY(ctn_convtasnet_fwd(cfg, params, io.x, B, T, io.out, nullptr, workspace, workspace_bytes, stream));
-  CTN_TRY(ctn_sisdr_pit_fwd(io.out, io.tgt, B, S, T, 1e-12f, io.loss_b, io.perm, io.loss_mean, nullptr, io.scratch, stream));
+  CTN_TRY(ctn_sisdr_pit_fwd(io.out, io.tgt, B, S, T, loss_eps, io.loss_b, io.perm, io.loss_mean, nullptr, io.scratch, stream));
   if (out_host && (e = cudaMemcpyAsync(out_host, io.out, sizeof(float) * (size_t)B * S * T, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(loss_mean_host, io.loss_mean, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(perm_host, io.perm, sizeof(int64_t) * (size_t)B * S, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;

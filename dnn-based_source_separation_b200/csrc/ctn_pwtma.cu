@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
             const int step = dcls == 4 ? d : 4;
             const int first = dcls == 4 ? tbase - d : tbase - 4;
-            if (dw_interior) {
+            // channels past K (K % 32 != 0: the last slab's second half) are rows of the NEXT sample: boundary path, zeroed
+            if (dw_interior && c < a.K) {
               if (dcls == 4) v[0] = dw_channel<4, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);
               else if (dcls == 2) v[0] = dw_channel<2, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);
               else v[0] = dw_channel<1, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);

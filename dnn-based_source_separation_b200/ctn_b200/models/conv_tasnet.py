@@ -195,6 +195,39 @@ class ConvTasNet(nn.Module):
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
+    def separate_host(self, mixture_host, sources_host, out_host=None, loss_eps=EPS):
+        """End-to-end call on HOST buffers (ctn_convtasnet_loss_host): H2D copies of the (pinned) mixture (B,1,T) and sources
+        (B,S,T), forward + PIT(NegSISDR) on the device, D2H of the estimates into ``out_host`` (optional), the mean loss and the
+        permutation -- all enqueued on the current stream.  Returns (loss (1,) pinned, perm (B,S) int64 pinned); the caller
+        synchronises the stream before reading them."""
+        dev = self.encoder.conv1d.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("ctn_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, _, T = mixture_host.shape
+        key = (B, T, dev)
+        st = getattr(self, "_host_state", None)
+        if st is None or st[0] != key:
+            loss = torch.empty(1, dtype=torch.float32).pin_memory()
+            perm = torch.empty(B, self.n_sources, dtype=torch.int64).pin_memory()
+            st = (key, loss, perm)
+            self._host_state = st
+        _, loss, perm = st
+        cfg = self.native_config()
+        params, keep = self.native_params(dev)
+        need = C.c_size_t(0)
+        N.check(N.ctn_workspace_bytes(C.byref(cfg), B, T, C.byref(need)), "ctn_workspace_bytes")
+        ws = N.workspace(dev, need.value)
+        io_bytes = N.ctn_host_io_bytes(C.byref(cfg), B, T)
+        io = N.workspace(dev, io_bytes + 256, tag="host_io")
+        wbase, ibase = (ws.data_ptr() + 255) & ~255, (io.data_ptr() + 255) & ~255
+        with torch.cuda.device(dev):
+            N.check(N.ctn_convtasnet_loss_host(C.byref(cfg), C.byref(params), mixture_host.data_ptr(), sources_host.data_ptr(), B, T,
+                                               N.ptr(out_host), loss.data_ptr(), perm.data_ptr(), ibase, io.numel() - (ibase - io.data_ptr()),
+                                               wbase, ws.numel() - (wbase - ws.data_ptr()), float(loss_eps), N.stream_ptr(dev)),
+                    "ctn_convtasnet_loss_host")
+        self.last_launches = N.ctn_last_launch_count()
+        return loss, perm
+
     # ---- native plumbing ---------------------------------------------------------------------------
     def native_config(self):
         sep = self.separator

@@ -10,6 +10,8 @@ place a library is the right tool.  Everything between them
 residual add and the intra <-> inter layout swap -- is ONE native call (ctn_dprnn_norm_res_fwd, csrc/ctn_dprnn.cu).
 Envelope: non-causal (gLN, bidirectional inter-chunk LSTM), rnn_type='lstm', norm=True; forward only.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F_
@@ -19,6 +21,31 @@ from ..utils.tasnet import choose_layer_norm
 from .transform import ctn_dprnn_norm_res_fwd
 
 EPS = 1e-12
+
+
+LSTM_TF32 = False  # cuDNN's RNN path defaults to TF32 tensor-core math (1e-3 relative): off = fp32 parity with the reference
+
+
+@contextlib.contextmanager
+def _rnn_precision():
+    rnn = getattr(torch.backends.cudnn, "rnn", None)
+    if LSTM_TF32 or rnn is None or not hasattr(rnn, "fp32_precision"):
+        if LSTM_TF32 or not torch.backends.cudnn.allow_tf32:
+            yield
+            return
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            yield
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+        return
+    old = rnn.fp32_precision
+    rnn.fp32_precision = "ieee"
+    try:
+        yield
+    finally:
+        rnn.fp32_precision = old
 
 
 def choose_rnn(name, **kwargs):
@@ -53,7 +80,8 @@ class _ChunkRNN(nn.Module):
         B, D1, D2, F = z.shape
         dev = N.require_cuda(z)
         self.rnn.flatten_parameters()
-        y, _ = self.rnn(z.view(B * D1, D2, F))                  # cuDNN bi-LSTM over D2
+        with _rnn_precision():
+            y, _ = self.rnn(z.view(B * D1, D2, F))              # cuDNN bi-LSTM over D2, IEEE fp32 math
         y = F_.linear(y, self.fc.weight, self.fc.bias)           # (B*D1, D2, F)
         out = torch.empty((B, D2, D1, F) if swap else (B, D1, D2, F), dtype=torch.float32, device=dev)
         scratch = torch.empty(2 * B, dtype=torch.float64, device=dev)

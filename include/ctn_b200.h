@@ -201,12 +201,12 @@ size_t ctn_sisdr_pit_scratch_bytes(int B, int S);
 /* End-to-end call with HOST buffers (the "e2e" leg): copies x_host (B,1,T) and tgt_host (B,S,T) (pinned or
  * pageable) to the device staging areas, runs ctn_convtasnet_fwd + ctn_sisdr_pit_fwd, copies back out_host
  * (nullable, (B,S,T)), loss_mean_host (1), perm_host (B,S).  All on `stream`; the caller synchronises.
- * dev_io: device staging, at least ctn_host_io_bytes(). */
+ * dev_io: device staging of dev_io_bytes >= ctn_host_io_bytes() (checked); loss_eps: eps of the SI-SDR (sdr.py:122, 1e-12). */
 size_t ctn_host_io_bytes(const ctn_config_t* cfg, int B, int T);
 int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_params_t* params, const float* x_host,
                              const float* tgt_host, int B, int T, float* out_host, float* loss_mean_host,
-                             int64_t* perm_host, void* dev_io, void* workspace, size_t workspace_bytes,
-                             ctn_stream_t stream);
+                             int64_t* perm_host, void* dev_io, size_t dev_io_bytes, void* workspace,
+                             size_t workspace_bytes, float loss_eps, ctn_stream_t stream);
 
 /* ---- training path: what `loss.backward()` does in the reference trainer (egs/wsj0-mix/common/src/driver.py:146-150) ----
  * ctn_convtasnet_fwd_train == ctn_convtasnet_fwd (same estimate) but keeps, inside `train_ws`, what the backward needs:
@@ -229,6 +229,18 @@ int ctn_convtasnet_bwd(const ctn_config_t* cfg, const ctn_params_t* params, cons
  * coef = -1/S for NegSISDR(reduction='mean'), -1 for 'sum'. */
 int ctn_sisdr_pit_bwd(const float* est, const float* tgt, const int64_t* perm, int B, int S, int T, float eps,
                       const double* fwd_scratch, const float* grad_loss_b, float coef, float* d_est, ctn_stream_t stream);
+
+/* Training-step remainder, egs/wsj0-mix/common/src/driver.py:152-155 (clip_grad_norm_(max_norm) + Adam.step()), on the flat
+ * gradient bucket of ctn_convtasnet_bwd: g *= min(1, max_norm/(||g||+1e-6)) (max_norm <= 0: no clipping), then torch.optim.Adam
+ * arithmetic (amsgrad off).  params: device array of n_tensors parameter pointers; flat_off / numel: element offset of each
+ * tensor's gradient inside flat_grad / its size; exp_avg, exp_avg_sq: Adam state laid out like flat_grad; lr (float) and step
+ * (int64, advanced by one) are DEVICE scalars (graph-replayable); chunk_table: int32 pairs (tensor, offset) from
+ * ctn_clip_adam_chunks (host helper: returns the chunk count; pass null outputs to size the table); norm_out nullable (1). */
+int ctn_clip_adam_chunks(const int* numel, int n_tensors, int* chunk_tensor, int* chunk_offset, int capacity);
+int ctn_clip_adam_step(const int32_t* chunk_table, int n_chunks, float* const* params, const long long* flat_off,
+                       const int32_t* numel, int n_tensors, const float* flat_grad, size_t flat_numel, float* exp_avg,
+                       float* exp_avg_sq, double* sumsq_scratch, const float* lr, long long* step, float beta1, float beta2, float eps,
+                       float weight_decay, float max_norm, float* norm_out, ctn_stream_t stream);
 
 /* Test hook: ONE pointwise (1x1) contraction D[b][m][t] = epi(sum_k W[m][k] A[b][k][t]) in the selected numeric mode,
  * so tests can compare the tcgen05 kernels with the FFMA kernels operand by operand.  A (B,K,pitch), D (B,M,pitch),

@@ -118,3 +118,11 @@ def test_autograd_over_the_oracle_matches_reference_backward(golden_dir):
         tol = 2e-4 * g["absmax"] + 1e-12
         assert float((mine.flatten()[::rec["stride"]] - g["sample"]).abs().max()) <= tol, k
         assert abs(float(mine.double().sum()) - g["sum"]) <= 2e-4 * (g["sumsq"] * mine.numel()) ** 0.5 + 1e-9, k
+    # and in fp64 (the noise-free answer the GPU tests are anchored on): oracle autograd in double == reference backward in double
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in O.synth_state_dict(cfg, seed=rec["wseed"]).items()}
+    out64, _ = O.conv_tasnet_fwd(mixture.double(), sd64, cfg)
+    loss64, _ = O.pit_neg_sisdr(out64, sources.double())
+    loss64.backward()
+    assert abs(float(loss64) - rec["loss64"]) < 1e-9
+    for k, g in rec["grads"].items():
+        assert float((sd64[k].grad.flatten()[::rec["stride"]] - g["sample64"]).abs().max()) <= 1e-9 * max(1.0, g["absmax64"]), k

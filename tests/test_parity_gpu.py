@@ -388,7 +388,10 @@ def test_host_buffer_entry_point():
     io = torch.empty(N.ctn_host_io_bytes(C.byref(ncfg), B, T) + 512, dtype=torch.uint8, device=dev)
     al = lambda t: (t.data_ptr() + 255) & ~255
     N.check(N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(),
-                                       loss_h.data_ptr(), perm_h.data_ptr(), al(io), al(ws), need.value, N.stream_ptr(dev)))
+                                       loss_h.data_ptr(), perm_h.data_ptr(), al(io), io.numel() - 256, al(ws), need.value, 1e-12,
+                                       N.stream_ptr(dev)))
+    assert N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(), loss_h.data_ptr(),
+                                      perm_h.data_ptr(), al(io), 1024, al(ws), need.value, 1e-12, N.stream_ptr(dev)) == N.CTN_EWORKSPACE
     torch.cuda.synchronize()
     assert N.ctn_last_launch_count() > 10
     with torch.no_grad():

@@ -127,16 +127,45 @@ PAPER = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottlenec
              sep_num_blocks=3, sep_num_layers=8)
 
 
+def _oracle_grads64(cfg, sd, mixture, sources):
+    sd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    out, _ = O.conv_tasnet_fwd(mixture.double(), sd, cfg)
+    loss, perm = O.pit_neg_sisdr(out, sources.double(), batch_mean=True)
+    loss.backward()
+    return {k: v.grad for k, v in sd.items()}
+
+
+def _check_grads_vs_fp64(named_grads, g64, noise32, rtol=GRAD_RTOL):
+    """|g - g64| <= rtol * max|g64| + 2 * (the reference's own fp32-vs-fp64 error of that tensor).  At the paper size the fp32
+    backward of the reference is itself 3e-4 (median) ... 1e-1 (single PReLU slopes) away from its fp64 backward, relative to each
+    tensor's largest entry (measured: tests/golden/make_golden.py grad_case), so a second fp32 implementation cannot agree with
+    it to 2e-4; what can be asked is that it is as close to the fp64 answer as the reference's fp32 arithmetic is."""
+    worst, closer = (0.0, None), 0
+    for k, g in named_grads:
+        r = g64[k]
+        scale = float(r.abs().max())
+        err = float((g.double() - r).abs().max())
+        tol = rtol * scale + 2.0 * noise32[k] + GRAD_ATOL
+        assert err <= tol, "{}: |g-g64| {:.3e} (rel {:.2e}) > tol {:.3e}; reference fp32 noise {:.3e}".format(k, err, err / (scale + 1e-30), tol, noise32[k])
+        closer += err <= noise32[k]
+        if err / (scale + 1e-30) > worst[0]:
+            worst = (err / (scale + 1e-30), k)
+    return worst, closer
+
+
 @pytest.mark.parametrize("mode", [m for m in MODES if m != "fp32"])
 @pytest.mark.parametrize("S", [2, 3])
 def test_paper_size_gradients_vs_oracle_autograd(mode, S):
     """BASELINE hyper-parameters (N=512 L=16 B=128 H=512 Sc=128 X=8 R=3; cfg2 = 2 speakers, cfg3 = 3 speakers), batch 2,
     T = 8000: the tcgen05 weight-gradient kernel runs its 4 M-tiles / K = 512 shapes and the split-K red.add path.  All 343
-    gradient tensors against torch autograd over the oracle (egs/wsj0-mix/common/src/driver.py:146-150)."""
+    gradient tensors against torch autograd over the oracle IN FP64 (egs/wsj0-mix/common/src/driver.py:146-150), tolerance
+    anchored on the fp32 oracle's own distance to fp64 (see _check_grads_vs_fp64)."""
     cfg = O.OracleConfig(causal=False, n_sources=S, **PAPER)
     sd = O.synth_state_dict(cfg, seed=113)
     mixture, sources = O.synth_batch(2, S, 8000, seed=113)
-    ref_out, ref_loss, ref_perm, ref_grads = _oracle_grads(cfg, sd, mixture, sources)
+    ref_out, ref_loss, ref_perm, g32 = _oracle_grads(cfg, sd, mixture, sources)
+    g64 = _oracle_grads64(cfg, sd, mixture, sources)
+    noise32 = {k: float((g32[k].double() - g64[k]).abs().max()) for k in g64}
     model = build_model(cfg, sd, math=mode).train()
     out = model(mixture.cuda())
     torch.testing.assert_close(out.detach().cpu(), ref_out, rtol=1e-4, atol=2e-5)
@@ -144,14 +173,15 @@ def test_paper_size_gradients_vs_oracle_autograd(mode, S):
     assert torch.equal(perm.cpu(), ref_perm)
     torch.testing.assert_close(loss.detach().cpu(), ref_loss, rtol=0, atol=1e-4)
     loss.backward()
-    assert len(ref_grads) == 343
-    worst = _check_grads(model, ref_grads)
-    print("paper-size worst relative gradient error", worst)
+    assert len(g64) == 343
+    worst, closer = _check_grads_vs_fp64([(k, p.grad.detach().cpu()) for k, p in model.named_parameters()], g64, noise32)
+    print("paper-size worst relative gradient error vs fp64", worst, "| tensors at least as close to fp64 as the CPU fp32 oracle:", closer, "/ 343")
 
 
 def test_paper_size_gradients_vs_reference_golden(golden_dir):
-    """Same shape against the fixture minted from the UNMODIFIED reference's loss.backward() (tests/golden/make_golden.py
-    grad_case): loss, permutation, and every 97th element + fp64 sum of each of the 343 gradient tensors."""
+    """Same shape against the fixture minted from the UNMODIFIED reference's loss.backward() in fp64 (tests/golden/make_golden.py
+    grad_case): loss, permutation, and every 97th element of each of the 343 gradient tensors; tolerance anchored on the
+    reference's own fp32-vs-fp64 distance stored in the fixture."""
     import os
     rec = torch.load(os.path.join(golden_dir, "paper_3spk_grad.pt"), weights_only=False)
     cfg = O.OracleConfig(**rec["cfg"])
@@ -162,13 +192,51 @@ def test_paper_size_gradients_vs_reference_golden(golden_dir):
     loss.backward()
     assert torch.equal(perm.cpu(), rec["perm"])
     torch.testing.assert_close(loss.detach().cpu(), rec["loss"], rtol=0, atol=1e-4)
-    n = 0
-    for k, p in model.named_parameters():
-        g = rec["grads"][k]
-        mine = p.grad.detach().cpu()
-        assert tuple(mine.shape) == g["shape"], k
-        tol = GRAD_RTOL * g["absmax"] + GRAD_ATOL
-        assert float((mine.flatten()[::rec["stride"]] - g["sample"]).abs().max()) <= tol, k
-        assert abs(float(mine.double().sum()) - g["sum"]) <= GRAD_RTOL * (g["sumsq"] * mine.numel()) ** 0.5 + 1e-9, k
-        n += 1
-    assert n == 343
+    st = rec["stride"]
+    named = [(k, p.grad.detach().cpu().flatten()[::st]) for k, p in model.named_parameters()]
+    g64 = {k: g["sample64"] for k, g in rec["grads"].items()}
+    noise32 = {k: g["fp32_vs_fp64_maxabs"] for k, g in rec["grads"].items()}
+    assert len(named) == 343
+    # the sampled entries are scaled by the tensor's true max (absmax64), not the sample's
+    for k, g in named:
+        r = g64[k]
+        err = float((g.double() - r).abs().max())
+        tol = GRAD_RTOL * rec["grads"][k]["absmax64"] + 2.0 * noise32[k] + GRAD_ATOL
+        assert err <= tol, "{}: {:.3e} > {:.3e} (reference fp32 noise {:.3e})".format(k, err, tol, noise32[k])
+
+
+@pytest.mark.parametrize("max_norm,wd", [(5.0, 0.0), (0.05, 0.0), (None, 1e-2)])
+def test_native_clip_adam_matches_torch(max_norm, wd):
+    """ctn_clip_adam_step (3 launches over the flat gradient bucket) against torch.nn.utils.clip_grad_norm_ + torch.optim.Adam
+    (egs/wsj0-mix/common/src/driver.py:152-155) fed with the SAME gradients, 4 steps: parameters within 1e-6, reported total norm
+    equal.  max_norm = 0.05 makes the clip active every step."""
+    import copy
+    from ctn_b200.optim import FlatClipAdam
+    cfg = O.OracleConfig(n_basis=32, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=2)
+    ours = build_model(cfg, O.synth_state_dict(cfg, seed=3)).train()
+    ref = copy.deepcopy(ours)
+    mixture, sources = O.synth_batch(4, 2, 4000, seed=8)
+    mixture, sources = mixture.cuda(), sources.cuda()
+    crit = PIT1d(NegSISDR(), 2)
+    opt = FlatClipAdam(ours, lr=1e-3, weight_decay=wd, max_norm=max_norm)
+    topt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=wd)
+    for it in range(4):
+        opt.zero_grad()
+        loss, _ = crit(ours(mixture), sources)
+        loss.backward()
+        # hand the reference optimizer the very same gradients (the native backward sums with atomics: two runs differ by ~1e-7)
+        for p, q in zip(ours.parameters(), ref.parameters()):
+            q.grad = p.grad.detach().clone()
+        tn = opt.step()
+        if max_norm is not None:
+            tn_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+            torch.testing.assert_close(tn.reshape(()), tn_ref.reshape(()), rtol=1e-5, atol=1e-7)
+        topt.step()
+        if it == 1:
+            opt.set_lr(5e-4)                      # LR halving (adhoc_driver.py:25-39) without rebuilding anything
+            for gr in topt.param_groups:
+                gr["lr"] = 5e-4
+    for (k, p), q in zip(ours.named_parameters(), ref.parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-5, atol=1e-6, msg=lambda m, k=k: k + ": " + m)
+    assert int(opt.step_count[0]) == 4
