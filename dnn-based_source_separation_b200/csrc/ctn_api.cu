@@ -171,8 +171,10 @@ static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t
 }
 
 // TCN over ws->x (padded layout) -> ws->skip.  stats region must be zeroed by the caller.
+// dil (nullable): explicit dilation per block (ctn_tcn_blocks_fwd); default 2^layer (dilated=True, tdcn.py:52-54).
+// x_final (nullable): receives a pointer to the residual stream AFTER the last block (x_n), updated in the workspace.
 static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnWs* ws, int B, int frames, int pitch,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* dil = nullptr, float** x_final = nullptr) {
   const int R = c->num_blocks, X = c->num_layers, Bc = c->bottleneck, H = c->hidden, Sc = c->skip;
   if (c->causal)  // cLN: cumulative statistics -> un-fused pipeline in the reference's operation order
     return ctn_causal_tcn(c, blocks, ws->x, ws->skip, ws->h, ws->u, B, frames, pitch, ws->causal_ws, st);
@@ -213,7 +215,7 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       const ctn_block_params_t& p = blocks[i];
       const bool has_out = p.out_w != nullptr;
       if (!has_out && !(r == R - 1 && l == X - 1)) return CTN_EINVAL;
-      const int dilation = 1 << l;  // dilated=True (tdcn.py:52-54)
+      const int dilation = dil ? dil[i] : (1 << l);  // dilated=True (tdcn.py:52-54)
       double* st1 = ws->stats + (size_t)(2 * i) * B * 2;
       double* st2 = ws->stats + (size_t)(2 * i + 1) * B * 2;
       // K_A: h = PReLU(W1 x + b1), stats1
@@ -283,6 +285,15 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
     }
     CTN_TRY(ctn_skip_reduce(sj, (double)H * (double)frames, c->eps_tcn, ws->skip, B, Sc, frames, pitch, st));
   }
+  if (x_final) {
+    const int n = R * X;
+    float* xbuf[2] = {ws->x, ws->xalt};
+    float* xl = (c->math != CTN_MATH_FP32) ? xbuf[(n - 1) & 1] : ws->x;  // x_{n-1} (tcgen05 modes defer every update to the next block)
+    if (c->math != CTN_MATH_FP32 && blocks[n - 1].out_w)
+      CTN_TRY(ctn_finish_fwd(ws->rblk[n - 1], ws->folds[n - 1], ws->stats + (size_t)(2 * (n - 1) + 1) * B * 2, (double)H * (double)frames,
+                             c->eps_tcn, xl, ws->skip, B, Bc, Sc, 1, 2 /* x rows only */, frames, pitch, st));
+    *x_final = xl;
+  }
   return CTN_OK;
 }
 
@@ -320,6 +331,50 @@ extern "C" int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* bl
   }
   CTN_TRY(run_tcn(cfg, blocks, &ws, B, frames, pitch, st));
   CTN_TRY(ctn_copy_from_pitch(ws.skip, skip_out, B * cfg->skip, frames, pitch, st));
+  return CTN_OK;
+}
+
+// A run of residual blocks with explicit dilations, returning BOTH heads: ResidualBlock1d.forward (tdcn.py:107-147, n = 1) and
+// TimeDilatedConvBlock1d.forward (tdcn.py:65-75): x (B,Bc,frames) -> x_out (nullable; the residual stream after the last block,
+// which must have the output head) and skip_out (B,Sc,frames) = sum of the blocks' skip heads.  cfg as for ctn_tcn_fwd
+// (num_blocks * num_layers is ignored; n_blocks counts).
+extern "C" int ctn_tcn_blocks_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, int n_blocks, const int* dilations,
+                                  const float* x, float* x_out, float* skip_out, int B, int frames, void* workspace,
+                                  size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope(x);
+  if (!cfg || !blocks || !dilations || n_blocks <= 0 || n_blocks > CTN_MAX_BLOCKS || !x || !skip_out || !workspace || B <= 0 || frames <= 0)
+    return CTN_EINVAL;
+  ctn_config_t c = *cfg;
+  c.num_blocks = 1;
+  c.num_layers = n_blocks;
+  if (c.bottleneck <= 0 || c.hidden <= 0 || c.skip <= 0 || c.sep_kernel <= 0) return CTN_EINVAL;
+  if (c.causal) return CTN_EUNSUPPORTED;  // the causal pipeline takes its dilations from the layer index
+  for (int i = 0; i < n_blocks; ++i) {
+    if (dilations[i] < 1) return CTN_EINVAL;
+    if (!blocks[i].out_w && i != n_blocks - 1) return CTN_EINVAL;
+  }
+  if (x_out && !blocks[n_blocks - 1].out_w) return CTN_EINVAL;
+  if (((uintptr_t)workspace) & 255) return CTN_EALIGN;
+  const int pitch = ctn_pitch(frames);
+  Carver cv0(nullptr);
+  TcnWs ws;
+  carve_tcn(cv0, &c, B, pitch, &ws);
+  if (workspace_bytes < cv0.off + 256) return CTN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  carve_tcn(cv, &c, B, pitch, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.stats, 0, ws.stats_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  CTN_TRY(ctn_copy_to_pitch(x, ws.x, B * c.bottleneck, frames, pitch, st));
+  if (c.math == CTN_MATH_F16X3) {
+    e = cudaMemsetAsync(ws.x0_bound, 0, sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    CTN_TRY(ctn_absmax_pitch(ws.x, B * c.bottleneck, frames, pitch, ws.x0_bound, st));
+  }
+  float* xf = nullptr;
+  CTN_TRY(run_tcn(&c, blocks, &ws, B, frames, pitch, st, dilations, x_out ? &xf : nullptr));
+  if (x_out) CTN_TRY(ctn_copy_from_pitch(xf, x_out, B * c.bottleneck, frames, pitch, st));
+  CTN_TRY(ctn_copy_from_pitch(ws.skip, skip_out, B * c.skip, frames, pitch, st));
   return CTN_OK;
 }
 
@@ -373,8 +428,11 @@ extern "C" int ctn_workspace_bytes(const ctn_config_t* cfg, int batch, int T, si
 }
 
 // separator on ws->w (+ stats0 already accumulated) -> ws->what (= w*mask) and optionally the raw mask
+// dec (nullable): when the fused mask + decoder epilogue applies (fp16-piece mode, kernel 16 / stride 8, no mask / latent output
+// wanted) the estimates are written straight to dec->out and dec->fused is set; w_hat is then never materialised
+struct DecFuse { float* out; int crop_left, T_out; bool fused; };
 static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* ws, int B, int frames, int pitch,
-                         float* mask_out, cudaStream_t st) {
+                         float* mask_out, cudaStream_t st, DecFuse* dec = nullptr) {
   const int N = c->n_basis, Bc = c->bottleneck, Sc = c->skip, S = c->n_sources;
   if (c->causal) {
     // cLN0 -> bottleneck 1x1; ws->what is free until the mask kernel writes it: use it as the (B, N, pitch) scratch
@@ -412,6 +470,18 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
   if (c->math == CTN_MATH_F16X3 && !c->causal) a.act_scale = ws->tcn.scales + 2 * c->num_blocks * c->num_layers;
   // causal models: no operand scales (un-fused pipeline) -> the mask contraction stays on the tf32 pieces
   const int mask_math = (c->causal && c->math == CTN_MATH_F16X3) ? CTN_MATH_TF32X3 : c->math;
+  if (dec && !mask_out && mask_math == CTN_MATH_F16X3 && c->kernel_size == 16 && c->stride == 8) {
+    PwArgs f = a;
+    f.D = dec->out; f.dec_w = p->dec_w; f.dec_crop_left = dec->crop_left; f.dec_T_out = dec->T_out;
+    if (ctn_pw_tma_supported(f, PRO_PRELU, EPI_MASKDEC)) {
+      StageTimer tm(CTN_ST_MASK, st);
+      cudaError_t e = cudaMemsetAsync(dec->out, 0, sizeof(float) * (size_t)B * S * dec->T_out, st);  // tile seams are red.add'ed
+      if (e != cudaSuccess) return (int)e;
+      CTN_TRY(ctn_pw_tma(f, PRO_PRELU, EPI_MASKDEC, st));
+      dec->fused = true;
+      return CTN_OK;
+    }
+  }
   { StageTimer tm(CTN_ST_MASK, st); CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, mask_math, st)); }
   return CTN_OK;
 }
@@ -441,11 +511,14 @@ extern "C" int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* p
   { StageTimer tm(CTN_ST_ENC, st);
     CTN_TRY(ctn_encoder_fwd(x, params->enc_w, ws.w, B, T, pl, pr, cfg->n_basis, cfg->kernel_size, cfg->stride, cfg->enc_relu,
                             pitch, ws.stats0, st)); }
-  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, nullptr, st));
-  // decoder + crop (conv_tasnet.py:163-169)
-  { StageTimer tm(CTN_ST_DEC, st);
+  DecFuse dec{out, pl, T, false};
+  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, nullptr, st, latent ? nullptr : &dec));
+  if (!dec.fused) {
+    // decoder + crop (conv_tasnet.py:163-169)
+    StageTimer tm(CTN_ST_DEC, st);
     CTN_TRY(ctn_decoder_fwd(ws.what, params->dec_w, out, B * cfg->n_sources, cfg->n_basis, frames, pitch, cfg->kernel_size,
-                            cfg->stride, pl, T, st)); }
+                            cfg->stride, pl, T, st));
+  }
   if (latent) CTN_TRY(ctn_copy_from_pitch(ws.what, latent, B * cfg->n_sources * cfg->n_basis, frames, pitch, st));
   return CTN_OK;
 }

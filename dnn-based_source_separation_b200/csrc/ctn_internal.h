@@ -16,7 +16,7 @@ struct FoldedConv {
 #define CTN_MAX_BLOCKS 64
 // epilogue / prologue selectors of the pointwise (1x1) contraction kernels
 enum { PRO_NONE = 0, PRO_PRELU = 1, PRO_DW = 2, PRO_RES = 3 };
-enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3 };
+enum { EPI_RAW = 0, EPI_HEAD = 1, EPI_H = 2, EPI_MASK = 3, EPI_MASKDEC = 4 };
 
 struct PwArgs {
   const float* A;      // (B, K, pitch) activations
@@ -47,6 +47,10 @@ struct PwArgs {
   const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
   int Nb;                  // EPI_MASK: n_basis
   float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)
+  // EPI_MASKDEC (TMA-fed kernel): mask 1x1 + sigmoid + w*mask + transposed-conv decoder + crop in one epilogue; w_hat is never
+  // materialised.  D = estimates (B, M/Nb, dec_T_out) contiguous, ZERO-initialised by the caller (tile seams are red.add'ed)
+  const float* dec_w;      // (Nb, 1, 16) decoder basis, kernel 16 / stride 8
+  int dec_crop_left, dec_T_out;
   // PRO_RES (tcgen05 path): the operand is the UPDATED residual stream  x_new = A + rstd*res_r[:K] + (v1 - mean*rstd*v2)
   // (the deferred gLN2 of the previous block); CTAs with n-tile 0 also store x_new to res_x_out (ping-pong buffer).
   const float* res_r;       // (B, res_Mt, pitch) raw [out;skip] contraction of the previous block; rows [0,K) are used

@@ -76,6 +76,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+// arrive on a "slot free" barrier AFTER the values read from the slot exist in registers: `dep` (a value computed from them) is an
+// input operand, so the arrive cannot issue while the shared-memory loads are still in flight (a release does not wait for
+// outstanding LDS by itself; the TMA engine would otherwise overwrite the slot under them)
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, float dep) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "f"(dep) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -126,14 +132,30 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
   ptx::tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
 
-  const int items_per_cta = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // EPI_MASKDEC: a CTA walks ALL n-tiles of a (sample, time tile) back to back (the decoder sums over the channels of a source
+  // in registers); the other kernels interleave n-tiles across CTAs (n-tile fastest, co-running CTAs share activations in L2)
+  const int tiles_total = g.num_items / g.n_tiles;
+  const int items_per_cta = EPI == EPI_MASKDEC ? ((tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * g.n_tiles
+                                               : (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto decode = [&](int it2, int& nt2, int& tt2, int& b2) {
-    const int J = (int)blockIdx.x + it2 * (int)gridDim.x;
-    nt2 = J % g.n_tiles;
-    const int L = J / g.n_tiles;
+    int L;
+    if (EPI == EPI_MASKDEC) {
+      nt2 = it2 % g.n_tiles;
+      L = (int)blockIdx.x + (it2 / g.n_tiles) * (int)gridDim.x;
+    } else {
+      const int J = (int)blockIdx.x + it2 * (int)gridDim.x;
+      nt2 = J % g.n_tiles;
+      L = J / g.n_tiles;
+    }
     tt2 = L % g.t_tiles;
     b2 = L / g.t_tiles;
   };
+  if (EPI == EPI_MASKDEC) {
+    // decoder basis (Nb x 16 taps) resident in shared memory behind the raw ring, then the [2][128][16] combine buffer
+    float* sD = reinterpret_cast<float*>(raw0_p + (size_t)g.raw_stages * g.raw_stage_bytes);
+    for (int i = threadIdx.x; i < a.Nb * 16; i += blockDim.x) sD[i] = __ldg(a.dec_w + i);
+    __syncthreads();
+  }
 
   if (warp == 5) {
     // ===================================== TMA LOADER ========================================================
@@ -234,8 +256,6 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               prm = reinterpret_cast<const float*>(rb) + RC * wd + pw * 8;
             }
             const float4 p0 = *reinterpret_cast<const float4*>(prm), p1 = *reinterpret_cast<const float4*>(prm + 4);
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->rempty[rs]));  // release: the reads above are done
             // fold the operand scale into the (positively homogeneous) PReLU: scale taps and bias
             const float gsc = p0.x * mr1.y, gsh = p0.y - mr1.x * mr1.y * p0.x;
             const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
@@ -252,6 +272,11 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               else if (dcls == 2) v[0] = dw_channel<2, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, cv, dls, dlss);
               else v[0] = dw_channel<1, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, cv, dls, dlss);
             }
+            {  // every lane's loads are complete once its outputs exist; then the warp hands the raw slot back
+              const float dep = (v[0].x + v[0].y) + (v[0].z + v[0].w) + (q0.x + q1.x + q2.x + p1.y);
+              __syncwarp();
+              if (lane == 0) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rs]), dep);
+            }
           } else {
             float4 rr[CPW];
 #pragma unroll
@@ -260,8 +285,6 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               v[j] = *reinterpret_cast<const float4*>(r0);
               if (PRO == PRO_RES) rr[j] = *reinterpret_cast<const float4*>(r0 + RC * TM);
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->rempty[rs]));
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
               const int k = ks * KS + sub * RC + pw * CPW + j;
@@ -285,6 +308,16 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               }
               x.x *= act_s; x.y *= act_s; x.z *= act_s; x.w *= act_s;
               v[j] = x;
+            }
+            {
+              float dep = 0.f;
+#pragma unroll
+              for (int j = 0; j < CPW; ++j) {
+                dep += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+                if (PRO == PRO_RES) dep += rr[j].x + rr[j].w;
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rs]), dep);
             }
           }
           if (sub == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
@@ -371,6 +404,9 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
     const int egroup = (EGROUPS == 2 && warp >= FIRST_PROD + PROD_WARPS) ? 1 : 0;
     const int te = (warp & 3) * 32 + lane;
     const int tid_e = egroup * 128 + te;
+    float2 dacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dacc[i] = make_float2(0.f, 0.f);
     for (int it = 0; it < items_per_cta; ++it) {
       int nt, tt, b;
       decode(it, nt, tt, b);
@@ -379,7 +415,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
       const bool tvalid = t < a.frames;
       const int n0 = nt * g.n_tile;
       const int nvalid = min(g.n_tile, a.M - n0);
-      if (EPI == EPI_H) {
+      if (EPI == EPI_H || EPI == EPI_MASKDEC) {
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");  // previous item's readers are done with sp
         for (int i = tid_e; i < g.n_tile; i += 128 * EGROUPS) sp[i] = i < nvalid ? __ldg(a.bias + n0 + i) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");
@@ -395,7 +431,39 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
       const int ncols = egroup == 0 ? csplit : ncols_all;
       const bool do_store = !(g.dbg & 1u);
       const bool tile_full = tt * TM + TM <= a.frames;
+      // EPI_MASKDEC: w_hat[n][t] = w[n][t] * sigmoid(logit) is contracted on the spot with the decoder basis:
+      //   full[8 t + k] += w_hat[n][t] * Dec[n][k], k < 16 (ConvTranspose1d(N,1,16,stride 8), filterbank.py:245-247), 16 partial
+      // sums per thread (= per frame) in registers across the n-tiles of one source
+      const float* sD = reinterpret_cast<const float*>(raw0_p + (size_t)g.raw_stages * g.raw_stage_bytes);
+      float* accbuf = const_cast<float*>(sD) + a.Nb * 16;
+      const float* Wp = (EPI == EPI_MASKDEC) ? a.wenc + (size_t)b * a.Nb * a.pitch + t : nullptr;
+      const int nb0 = (EPI == EPI_MASKDEC) ? n0 % a.Nb : 0;
+      if (EPI == EPI_MASKDEC && nb0 == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dacc[i] = make_float2(0.f, 0.f);
+      }
+      auto process_dec = [&](const uint32_t (&buf)[16], int c0) {
+        float wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = (c0 + j < nvalid) ? __ldg(Wp + (size_t)(nb0 + c0 + j) * a.pitch) : 0.f;
+        const float osc = ssc_all[n0 + c0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float logit = fmaf(__uint_as_float(buf[j]), osc, sp[c0 + j]);
+          float o = __fdividef(wv[j], 1.f + __expf(-logit));
+          if (!tvalid || c0 + j >= nvalid) o = 0.f;
+          const float4* dr = reinterpret_cast<const float4*>(sD + (size_t)(nb0 + c0 + j) * 16);
+          const float2 o2 = make_float2(o, o);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 d4 = dr[q4];
+            dacc[2 * q4] = __ffma2_rn(o2, make_float2(d4.x, d4.y), dacc[2 * q4]);
+            dacc[2 * q4 + 1] = __ffma2_rn(o2, make_float2(d4.z, d4.w), dacc[2 * q4 + 1]);
+          }
+        }
+      };
       auto process = [&](const uint32_t (&buf)[16], int c0) {
+        if (EPI == EPI_MASKDEC) { process_dec(buf, c0); return; }
         float* q = Dp + (size_t)c0 * a.pitch;
         const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
         const float osc = ssc_all[n0 + c0];  // one power-of-two scale per 16-row weight group (and the operand scale)
@@ -450,6 +518,48 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(ptx::smem_u32(&hdr->tempty[acc]));
+      if (EPI == EPI_MASKDEC && (n0 + g.n_tile) % a.Nb == 0) {
+        // last n-tile of source s: combine the two column halves (epilogue groups) and the two overlapping frames, crop
+        // (conv_tasnet.py:169) and store.  Thread (group gq, frame te) owns samples 8 te + 4 gq .. +3 of the tile.
+        float4* ab = reinterpret_cast<float4*>(accbuf + ((size_t)egroup * 128 + te) * 16);
+        ab[0] = make_float4(dacc[0].x, dacc[0].y, dacc[1].x, dacc[1].y);
+        ab[1] = make_float4(dacc[2].x, dacc[2].y, dacc[3].x, dacc[3].y);
+        ab[2] = make_float4(dacc[4].x, dacc[4].y, dacc[5].x, dacc[5].y);
+        ab[3] = make_float4(dacc[6].x, dacc[6].y, dacc[7].x, dacc[7].y);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");
+        const int src = n0 / a.Nb, S = a.M / a.Nb;
+        float* yo = a.D + ((size_t)b * S + src) * (size_t)a.dec_T_out;
+        const float4 c0a = *reinterpret_cast<const float4*>(accbuf + (size_t)te * 16 + egroup * 4);
+        const float4 c0b = *reinterpret_cast<const float4*>(accbuf + (size_t)(128 + te) * 16 + egroup * 4);
+        float4 v = make_float4(c0a.x + c0b.x, c0a.y + c0b.y, c0a.z + c0b.z, c0a.w + c0b.w);
+        if (te > 0) {
+          const float4 p0 = *reinterpret_cast<const float4*>(accbuf + (size_t)(te - 1) * 16 + 8 + egroup * 4);
+          const float4 p1 = *reinterpret_cast<const float4*>(accbuf + (size_t)(128 + te - 1) * 16 + 8 + egroup * 4);
+          v.x += p0.x + p1.x; v.y += p0.y + p1.y; v.z += p0.z + p1.z; v.w += p0.w + p1.w;
+        }
+        const long long tau = (long long)8 * t + egroup * 4 - a.dec_crop_left;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        if (te > 0 && tau >= 0 && tau + 3 < a.dec_T_out && ((tau & 3) == 0)) {
+          *reinterpret_cast<float4*>(yo + tau) = v;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (tau + e < 0 || tau + e >= a.dec_T_out) continue;
+            if (te > 0) yo[tau + e] = vv[e];
+            else atomicAdd(yo + tau + e, vv[e]);   // first frame of the tile: the previous tile's last frame adds its taps 8..15
+          }
+        }
+        if (te == 127) {  // taps 8..15 of the tile's last frame land in the next tile's first 8 samples
+          const float4 q0 = *reinterpret_cast<const float4*>(accbuf + (size_t)127 * 16 + 8 + egroup * 4);
+          const float4 q1 = *reinterpret_cast<const float4*>(accbuf + (size_t)(128 + 127) * 16 + 8 + egroup * 4);
+          const float tv[4] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, q0.w + q1.w};
+          const long long tau2 = (long long)8 * (t + 1) + egroup * 4 - a.dec_crop_left;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (tau2 + e >= 0 && tau2 + e < a.dec_T_out) atomicAdd(yo + tau2 + e, tv[e]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EGROUPS) : "memory");  // accbuf is reused by the next source
+      }
       if (EPI == EPI_H) {
         const double sd = warp_sum_d((double)ls), ssd = warp_sum_d((double)lss);
         if (lane == 0) { atomicAdd(&a.stats_out[2 * b], sd); atomicAdd(&a.stats_out[2 * b + 1], ssd); }
@@ -526,7 +636,14 @@ int ctn_pw_tma_supported(const PwArgs& a, int pro, int epi) {
     const int n_tile = a.M >= 256 ? 256 : ((a.M + 15) / 16) * 16;
     if (((a.M + n_tile - 1) / n_tile) * n_tile > 2048) return 0;
   }
-  if (!((pro == PRO_DW && epi == EPI_RAW) || ((pro == PRO_RES || pro == PRO_NONE) && epi == EPI_H))) return 0;
+  if (!((pro == PRO_DW && epi == EPI_RAW) || ((pro == PRO_RES || pro == PRO_NONE) && epi == EPI_H) || (pro == PRO_PRELU && epi == EPI_MASKDEC)))
+    return 0;
+  if (epi == EPI_MASKDEC) {
+    static const char* envd = getenv("CTN_MASKDEC");
+    if (envd && atoi(envd) == 0) return 0;
+    const int n_tile = a.M >= 256 ? 256 : ((a.M + 15) / 16) * 16;
+    if (!a.dec_w || a.Nb <= 0 || a.M % a.Nb != 0 || a.Nb % n_tile != 0 || a.Nb > 1024) return 0;  // whole n-tiles per source; basis fits smem
+  }
   if (a.pitch % TM != 0 || a.store_pre) return 0;
   if (pro == PRO_DW && (a.dw_pad_left != a.dw_dilation || a.dw_dilation < 1 || !a.dw_params)) return 0;
   return 1;
@@ -568,7 +685,8 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
     if (pro == PRO_RES) CTN_TRY(make_map(&g.tmR, a.res_r, a.B * a.res_Mt, a.pitch, TM, RC));
   }
   g.raw_stage_bytes = (g.raw_tx_bytes + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 1024 - g.hdr_bytes;
+  const size_t dec_bytes = epi == EPI_MASKDEC ? ((size_t)a.Nb * 16 + 2 * 128 * 16) * sizeof(float) : 0;
+  const size_t budget = 227 * 1024 - 1024 - g.hdr_bytes - dec_bytes;
   static const char* env_ops = getenv("CTN_TMA_OPSTAGES");
   int op = env_ops ? atoi(env_ops) : 3;
   if (op < 2) op = 2;
@@ -581,7 +699,7 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   if (env_raw && atoi(env_raw) >= 2 && atoi(env_raw) < raw) raw = atoi(env_raw);
   g.op_stages = op;
   g.raw_stages = raw;
-  const size_t smem = 1024 + g.hdr_bytes + (size_t)op * g.op_stage_bytes + (size_t)raw * g.raw_stage_bytes;
+  const size_t smem = 1024 + g.hdr_bytes + (size_t)op * g.op_stage_bytes + (size_t)raw * g.raw_stage_bytes + dec_bytes;
   int grid = num_sms();
   static const char* env_grid = getenv("CTN_UMMA_GRID");
   if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
@@ -589,5 +707,9 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   if (pro == PRO_DW && epi == EPI_RAW) return launch<PRO_DW, EPI_RAW>(g, smem, grid, st);
   if (pro == PRO_RES && epi == EPI_H) return launch<PRO_RES, EPI_H>(g, smem, grid, st);
   if (pro == PRO_NONE && epi == EPI_H) return launch<PRO_NONE, EPI_H>(g, smem, grid, st);
+  if (pro == PRO_PRELU && epi == EPI_MASKDEC) {
+    const int tiles = a.B * g.t_tiles;
+    return launch<PRO_PRELU, EPI_MASKDEC>(g, smem, grid < tiles ? grid : tiles, st);
+  }
   return CTN_EUNSUPPORTED;
 }

@@ -87,7 +87,7 @@ class Separator(nn.Module):
         if input.dim() != 3 or input.size(1) != self.num_features:
             raise ValueError("input.size() is expected (?, {}, ?), but given {}".format(self.num_features, tuple(input.size())))
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+            raise NotImplementedError("stand-alone Separator.forward is inference-only (training runs through ConvTasNet.forward, one autograd node): call under torch.no_grad()")
         w = input.contiguous()
         dev = N.require_cuda(w)
         B, _, frames = w.shape

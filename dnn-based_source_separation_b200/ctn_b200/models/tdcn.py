@@ -83,7 +83,9 @@ class ResidualBlock1d(nn.Module):
             dilation=dilation, causal=causal, nonlinear=nonlinear, norm=norm, dual_head=dual_head, eps=eps)
 
     def forward(self, input):
-        raise NotImplementedError("ResidualBlock1d is fused into TimeDilatedConvNet.forward on the sm_100a path")
+        """input (batch_size, num_features, T) -> (output or None, skip): tdcn.py:107-147, one fused block through
+        ctn_tcn_blocks_fwd (non-causal gLN, stride 1)."""
+        return run_blocks([self], input, want_output=self.dual_head)
 
     def native_params(self):
         """Device pointers in the order of ctn_block_params_t (include/ctn_b200.h)."""
@@ -114,7 +116,44 @@ class TimeDilatedConvBlock1d(nn.Module):
         self.net = nn.Sequential(*net)
 
     def forward(self, input):
-        raise NotImplementedError("TimeDilatedConvBlock1d is fused into TimeDilatedConvNet.forward on the sm_100a path")
+        """input (batch_size, num_features, T) -> (output or None, skip sum of the layers): tdcn.py:65-75"""
+        blocks = list(self.net)
+        return run_blocks(blocks, input, want_output=blocks[-1].dual_head)
+
+
+def run_blocks(blocks, input, want_output, math=None):
+    """A run of ResidualBlock1d modules with their own dilations through ctn_tcn_blocks_fwd -> (output | None, skip)."""
+    if input.dim() != 3:
+        raise ValueError("input is expected 3-D (batch_size, num_features, T), but given {}".format(tuple(input.size())))
+    if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for b in blocks for p in b.parameters())):
+        raise NotImplementedError("block-level forward is inference-only: training goes through ConvTasNet.forward (one autograd node)")
+    b0 = blocks[0]
+    if b0.causal or b0.stride != 1 or not b0.norm or not b0.nonlinear:
+        raise NotImplementedError("stand-alone blocks: non-causal gLN, stride 1, prelu only")
+    x = input.contiguous()
+    dev = N.require_cuda(x)
+    B, F_in, frames = x.shape
+    cfg = N.Config()
+    cfg.bottleneck, cfg.hidden = b0.bottleneck_conv1d.in_channels, b0.bottleneck_conv1d.out_channels
+    cfg.skip = b0.separable_conv1d.skip_pointwise_conv1d.out_channels
+    cfg.sep_kernel, cfg.num_blocks, cfg.num_layers, cfg.causal = b0.kernel_size, 1, len(blocks), 0
+    cfg.math = resolve_math(math)
+    cfg.eps_tcn = cfg.eps = float(b0.separable_conv1d.eps)
+    if F_in != cfg.bottleneck:
+        raise ValueError("input.size() is expected (?, {}, ?), but given {}".format(cfg.bottleneck, tuple(input.size())))
+    arr, keep = block_param_array(blocks, dev)
+    dil = (C.c_int * len(blocks))(*[int(b.dilation) for b in blocks])
+    cfg2 = N.Config.from_buffer_copy(cfg)
+    cfg2.num_layers = len(blocks)
+    need = C.c_size_t(0)
+    N.check(N.ctn_tcn_workspace_bytes(C.byref(cfg2), B, frames, C.byref(need)), "ctn_tcn_workspace_bytes")
+    ws = N.workspace(dev, need.value)
+    base = (ws.data_ptr() + 255) & ~255
+    skip = torch.empty(B, cfg.skip, frames, dtype=torch.float32, device=dev)
+    out = torch.empty(B, cfg.bottleneck, frames, dtype=torch.float32, device=dev) if want_output else None
+    N.check(N.ctn_tcn_blocks_fwd(C.byref(cfg2), arr, len(blocks), dil, x.data_ptr(), N.ptr(out), skip.data_ptr(), B, frames, base,
+                                 ws.numel() - (base - ws.data_ptr()), N.stream_ptr(dev)), "ctn_tcn_blocks_fwd")
+    return out, skip
 
 
 def block_param_array(residual_blocks, dev):
@@ -172,7 +211,7 @@ class TimeDilatedConvNet(nn.Module):
         if input.dim() != 3 or input.size(1) != self.num_features:
             raise ValueError("input.size() is expected (?, {}, ?), but given {}".format(self.num_features, tuple(input.size())))
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+            raise NotImplementedError("stand-alone TimeDilatedConvNet.forward is inference-only (training runs through ConvTasNet.forward, one autograd node): call under torch.no_grad()")
         x = input.contiguous()
         dev = N.require_cuda(x)
         B, _, frames = x.shape

