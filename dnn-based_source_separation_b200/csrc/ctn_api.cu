@@ -243,7 +243,10 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, pro1, EPI_H, c->math, st)); }
       const int Mt = has_out ? Bc + Sc : Sc;
       const int pad_left = c->causal ? (c->sep_kernel - 1) * dilation : ((c->sep_kernel - 1) * dilation) / 2;
-      if (c->math != CTN_MATH_FP32 && c->sep_kernel == 3) {
+      // fused depthwise producer: 3 taps at dilation 1, 2 or a multiple of 4 (128-bit aligned tap loads); anything else runs the
+      // stand-alone depthwise stage
+      const bool dw_fusable = c->sep_kernel == 3 && (dilation == 1 || dilation == 2 || dilation % 4 == 0);
+      if (c->math != CTN_MATH_FP32 && dw_fusable) {
         // K_BC fused (tcgen05): the producer warps compute u = PReLU(dwconv(gLN1(h))) (+stats2) on the fly and feed
         // it straight to the tensor core; u never touches HBM.  r = [Wo;Ws] diag(gamma2) u
         StageTimer tm(CTN_ST_PW2, st);

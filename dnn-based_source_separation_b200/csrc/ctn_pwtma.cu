@@ -82,12 +82,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void mbar_arrive_after(uint32_t bar, float dep) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "f"(dep) : "memory");
 }
+// shared-memory accesses of the producers' inner loop by 32-bit shared address (a generic pointer costs an S2R/LEA/IADD
+// window-base computation per access: 15 % of the producers' instructions in the ncu source view)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
-template <int PRO, int EPI>
+// DWM (PRO_DW only): depthwise tap geometry fixed at compile time -- 1 / 2: dilation 1 / 2 in the aligned window [t-4, t+8);
+// 3: dilation >= 4, one window box of 128 + 2d frames; 4: dilation >= 128, three boxes of 128 frames.  0 for the other prologues.
+template <int PRO, int EPI, int DWM>
 __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_constant__ TmaArgs g) {
+  constexpr int DCLS = DWM == 1 ? 1 : (DWM == 2 ? 2 : 4);
+  constexpr bool THREE = DWM == 4;
   constexpr int PROD_WARPS = Roles<PRO>::PROD_WARPS, EGROUPS = Roles<PRO>::EGROUPS, FIRST_PROD = Roles<PRO>::FIRST_PROD;
   constexpr int CPW = RC / PROD_WARPS;  // channels of a raw stage per producer warp (1 or 2)
   extern __shared__ uint8_t smem_raw[];
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             ptx::mbar_arrive_expect_tx(fb, g.raw_tx_bytes);
             if (!(g.dbg & 2u)) {
               if (PRO == PRO_DW) {
-                if (g.dw_three) {
+                if (THREE) {
 #pragma unroll
                   for (int k = 0; k < 3; ++k)
                     tma_load_2d(dst + (uint32_t)k * (RC * TM * 4), &g.tmA, tt * TM + (k - 1) * a.dw_dilation, b * a.K + c, fb);
@@ -211,6 +225,10 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
     if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
     int s = 0, rs = 0;
     uint32_t ph = 0, rph = 0;
+    // PRO_DW: float offsets of this thread's first tap / its channel's parameter row inside a raw stage (constant per thread)
+    const int dw_wd = TM + 2 * g.dw_pad;
+    const int dw_qoff = THREE ? pw * TM + lane * 4 : pw * dw_wd + lane * 4;
+    const int dw_poff = (THREE ? 3 * RC * TM : RC * dw_wd) + pw * 8;
     for (int it = 0; it < items_per_cta; ++it) {
       int nt, tt, b;
       decode(it, nt, tt, b);
@@ -219,61 +237,39 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
       if (PRO == PRO_DW) mr1 = gln_mean_rstd(a.dw_stats_in + 2 * b, (double)a.K * (double)a.frames, a.dw_eps);
       if (PRO == PRO_RES) mr_res = gln_mean_rstd(a.res_stats + 2 * b, a.res_n, a.res_eps);
       const int tbase = tt * TM + lane * 4;
-      int dcls = 4;
       bool dw_interior = false;
       if (PRO == PRO_DW) {
         const int d = a.dw_dilation;
-        dcls = d >= 4 ? 4 : d;
-        const int reach = d >= 4 ? d : 4;
+        const int reach = DCLS == 4 ? d : 4;
         dw_interior = (tt * TM - reach >= 0) && (tt * TM + TM - 1 + reach + 3 < a.frames) && (a.K % RC == 0);
       }
       for (int ks = 0; ks < g.k_slabs; ++ks) {
 #pragma unroll
         for (int sub = 0; sub < SUBS; ++sub) {
           ptx::mbar_wait(ptx::smem_u32(&hdr->rfull[rs]), rph);
-          const uint8_t* rb = raw0_p + (size_t)rs * g.raw_stage_bytes;
+          const uint32_t rb_s = raw0 + (uint32_t)rs * g.raw_stage_bytes;  // shared address of the raw stage
           float4 v[CPW];
           if (PRO == PRO_DW) {
             // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + (k-1)*d] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside
             static_assert(PRO != PRO_DW || CPW == 1, "one channel per producer warp");
             const int d = a.dw_dilation;
             const int c = ks * KS + sub * RC + pw;
-            float4 q0, q1, q2;
-            const float* prm;
-            if (g.dw_three) {
-              const float* r0 = reinterpret_cast<const float*>(rb) + pw * TM + lane * 4;
-              q0 = *reinterpret_cast<const float4*>(r0);
-              q1 = *reinterpret_cast<const float4*>(r0 + RC * TM);
-              q2 = *reinterpret_cast<const float4*>(r0 + 2 * RC * TM);
-              prm = reinterpret_cast<const float*>(rb) + 3 * RC * TM + pw * 8;
-            } else {
-              const int wd = TM + 2 * g.dw_pad;
-              const int step = dcls == 4 ? d : 4;  // d < 4: the aligned window [t-4, t+8)
-              const float* r0 = reinterpret_cast<const float*>(rb) + pw * wd + lane * 4 + (g.dw_pad - (dcls == 4 ? d : 4));
-              q0 = *reinterpret_cast<const float4*>(r0);
-              q1 = *reinterpret_cast<const float4*>(r0 + step);
-              q2 = *reinterpret_cast<const float4*>(r0 + 2 * step);
-              prm = reinterpret_cast<const float*>(rb) + RC * wd + pw * 8;
-            }
-            const float4 p0 = *reinterpret_cast<const float4*>(prm), p1 = *reinterpret_cast<const float4*>(prm + 4);
+            // tap loads: window mode -- the thread's first tap sits lane*4 floats into its channel row (the window starts `pad`
+            // frames before the tile and pad == max(d, 4)); three-box mode -- same column in the boxes at t-d, t, t+d
+            const uint32_t step_b = 4u * (uint32_t)(THREE ? RC * TM : (DCLS == 4 ? d : 4));
+            const uint32_t qa = rb_s + 4u * (uint32_t)dw_qoff, pa = rb_s + 4u * (uint32_t)dw_poff;
+            const float4 q0 = lds128(qa), q1 = lds128(qa + step_b), q2 = lds128(qa + 2 * step_b);
+            const float4 p0 = lds128(pa), p1 = lds128(pa + 16);
             // fold the operand scale into the (positively homogeneous) PReLU: scale taps and bias
             const float gsc = p0.x * mr1.y, gsh = p0.y - mr1.x * mr1.y * p0.x;
             const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
-            const int step = dcls == 4 ? d : 4;
-            const int first = dcls == 4 ? tbase - d : tbase - 4;
+            const int tstep = DCLS == 4 ? d : 4;
+            const int first = DCLS == 4 ? tbase - d : tbase - 4;
             // channels past K (K % 32 != 0: the last slab's second half) are rows of the NEXT sample: boundary path, zeroed
-            if (dw_interior && c < a.K) {
-              if (dcls == 4) v[0] = dw_channel<4, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);
-              else if (dcls == 2) v[0] = dw_channel<2, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);
-              else v[0] = dw_channel<1, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, true, dls, dlss);
-            } else {
-              const bool cv = c < a.K;
-              if (dcls == 4) v[0] = dw_channel<4, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, cv, dls, dlss);
-              else if (dcls == 2) v[0] = dw_channel<2, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, cv, dls, dlss);
-              else v[0] = dw_channel<1, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, step, tbase, a.frames, cv, dls, dlss);
-            }
+            if (dw_interior && c < a.K) v[0] = dw_channel<DCLS, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, true, dls, dlss);
+            else v[0] = dw_channel<DCLS, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, c < a.K, dls, dlss);
             {  // every lane's loads are complete once its outputs exist; then the warp hands the raw slot back
-              const float dep = (v[0].x + v[0].y) + (v[0].z + v[0].w) + (q0.x + q1.x + q2.x + p1.y);
+              const float dep = v[0].x + (q0.x + q1.x) + (q2.x + p1.y);
               __syncwarp();
               if (lane == 0) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rs]), dep);
             }
@@ -281,9 +277,9 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             float4 rr[CPW];
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
-              const float* r0 = reinterpret_cast<const float*>(rb) + (pw * CPW + j) * TM + lane * 4;
-              v[j] = *reinterpret_cast<const float4*>(r0);
-              if (PRO == PRO_RES) rr[j] = *reinterpret_cast<const float4*>(r0 + RC * TM);
+              const uint32_t r0 = rb_s + 4u * (uint32_t)((pw * CPW + j) * TM + lane * 4);
+              v[j] = lds128(r0);
+              if (PRO == PRO_RES) rr[j] = lds128(r0 + 4u * RC * TM);
             }
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
@@ -321,7 +317,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             }
           }
           if (sub == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
-          uint8_t* ob = smem + g.hdr_bytes + (size_t)s * g.op_stage_bytes;
+          const uint32_t ob = op0 + (uint32_t)s * g.op_stage_bytes;
 #pragma unroll
           for (int j = 0; j < CPW; ++j) {
             // MN-major 16-bit SWIZZLE_128B: atoms of 64 time steps x 8 channels (1024 B): channel row r = kl & 7 at r*128 B,
@@ -333,8 +329,8 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             uint2 h2, l2;
             ptx::split_f16x2(v[j].x, v[j].y, h2.x, l2.x);
             ptx::split_f16x2(v[j].z, v[j].w, h2.y, l2.y);
-            *reinterpret_cast<uint2*>(ob + off16) = h2;
-            *reinterpret_cast<uint2*>(ob + A_BYTES + off16) = l2;
+            sts64(ob + off16, h2.x, h2.y);
+            sts64(ob + A_BYTES + off16, l2.x, l2.y);
           }
           if (sub == SUBS - 1) {
             ptx::fence_proxy_async_smem();
@@ -610,16 +606,16 @@ int num_sms() {
   return g_sms[dev];
 }
 
-template <int PRO, int EPI>
+template <int PRO, int EPI, int DWM = 0>
 int launch(const TmaArgs& g, size_t smem, int grid, cudaStream_t st) {
   static bool attr_done[CTN_MAX_DEVICES] = {false};
   const int dev = ctn_current_device();
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_pw_tma<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_pw_tma<PRO, EPI, DWM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev] = true;
   }
-  k_pw_tma<PRO, EPI><<<grid, Roles<PRO>::THREADS, smem, st>>>(g);
+  k_pw_tma<PRO, EPI, DWM><<<grid, Roles<PRO>::THREADS, smem, st>>>(g);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
@@ -645,7 +641,9 @@ int ctn_pw_tma_supported(const PwArgs& a, int pro, int epi) {
     if (!a.dec_w || a.Nb <= 0 || a.M % a.Nb != 0 || a.Nb % n_tile != 0 || a.Nb > 1024) return 0;  // whole n-tiles per source; basis fits smem
   }
   if (a.pitch % TM != 0 || a.store_pre) return 0;
-  if (pro == PRO_DW && (a.dw_pad_left != a.dw_dilation || a.dw_dilation < 1 || !a.dw_params)) return 0;
+  if (pro == PRO_DW && (a.dw_pad_left != a.dw_dilation || a.dw_dilation < 1 || !a.dw_params ||
+                        !(a.dw_dilation == 1 || a.dw_dilation == 2 || a.dw_dilation % 4 == 0)))
+    return 0;
   return 1;
 }
 
@@ -704,7 +702,11 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   static const char* env_grid = getenv("CTN_UMMA_GRID");
   if (env_grid && atoi(env_grid) > 0) grid = atoi(env_grid);
   if (grid > g.num_items) grid = g.num_items;
-  if (pro == PRO_DW && epi == EPI_RAW) return launch<PRO_DW, EPI_RAW>(g, smem, grid, st);
+  if (pro == PRO_DW && epi == EPI_RAW) {
+    if (g.dw_three) return launch<PRO_DW, EPI_RAW, 4>(g, smem, grid, st);
+    if (a.dw_dilation >= 4) return launch<PRO_DW, EPI_RAW, 3>(g, smem, grid, st);
+    return a.dw_dilation == 2 ? launch<PRO_DW, EPI_RAW, 2>(g, smem, grid, st) : launch<PRO_DW, EPI_RAW, 1>(g, smem, grid, st);
+  }
   if (pro == PRO_RES && epi == EPI_H) return launch<PRO_RES, EPI_H>(g, smem, grid, st);
   if (pro == PRO_NONE && epi == EPI_H) return launch<PRO_NONE, EPI_H>(g, smem, grid, st);
   if (pro == PRO_PRELU && epi == EPI_MASKDEC) {
