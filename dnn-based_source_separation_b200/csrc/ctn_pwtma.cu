@@ -50,7 +50,7 @@ struct TmaArgs {
   const float* act_scale;  // power-of-two scale of the activation operand (device scalar; nullable = 1)
   int n_tile, n_tiles, k_slabs, t_tiles, num_items;
   int op_stages, raw_stages;
-  uint32_t op_stage_bytes, raw_stage_bytes, raw_tx_bytes, w_bytes, hdr_bytes, idesc;
+  uint32_t op_stage_bytes, raw_stage_bytes, raw_tx_bytes, w_bytes, hdr_bytes, res_tab_off, idesc;
   int dw_three;  // PRO_DW: 0 = one window box of 128 + 2*dw_pad frames, 1 = three boxes of 128 frames at t-d, t, t+d
   int dw_pad;    // window mode: halo frames on each side (dilation rounded up to a multiple of 4)
   uint32_t dbg;
@@ -140,6 +140,14 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
   {
     const float inv = 1.f / act_s;  // power of two: exact
     for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += blockDim.x) ssc_all[i] = __ldg(g.oscale + i) * inv;
+  }
+  float* s_res = reinterpret_cast<float*>(smem + g.res_tab_off);  // [2][k_slabs*KS]: v1, v2 (zero past K)
+  if (PRO == PRO_RES) {
+    const int kp = g.k_slabs * KS;
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) {
+      s_res[i] = i < a.K ? __ldg(a.res_v1 + i) : 0.f;
+      s_res[kp + i] = i < a.K ? __ldg(a.res_v2 + i) : 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -288,8 +296,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               if (PRO == PRO_RES) {
                 // x_new = x + rstd2*r + (v1 - mean2*rstd2*v2): the previous block's residual update, applied on the fly;
                 // the n-tile-0 item of each time tile also writes x_new for the block after next
-                const int kc = k < a.K ? k : a.K - 1;
-                const float cst = __ldg(a.res_v1 + kc) - mr_res.x * mr_res.y * __ldg(a.res_v2 + kc);
+                const float cst = s_res[k] - mr_res.x * mr_res.y * s_res[g.k_slabs * KS + k];
                 x.x = fmaf(mr_res.y, rr[j].x, x.x + cst); x.y = fmaf(mr_res.y, rr[j].y, x.y + cst);
                 x.z = fmaf(mr_res.y, rr[j].z, x.z + cst); x.w = fmaf(mr_res.y, rr[j].w, x.w + cst);
                 if (tbase + 0 >= a.frames) x.x = 0.f;
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
         }
         const long long tau = (long long)8 * t + egroup * 4 - a.dec_crop_left;
         const float vv[4] = {v.x, v.y, v.z, v.w};
-        if (te > 0 && tau >= 0 && tau + 3 < a.dec_T_out && ((tau & 3) == 0)) {
+        if (te > 0 && tau >= 0 && tau + 3 < a.dec_T_out && ((reinterpret_cast<uintptr_t>(yo + tau) & 15) == 0)) {
           *reinterpret_cast<float4*>(yo + tau) = v;
         } else {
 #pragma unroll
@@ -666,7 +673,10 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   g.idesc = ptx::make_idesc_f16(TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
   static const char* env_dbg = getenv("CTN_UMMA_DBG");
   g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
-  g.hdr_bytes = (uint32_t)(HDR_FIXED + ((g.n_tiles * g.n_tile * 4 + 1023) & ~1023));
+  // header: barriers + epilogue parameters (HDR_FIXED), the output scale table, then (PRO_RES) the folded bias vectors v1, v2 of the
+  // previous block for all K channels (two global loads per channel and stage sat on the producers' critical path otherwise)
+  g.res_tab_off = (uint32_t)(HDR_FIXED + g.n_tiles * g.n_tile * 4);
+  g.hdr_bytes = (uint32_t)((g.res_tab_off + (pro == PRO_RES ? 2 * g.k_slabs * KS * 4 : 0) + 1023) & ~1023u);
   g.op_stage_bytes = 2u * A_BYTES + 2u * g.w_bytes;
   uint32_t raw_data = 0;
   if (pro == PRO_DW) {
