@@ -34,7 +34,10 @@ PAPER = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottlenec
 CFG4 = dict(n_basis=64, kernel_size=2, sep_hidden_channels=128, sep_bottleneck_channels=64, sep_chunk_size=250, sep_hop_size=125,
             sep_num_blocks=6)
 METRIC = "audio-sec/s Conv-TasNet 2spk 4s@8kHz fwd+SI-SDR-PIT"
-CPU_THREADS = 32  # fixed team size of the CPU arm (torch's intra-op pool stops scaling around here on these tensor sizes)
+# CPU arm: fixed team size and mini-batch.  Round-1 sweeps on the GPU box's host (128 logical cores) found 8-16 torch threads on
+# 4-mixture mini-batches fastest (the reference trainer's own batch size is 4); 32 threads on the whole 32-mixture batch is 2.4x slower.
+CPU_THREADS = 16
+CPU_CHUNK = 4
 
 
 def parse():
@@ -154,16 +157,18 @@ def cpu_reference_leg(args, steps, warmup, cpu_batch):
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out, _ = fwd(mixture)
-            loss, perm = O.pit_neg_sisdr(out, sources)
-            float(loss)
+            tot = 0.0
+            for lo in range(0, cpu_batch, CPU_CHUNK):     # one step = the whole batch, walked in mini-batches of CPU_CHUNK mixtures
+                out, _ = fwd(mixture[lo:lo + CPU_CHUNK])
+                loss_b, perm = O.pit_neg_sisdr(out, sources[lo:lo + CPU_CHUNK], batch_mean=False)
+                tot += float(loss_b.sum())
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
     value = cpu_batch * args.seconds * len(times) / total
     return dict(value=value, unit="audio-sec/s", cores=thr, kind="port",
                 sample=f"{cpu_batch} x {args.seconds:g} s @ {args.sample_rate} Hz per step, {len(times)} steps (+{warmup} warm-up), "
-                       f"oracle/ port of the reference forward + PIT under no_grad, {thr} torch threads on {cores} logical cores",
+                       f"oracle/ port of the reference forward + PIT under no_grad in mini-batches of {CPU_CHUNK}, {thr} torch threads on {cores} logical cores",
                 ms_per_step=1e3 * total / len(times))
 
 
@@ -473,10 +478,26 @@ def main():
         Sn = (frames + ((P_ - (frames - K_) % P_) % P_) - K_) // P_ + 1
         state = B * Sn * K_ * F_ * 4.0
         glue_bytes = 12 * 4 * state + 2 * state + 2 * B * F_ * frames * 4.0   # 12 x (stats read + Y,R read + out write) + segment + overlap-add
-        roof = {"kernel": "ctn_dprnn_norm_res_fwd (x12) + segment + overlap-add", "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": None, "traffic": None, "algorithmic_bytes_per_step": glue_bytes,
-                "ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
-                "note": "per-kernel durations in profiles/ (ncu launch list of this command); the cuDNN LSTM recurrences are library code"}
+        # the dominant kernel of OUR part of the path, timed alone on tensors of the cfg4 state shape (CUDA events, burst peak applies)
+        Y = torch.randn(B, Sn, K_, F_, device=dev)
+        R0 = torch.randn(B, Sn, K_, F_, device=dev)
+        O_ = torch.empty(B, K_, Sn, F_, device=dev)
+        gam, bet = torch.ones(F_, device=dev), torch.zeros(F_, device=dev)
+        scr = torch.empty(2 * B, dtype=torch.float64, device=dev)
+
+        def glue():
+            N.check(N.ctn_dprnn_norm_res_fwd(Y.data_ptr(), R0.data_ptr(), gam.data_ptr(), bet.data_ptr(), O_.data_ptr(), B, Sn, K_, F_, 1e-12, 1,
+                                             scr.data_ptr(), N.stream_ptr(dev)), "ctn_dprnn_norm_res_fwd")
+        for _ in range(3):
+            glue()
+        ms_glue, _, _ = cuda_time(glue, 10, torch, D, dev)
+        per_call = 4 * state   # Y read twice (statistics, apply), R read, out written
+        ach = per_call / (ms_glue / 10 * 1e-3) / 1e9
+        roof = {"kernel": "ctn_dprnn_norm_res_fwd (gLN + residual + path swap; 12 calls per step)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "ms_per_call": ms_glue / 10, "algorithmic_bytes_per_call": per_call,
+                "glue_bytes_per_step": glue_bytes, "glue_ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
+                "note": "our kernels on this path are HBM-bound data movement; the step time is dominated by the 12 cuDNN bi-LSTM recurrences "
+                        "(library code, IEEE fp32 for parity with the reference; ctn_b200.models.dprnn.LSTM_TF32 = True trades parity for speed)"}
 
     line = {
         "metric": METRIC if args.config == "cfg2" else METRIC.replace("Conv-TasNet 2spk 4s@8kHz", workload_config(args, world)["workload"].split(",")[0]),

@@ -2,6 +2,7 @@
 //   encoder writes N*frames floats per sample (262 MB at cfg2), decoder reads S*N*frames floats.
 // Lanes run along time so every global access is a 128-byte coalesced row segment; the 16-tap filter bank
 // lives transposed in shared memory and is read with broadcast 128-bit LDS.
+#include <stdlib.h>
 #include "ctn_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -65,6 +66,78 @@ __global__ void __launch_bounds__(128) k_encoder(const float* __restrict__ x, co
   }
 }
 
+// Fast path (kernel = 2 x stride: the Conv-TasNet / DPRNN-TasNet encoders): thread = 4 consecutive frames x 4 channels per step, so
+// one broadcast LDS.128 of the filter bank feeds 16 FMAs (the kernel above issues one per 4) and every store is a 128-bit STG -- a
+// warp writes 512 contiguous bytes of one channel row.  Block = 128 frames x all N channels, 4 warps each owning a quarter of the
+// channels; gLN statistics per thread in fp32 (<= 64 values), then double.
+template <int L, int STRIDE>
+__global__ void __launch_bounds__(128) k_encoder_v4(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ w, int T,
+                                                    int pad_left, int N, int frames, int pitch, int relu, double* __restrict__ stats) {
+  constexpr int XW = 3 * STRIDE + L;  // input samples under 4 consecutive frames
+  extern __shared__ float sm[];
+  const int N4 = (N + 3) & ~3;
+  float* Wt = sm;                     // [L][N4]
+  float* xs = sm + L * N4;            // [127*STRIDE + L]
+  __shared__ double red[64];
+  const int b = blockIdx.y, f0 = blockIdx.x * 128, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < L * N4; i += 128) {
+    const int k = i / N4, n = i - k * N4;
+    Wt[i] = n < N ? W[n * L + k] : 0.f;
+  }
+  const int seg = 127 * STRIDE + L;
+  const float* xb = x + (size_t)b * T;
+  for (int i = tid; i < seg; i += 128) {
+    const int t = f0 * STRIDE + i - pad_left;
+    xs[i] = (t >= 0 && t < T) ? xb[t] : 0.f;
+  }
+  __syncthreads();
+  float xw[XW];
+#pragma unroll
+  for (int k = 0; k < XW; ++k) xw[k] = xs[lane * 4 * STRIDE + k];
+  const int f = f0 + lane * 4;
+  const bool v0 = f < frames, v1 = f + 1 < frames, v2 = f + 2 < frames, v3 = f + 3 < frames;
+  const int nq = ((N4 / 4 + 3) / 4) * 4;  // channels per warp, a multiple of 4
+  const int n_beg = warp * nq, n_end = min(N, n_beg + nq);
+  double s = 0.0, ss = 0.0;
+  float ls = 0.f, lss = 0.f;
+  int since = 0;
+  for (int n = n_beg; n < n_end; n += 4) {
+    float a[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[c][q] = 0.f;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const float4 wv = *reinterpret_cast<const float4*>(&Wt[k * N4 + n]);
+      const float wc[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[c][q] = fmaf(wc[c], xw[q * STRIDE + k], a[c][q]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (n + c >= N) break;
+      float4 o = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (!v0) o.x = 0.f;
+      if (!v1) o.y = 0.f;
+      if (!v2) o.z = 0.f;
+      if (!v3) o.w = 0.f;
+      *reinterpret_cast<float4*>(w + ((size_t)b * N + n + c) * pitch + f) = o;
+      ls += (o.x + o.y) + (o.z + o.w);
+      lss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, lss))));
+    }
+    if (++since == 4) { s += ls; ss += lss; ls = 0.f; lss = 0.f; since = 0; }  // spill fp32 partials (<= 64 values) to double
+  }
+  if (stats != nullptr) {
+    s += ls; ss += lss;
+    block_sum2_d(s, ss, red);
+    if (tid == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+  }
+}
+
 template <int L>
 static int launch_encoder(const float* x, const float* W, float* w, int B, int T, int pad_left, int N, int stride,
                           int frames, int pitch, int relu, double* stats, cudaStream_t st) {
@@ -76,6 +149,19 @@ static int launch_encoder(const float* x, const float* W, float* w, int B, int T
     if (e != cudaSuccess) return (int)e;
   }
   dim3 grid((pitch + 127) / 128, B);
+  static const char* env_v4 = getenv("CTN_ENC_V4");
+  if constexpr (L <= 20) {  // longer kernels: the 3*stride + L input window no longer fits the register file
+  if (stride * 2 == L && pitch % 128 == 0 && (((uintptr_t)w) & 15) == 0 && !(env_v4 && atoi(env_v4) == 0)) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_encoder_v4<L, L / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    k_encoder_v4<L, L / 2><<<grid, 128, smem, st>>>(x, W, w, T, pad_left, N, frames, pitch, relu, stats);
+    CTN_COUNT_LAUNCH();
+    CTN_RETURN_IF_CUDA_ERR();
+    return CTN_OK;
+  }
+  }
   k_encoder<L><<<grid, 128, smem, st>>>(x, W, w, T, pad_left, N, stride, frames, pitch, relu, stats);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();

@@ -13,8 +13,17 @@ def sisdr(input, target, eps=EPS):
     assert n_dims in [2, 3, 4], "Only 2D or 3D or 4D tensor is acceptable, but given {}D tensor.".format(n_dims)
     if input.shape != target.shape:
         raise ValueError("input and target must have the same shape")
-    if torch.is_grad_enabled() and (input.requires_grad or target.requires_grad):
-        raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+    if torch.is_grad_enabled() and target.requires_grad:
+        raise NotImplementedError("gradient w.r.t. the SI-SDR target is not built")
+    if torch.is_grad_enabled() and input.requires_grad:
+        # autograd: every row is a 1-source PIT problem (identity permutation) -> the fused forward/backward pair
+        # ctn_sisdr_pit_fwd / ctn_sisdr_pit_bwd; its loss is -SI-SDR
+        from .pit import _PitNegSisdrFn
+        T = input.shape[-1]
+        x, t = input.contiguous().view(-1, 1, T), target.contiguous().view(-1, 1, T)
+        N.require_cuda(x, t)
+        neg, _ = _PitNegSisdrFn.apply(x, t, float(eps))
+        return (-neg).view(input.shape[:-1])
     x, t = input.contiguous(), target.contiguous()
     dev = N.require_cuda(x, t)
     T = x.shape[-1]

@@ -27,6 +27,14 @@ EPS = 1e-12
 DEFAULT_MATH = None
 
 
+def _load_checkpoint(path):
+    """trainer checkpoints are plain dicts of tensors / python scalars: try the safe loader first"""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
 def _norm_affine(norm):
     return (norm.norm.weight, norm.norm.bias) if hasattr(norm, "norm") else (norm.gamma, norm.beta)
 
@@ -169,7 +177,7 @@ class ConvTasNet(nn.Module):
     def build_model(cls, model_path, load_state_dict=False):
         """Rebuild from a trainer checkpoint (dict = get_config() + 'state_dict'); tolerates the legacy keys
         n_bases / enc_bases / dec_bases like the reference (conv_tasnet.py:204-206)."""
-        config = torch.load(model_path, map_location=lambda storage, loc: storage, weights_only=False)
+        config = _load_checkpoint(model_path)
         get = config.get
         model = cls(
             get('n_bases') or config['n_basis'], in_channels=get('in_channels') or 1,
@@ -187,9 +195,71 @@ class ConvTasNet(nn.Module):
             model.load_state_dict(config['state_dict'])
         return model
 
+    # Google-Drive ids of the reference's published checkpoints (conv_tasnet.py:17-55); the files themselves are fetched by the
+    # reference's utils.utils.download_pretrained_model_from_google_drive -- this path only LOADS them (same directory layout)
+    pretrained_model_ids = {
+        "wsj0-mix": {8000: {2: {"enc_relu": "1yy-o7TyS1EcBWZ41rskMAVavtuEi4fMe"}, 3: {"enc_relu": "1-4Abl7LnEtwqMnAFQOcNLUOaDbgp3NoG"}},
+                     16000: {2: "", 3: ""}},
+        "wham/enhance-single": {8000: "1-6oiSK_CEE5Vl4OCy8TinA0cKsFFfGUg", 16000: ""},
+        "wham/enhance-both": {8000: "1-GISUVcWjMeP3GLvojz9b0svw6gkmd2G", 16000: ""},
+        "wham/separate-noisy": {8000: "1-0ckoPjaIiTJwv9Qotz6fkY2xeC77xdi", 16000: ""},
+        "musdb18": {44100: {"4sec_L20": "1A6dIofHZJQCUkyq-vxZ6KbPmEHLcf4WK", "8sec_L20": "1C4uv2z0w1s4rudIMaErLyEccNprJQWSZ",
+                            "8sec_L64": "1paXNGgH8m0kiJTQnn1WH-jEIurCKXwtw"}},
+        "librispeech": {16000: {2: "1NI6Q_WZHiTKkgkNTEcZE1yHskHgYUHpy"}},
+    }
+
     @classmethod
     def build_from_pretrained(cls, root="./pretrained", quiet=False, load_state_dict=True, **kwargs):
-        raise NotImplementedError("pretrained download (Google Drive) is outside this path; use build_model(path)")
+        """conv_tasnet.py:239-310: resolve <root>/ConvTasNet/<task>/sr.../model/<choice>.pth from (task, sample_rate, n_sources, config,
+        model_choice) exactly like the reference and build the model from it.  The download step is the reference's own helper
+        (Google Drive); when the file is not there and that helper is not importable, FileNotFoundError names the expected path."""
+        import os
+        task = kwargs.get('task')
+        if task not in cls.pretrained_model_ids:
+            raise KeyError("Invalid task ({}) is specified.".format(task))
+        ids = cls.pretrained_model_ids[task]
+        extra = {}
+        if task in ['wsj0-mix', 'wsj0']:
+            sample_rate = kwargs.get('sample_rate') or 8000
+            n_sources = kwargs.get('n_sources') or 2
+            config = kwargs.get('config') or 'enc_relu'
+            model_id = ids[sample_rate][n_sources][config]
+            download_dir = os.path.join(root, cls.__name__, task, "sr{}/{}speakers/{}".format(sample_rate, n_sources, config))
+            extra['n_sources'] = n_sources
+        elif task == 'musdb18':
+            sample_rate = kwargs.get('sample_rate') or 44100
+            config = kwargs.get('config') or '4sec_L20'
+            model_id = ids[sample_rate][config]
+            download_dir = os.path.join(root, cls.__name__, task, "sr{}".format(sample_rate), config)
+        elif task in ['wham/separate-noisy', 'wham/enhance-single', 'wham/enhance-both']:
+            sample_rate = kwargs.get('sample_rate') or 8000
+            model_id = ids[sample_rate]
+            download_dir = os.path.join(root, cls.__name__, task, "sr{}".format(sample_rate))
+        elif task == 'librispeech':
+            sample_rate = kwargs.get('sample_rate') or 16000
+            n_sources = kwargs.get('n_sources') or 2
+            model_id = ids[sample_rate][n_sources]
+            download_dir = os.path.join(root, cls.__name__, task, "sr{}/{}speakers".format(sample_rate, n_sources))
+            extra['n_sources'] = n_sources
+        else:
+            raise NotImplementedError("Not support task={}.".format(task))
+        extra['sample_rate'] = sample_rate
+        model_choice = kwargs.get('model_choice') or 'best'
+        model_path = os.path.join(download_dir, "model", "{}.pth".format(model_choice))
+        if not os.path.exists(model_path):
+            try:
+                from utils.utils import download_pretrained_model_from_google_drive  # the reference's helper, when src/ is on the path
+            except Exception:
+                raise FileNotFoundError("{} not found (Google-Drive id {!r}); place the reference checkpoint there -- this path loads "
+                                        "checkpoints, it does not download them".format(model_path, model_id))
+            download_pretrained_model_from_google_drive(model_id, download_dir, quiet=quiet)
+        config = _load_checkpoint(model_path)
+        model = cls.build_model(model_path, load_state_dict=load_state_dict)
+        if task == 'musdb18':
+            extra.update({'sources': config['sources'], 'n_sources': len(config['sources'])})
+        for key, value in extra.items():
+            setattr(model, key, value)
+        return model
 
     @property
     def num_parameters(self):

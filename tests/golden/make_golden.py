@@ -130,6 +130,25 @@ def grad_case(name, cfg: O.OracleConfig, batch, T, wseed, xseed, stride=97):
     print(f"{name}: loss {float(loss):.6f} perm {perm.tolist()} {len(grads)} gradient tensors -> {os.path.getsize(path)} B")
 
 
+def checkpoint_case():
+    """A trainer checkpoint written the way the reference's TrainerBase.save_model does (egs/wsj0-mix/common/src/driver.py:208-226):
+    get_config() + state_dict + optimizer / bookkeeping entries, from the unmodified reference model (tiny_gln weights)."""
+    cfg = O.OracleConfig(n_basis=16, kernel_size=4, sep_hidden_channels=16, sep_bottleneck_channels=8, sep_skip_channels=8,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False)
+    ref = build_reference(cfg)
+    ref.load_state_dict(O.synth_state_dict(cfg, seed=11), strict=True)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    config = ref.get_config()
+    config['state_dict'] = ref.state_dict()
+    config['optim_dict'] = opt.state_dict()
+    config['best_loss'], config['no_improvement'] = float('infinity'), 0
+    config['train_loss'], config['valid_loss'] = torch.zeros(3), torch.zeros(3)
+    config['epoch'] = 1
+    path = os.path.join(HERE, "ref_ckpt_tiny_gln.pth")
+    torch.save(config, path)
+    print("ref_ckpt_tiny_gln.pth ->", os.path.getsize(path), "B; config keys", sorted(k for k in config if k != 'state_dict'))
+
+
 def dprnn_cases():
     """DPRNN-TasNet (BASELINE cfg4) goldens from the unmodified reference: transform.py modules, one tiny model, and the cfg4
     hyper-parameters (N=64 L=2 F=64 H=128 K=250 P=125 B=6) on a short batch (strided subsample + fp64 checksums)."""
@@ -256,6 +275,9 @@ def module_cases():
 def main():
     paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
                  sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
+    if len(sys.argv) > 1 and sys.argv[1] == "ckpt":
+        checkpoint_case()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "dprnn":
         dprnn_cases()
         return
@@ -279,6 +301,7 @@ def main():
     module_cases()
     grad_case("paper_3spk_grad", O.OracleConfig(**paper, causal=False, n_sources=3), batch=2, T=8000, wseed=113, xseed=113)
     dprnn_cases()
+    checkpoint_case()
 
 
 if __name__ == "__main__":
