@@ -19,7 +19,7 @@
 //
 // Warp roles (one persistent CTA per SM):
 //   0-3    epilogue group 0            4  TMEM allocator + MMA issuer        5  TMA loader (one elected lane)
-//   6..    producers (PRO_DW: 16 warps x 1 channel of a 16-channel raw stage; else 8 warps x 2 channels)
+//   6..13  producers: 8 warps, each 2 channels of each of the two 16-channel raw stages of a slab (4 interleaved channel streams)
 //   then   epilogue group 1 (EPI_H kernels: 4 more warps, upper half of the columns)
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -57,7 +57,7 @@ struct TmaArgs {
 };
 
 template <int PRO> struct Roles {
-  static constexpr int PROD_WARPS = PRO == PRO_DW ? 16 : 8;
+  static constexpr int PROD_WARPS = 8;  // x SUBS * CPW = 4 channel streams per warp and slab
   static constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;
   static constexpr int FIRST_PROD = 6;
   static constexpr int THREADS = (4 + 1 + 1 + PROD_WARPS + 4 * (EGROUPS - 1)) * 32;
@@ -228,15 +228,16 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
     __syncwarp();
   } else if (warp >= FIRST_PROD && warp < FIRST_PROD + PROD_WARPS) {
     // ===================================== PRODUCERS ========================================================
+    // One step = one 32-channel operand slab = TWO raw stages; every warp works on SUBS * CPW = 4 independent channel streams
+    // per step (knob matrix of round 2: the producers alone took 104 us per pw2 launch at ~10 cycles per instruction and warp --
+    // dependent LDS -> FMA -> cvt -> STS chains, not issue slots; four interleaved streams per warp give the scheduler the
+    // instruction-level parallelism, and the fence / full-arrive / empty-wait are paid once per slab instead of per 16 channels)
     const int pw = warp - FIRST_PROD;
     float pslope = 0.f;
     if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
     int s = 0, rs = 0;
     uint32_t ph = 0, rph = 0;
-    // PRO_DW: float offsets of this thread's first tap / its channel's parameter row inside a raw stage (constant per thread)
-    const int dw_wd = TM + 2 * g.dw_pad;
-    const int dw_qoff = THREE ? pw * TM + lane * 4 : pw * dw_wd + lane * 4;
-    const int dw_poff = (THREE ? 3 * RC * TM : RC * dw_wd) + pw * 8;
+    const int dw_wd = TM + 2 * g.dw_pad;  // PRO_DW window mode: floats per channel row of a raw stage
     for (int it = 0; it < items_per_cta; ++it) {
       int nt, tt, b;
       decode(it, nt, tt, b);
@@ -252,79 +253,84 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
         dw_interior = (tt * TM - reach >= 0) && (tt * TM + TM - 1 + reach + 3 < a.frames) && (a.K % RC == 0);
       }
       for (int ks = 0; ks < g.k_slabs; ++ks) {
+        // the two raw stages of this slab (the ring may wrap between them)
+        int rsv[SUBS];
+        uint32_t rphv[SUBS];
 #pragma unroll
         for (int sub = 0; sub < SUBS; ++sub) {
-          ptx::mbar_wait(ptx::smem_u32(&hdr->rfull[rs]), rph);
-          const uint32_t rb_s = raw0 + (uint32_t)rs * g.raw_stage_bytes;  // shared address of the raw stage
-          float4 v[CPW];
+          rsv[sub] = rs; rphv[sub] = rph;
+          if (++rs == g.raw_stages) { rs = 0; rph ^= 1u; }
+        }
+        float4 v[SUBS][CPW];
+        float dep = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < SUBS; ++sub) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->rfull[rsv[sub]]), rphv[sub]);
+          const uint32_t rb_s = raw0 + (uint32_t)rsv[sub] * g.raw_stage_bytes;  // shared address of the raw stage
           if (PRO == PRO_DW) {
             // u[c][t] = PReLU( sum_k wd[c][k] * hn[c][t + (k-1)*d] + bd[c] ), hn = gLN1(h) inside [0,frames), 0 outside
-            static_assert(PRO != PRO_DW || CPW == 1, "one channel per producer warp");
             const int d = a.dw_dilation;
-            const int c = ks * KS + sub * RC + pw;
             // tap loads: window mode -- the thread's first tap sits lane*4 floats into its channel row (the window starts `pad`
             // frames before the tile and pad == max(d, 4)); three-box mode -- same column in the boxes at t-d, t, t+d
             const uint32_t step_b = 4u * (uint32_t)(THREE ? RC * TM : (DCLS == 4 ? d : 4));
-            const uint32_t qa = rb_s + 4u * (uint32_t)dw_qoff, pa = rb_s + 4u * (uint32_t)dw_poff;
-            const float4 q0 = lds128(qa), q1 = lds128(qa + step_b), q2 = lds128(qa + 2 * step_b);
-            const float4 p0 = lds128(pa), p1 = lds128(pa + 16);
-            // fold the operand scale into the (positively homogeneous) PReLU: scale taps and bias
-            const float gsc = p0.x * mr1.y, gsh = p0.y - mr1.x * mr1.y * p0.x;
-            const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
             const int tstep = DCLS == 4 ? d : 4;
             const int first = DCLS == 4 ? tbase - d : tbase - 4;
-            // channels past K (K % 32 != 0: the last slab's second half) are rows of the NEXT sample: boundary path, zeroed
-            if (dw_interior && c < a.K) v[0] = dw_channel<DCLS, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, true, dls, dlss);
-            else v[0] = dw_channel<DCLS, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, c < a.K, dls, dlss);
-            {  // every lane's loads are complete once its outputs exist; then the warp hands the raw slot back
-              const float dep = v[0].x + (q0.x + q1.x) + (q2.x + p1.y);
-              __syncwarp();
-              if (lane == 0) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rs]), dep);
-            }
-          } else {
-            float4 rr[CPW];
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
-              const uint32_t r0 = rb_s + 4u * (uint32_t)((pw * CPW + j) * TM + lane * 4);
-              v[j] = lds128(r0);
-              if (PRO == PRO_RES) rr[j] = lds128(r0 + 4u * RC * TM);
+              const int cl = pw * CPW + j;  // channel within the raw stage
+              const int c = ks * KS + sub * RC + cl;
+              const uint32_t qa = rb_s + 4u * (uint32_t)((THREE ? cl * TM : cl * dw_wd) + lane * 4);
+              const uint32_t pa = rb_s + 4u * (uint32_t)((THREE ? 3 * RC * TM : RC * dw_wd) + cl * 8);
+              const float4 q0 = lds128(qa), q1 = lds128(qa + step_b), q2 = lds128(qa + 2 * step_b);
+              const float4 p0 = lds128(pa), p1 = lds128(pa + 16);
+              // fold the operand scale into the (positively homogeneous) PReLU: scale taps and bias
+              const float gsc = p0.x * mr1.y, gsh = p0.y - mr1.x * mr1.y * p0.x;
+              const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
+              // channels past K (K % 32 != 0: the last slab's second half) are rows of the NEXT sample: boundary path, zeroed
+              if (dw_interior && c < a.K) v[sub][j] = dw_channel<DCLS, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, true, dls, dlss);
+              else v[sub][j] = dw_channel<DCLS, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, c < a.K, dls, dlss);
+              dep += v[sub][j].x + (q0.x + q1.x) + (q2.x + p1.y);
             }
+          } else {
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
               const int k = ks * KS + sub * RC + pw * CPW + j;
-              float4 x = v[j];
+              const uint32_t r0 = rb_s + 4u * (uint32_t)((pw * CPW + j) * TM + lane * 4);
+              float4 x = lds128(r0);
               if (PRO == PRO_RES) {
                 // x_new = x + rstd2*r + (v1 - mean2*rstd2*v2): the previous block's residual update, applied on the fly;
                 // the n-tile-0 item of each time tile also writes x_new for the block after next
+                const float4 rr = lds128(r0 + 4u * RC * TM);
                 const float cst = s_res[k] - mr_res.x * mr_res.y * s_res[g.k_slabs * KS + k];
-                x.x = fmaf(mr_res.y, rr[j].x, x.x + cst); x.y = fmaf(mr_res.y, rr[j].y, x.y + cst);
-                x.z = fmaf(mr_res.y, rr[j].z, x.z + cst); x.w = fmaf(mr_res.y, rr[j].w, x.w + cst);
+                x.x = fmaf(mr_res.y, rr.x, x.x + cst); x.y = fmaf(mr_res.y, rr.y, x.y + cst);
+                x.z = fmaf(mr_res.y, rr.z, x.z + cst); x.w = fmaf(mr_res.y, rr.w, x.w + cst);
                 if (tbase + 0 >= a.frames) x.x = 0.f;
                 if (tbase + 1 >= a.frames) x.y = 0.f;
                 if (tbase + 2 >= a.frames) x.z = 0.f;
                 if (tbase + 3 >= a.frames) x.w = 0.f;
                 if (nt == 0 && k < a.K) *reinterpret_cast<float4*>(a.res_x_out + ((size_t)b * a.K + k) * a.pitch + tbase) = x;
+                dep += rr.x + rr.w;
               }
+              dep += x.x + x.w;
               if (k >= a.K) x = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past K belong to the next sample
               if (PRO == PRO_PRELU) {
                 x.x = prelu_f(x.x, pslope); x.y = prelu_f(x.y, pslope); x.z = prelu_f(x.z, pslope); x.w = prelu_f(x.w, pslope);
               }
               x.x *= act_s; x.y *= act_s; x.z *= act_s; x.w *= act_s;
-              v[j] = x;
-            }
-            {
-              float dep = 0.f;
-#pragma unroll
-              for (int j = 0; j < CPW; ++j) {
-                dep += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-                if (PRO == PRO_RES) dep += rr[j].x + rr[j].w;
-              }
-              __syncwarp();
-              if (lane == 0) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rs]), dep);
+              v[sub][j] = x;
             }
           }
-          if (sub == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
-          const uint32_t ob = op0 + (uint32_t)s * g.op_stage_bytes;
+        }
+        // every lane's loads are complete once `dep` exists; then the warp hands both raw slots back
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int sub = 0; sub < SUBS; ++sub) mbar_arrive_after(ptx::smem_u32(&hdr->rempty[rsv[sub]]), dep);
+        }
+        ptx::mbar_wait(ptx::smem_u32(&hdr->empty[s]), ph ^ 1u);
+        const uint32_t ob = op0 + (uint32_t)s * g.op_stage_bytes;
+#pragma unroll
+        for (int sub = 0; sub < SUBS; ++sub) {
 #pragma unroll
           for (int j = 0; j < CPW; ++j) {
             // MN-major 16-bit SWIZZLE_128B: atoms of 64 time steps x 8 channels (1024 B): channel row r = kl & 7 at r*128 B,
@@ -334,19 +340,16 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
             const uint32_t off16 = (uint32_t)(kl >> 3) * 2048u + (uint32_t)(lane >> 4) * 1024u + r8 * 128u +
                                    (((uint32_t)((lane & 15) >> 1) ^ r8) << 4) + (uint32_t)(lane & 1) * 8u;
             uint2 h2, l2;
-            ptx::split_f16x2(v[j].x, v[j].y, h2.x, l2.x);
-            ptx::split_f16x2(v[j].z, v[j].w, h2.y, l2.y);
+            ptx::split_f16x2(v[sub][j].x, v[sub][j].y, h2.x, l2.x);
+            ptx::split_f16x2(v[sub][j].z, v[sub][j].w, h2.y, l2.y);
             sts64(ob + off16, h2.x, h2.y);
             sts64(ob + A_BYTES + off16, l2.x, l2.y);
           }
-          if (sub == SUBS - 1) {
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
-            if (++s == g.op_stages) { s = 0; ph ^= 1u; }
-          }
-          if (++rs == g.raw_stages) { rs = 0; rph ^= 1u; }
         }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->full[s]));
+        if (++s == g.op_stages) { s = 0; ph ^= 1u; }
       }
       if (PRO == PRO_DW && nt == 0) {
         // the sums were taken over act_s * u: undo the power-of-two scale exactly in double

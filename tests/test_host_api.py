@@ -130,6 +130,28 @@ def test_get_config_build_model_roundtrip(tmp_path):
         assert k1 == k2 and torch.equal(v1, v2)
 
 
+def test_reference_trainer_checkpoint_loads(golden_dir):
+    """A checkpoint written by the UNMODIFIED reference the way its trainer does (driver.py:208-226; tests/golden/make_golden.py
+    checkpoint_case) rebuilds through build_model(load_state_dict=True): same config, same 71 tensors; the resumed optimizer state of
+    the reference (`optim_dict`) loads into torch.optim.Adam over our parameters (same parameter order)."""
+    path = os.path.join(golden_dir, "ref_ckpt_tiny_gln.pth")
+    m = ConvTasNet.build_model(path, load_state_dict=True)
+    pkg = torch.load(path, map_location="cpu", weights_only=False)
+    assert m.get_config() == {k: pkg[k] for k in m.get_config()}
+    sd = O.synth_state_dict(O.OracleConfig(n_basis=16, kernel_size=4, sep_hidden_channels=16, sep_bottleneck_channels=8, sep_skip_channels=8,
+                                           sep_num_blocks=2, sep_num_layers=3, causal=False), seed=11)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt.load_state_dict(pkg['optim_dict'])          # trainer resume path (driver.py:51-68)
+    assert pkg['epoch'] == 1
+    with pytest.raises(FileNotFoundError):
+        ConvTasNet.build_from_pretrained(root=str(golden_dir), task='wsj0-mix', sample_rate=8000, n_sources=2)
+    with pytest.raises(KeyError):
+        ConvTasNet.build_from_pretrained(task='no-such-task')
+
+
 def test_constructor_envelope_errors():
     with pytest.raises(AssertionError):
         ConvTasNet(64, 16, stride=7, enc_basis='trainable', dec_basis='trainable', enc_nonlinear=None)

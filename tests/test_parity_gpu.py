@@ -539,3 +539,30 @@ def test_fused_mask_decoder_matches_unfused_and_oracle(T, S):
     # tile seams are added with two-operand red.add (order-independent); run-to-run differences can only come from the order of the
     # fp64 statistics atomics upstream
     torch.testing.assert_close(fused, again, rtol=0, atol=1e-6)
+
+
+def test_reference_checkpoint_runs_on_the_kernels(golden_dir):
+    """reference trainer checkpoint (tests/golden/ref_ckpt_tiny_gln.pth) -> build_model -> sm_100a forward == the golden output the
+    reference itself produced with those weights (tiny_gln)."""
+    rec = _load(golden_dir, "tiny_gln")
+    model = ConvTasNet.build_model(os.path.join(golden_dir, "ref_ckpt_tiny_gln.pth"), load_state_dict=True).cuda().eval()
+    mixture, sources = O.synth_batch(rec["batch"], 2, rec["T"], seed=rec["xseed"])
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        loss, perm = PIT1d(NegSISDR(), 2)(out, sources.cuda())
+    torch.testing.assert_close(out.cpu(), rec["out"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), rec["latent"], rtol=RTOL, atol=ATOL)
+    assert torch.equal(perm.cpu(), rec["perm"])
+
+
+def test_sisdr_autograd_matches_oracle():
+    """sisdr / NegSISDR under autograd (training without PIT): gradient w.r.t. the estimate vs torch autograd over the oracle."""
+    g = torch.Generator().manual_seed(3)
+    est, tgt = torch.randn(4, 3, 2000, generator=g), torch.randn(4, 3, 2000, generator=g)
+    e_ref = est.clone().requires_grad_(True)
+    O.neg_sisdr(e_ref, tgt).backward()
+    e = est.cuda().requires_grad_(True)
+    loss = NegSISDR()(e, tgt.cuda())
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), O.neg_sisdr(est, tgt), rtol=0, atol=1e-4)
+    torch.testing.assert_close(e.grad.cpu(), e_ref.grad, rtol=1e-4, atol=1e-5 * float(e_ref.grad.abs().max()))
