@@ -136,16 +136,22 @@ __global__ void __launch_bounds__(256) k_scale_partials(const ScaleJobs jobs, fl
   dskip = block_max(dskip, red);
   if (threadIdx.x == 0) { part[3 * blockIdx.x] = u; part[3 * blockIdx.x + 1] = dout; part[3 * blockIdx.x + 2] = dskip; }
 }
-__global__ void __launch_bounds__(32) k_scale_chain(const ScaleJobs jobs, const float* __restrict__ part) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_scale_chain(const ScaleJobs jobs, const float* __restrict__ part) {
+  // stage everything the serial chain needs in shared memory first (the dependent global loads of a one-thread loop cost 12 us)
+  __shared__ float sp[3 * CTN_MAX_BLOCKS];
+  __shared__ float sx[8];
+  for (int i = threadIdx.x; i < 3 * jobs.n; i += blockDim.x) sp[i] = part[i];
   float X = 0.f;
-  for (int i = 0; i < jobs.x0_n; ++i) X = fmaxf(X, fabsf(jobs.x0_bound[i]));
+  for (int i = threadIdx.x; i < jobs.x0_n; i += blockDim.x) X = fmaxf(X, fabsf(jobs.x0_bound[i]));
+  X = block_max(X, sx);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   float S = 0.f;
   for (int i = 0; i < jobs.n; ++i) {
     jobs.scales[2 * i] = pow2_scale_for(X);
-    jobs.scales[2 * i + 1] = pow2_scale_for(part[3 * i]);
-    X += part[3 * i + 1];
-    S += part[3 * i + 2];
+    jobs.scales[2 * i + 1] = pow2_scale_for(sp[3 * i]);
+    X += sp[3 * i + 1];
+    S += sp[3 * i + 2];
   }
   const float am = jobs.mask_slope ? fmaxf(1.f, fabsf(jobs.mask_slope[0])) : 1.f;
   jobs.scales[2 * jobs.n] = pow2_scale_for(am * S);
@@ -155,7 +161,7 @@ int ctn_act_scales(const ScaleJobs& jobs, cudaStream_t st) {
   float* part = jobs.scales + 2 * jobs.n + 1;  // scratch behind the scales: 3 floats per block
   k_scale_partials<<<jobs.n, 256, 0, st>>>(jobs, part);
   CTN_COUNT_LAUNCH();
-  k_scale_chain<<<1, 32, 0, st>>>(jobs, part);
+  k_scale_chain<<<1, 256, 0, st>>>(jobs, part);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
@@ -405,17 +411,26 @@ int ctn_finish_fwd(const float* outraw, const FoldedConv f, const double* stats2
 // grid (pitch/512, Sc, B), block 128: thread = 4 consecutive frames of one skip channel, loops over the blocks
 __global__ void __launch_bounds__(128) k_skip_reduce(const SkipJobs jobs, double n2, float eps, float* __restrict__ skip, int Sc,
                                                      int frames, int pitch) {
+  // per residual block the (rstd, folded constant) of this (sample, channel) -- computed ONCE per thread block (the fp64 mean /
+  // rstd evaluation used to run 24 times in every thread and out-weighed the 24 loads it accompanied)
+  __shared__ float s_rstd[CTN_MAX_BLOCKS], s_c[CTN_MAX_BLOCKS];
   const int b = blockIdx.z, m = blockIdx.y;
+  if (threadIdx.x < jobs.n) {
+    const SkipJob& jb = jobs.j[threadIdx.x];
+    const float2 mr = gln_mean_rstd(jb.stats2 + 2 * b, n2, eps);
+    s_rstd[threadIdx.x] = mr.y;
+    s_c[threadIdx.x] = __ldg(jb.v1 + jb.off + m) - mr.x * mr.y * __ldg(jb.v2 + jb.off + m);
+  }
+  __syncthreads();
   const int t = (blockIdx.x * 128 + threadIdx.x) * 4;
   if (t >= pitch) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < jobs.n; ++i) {
     const SkipJob& jb = jobs.j[i];
-    const float2 mr = gln_mean_rstd(jb.stats2 + 2 * b, n2, eps);
-    const float c = __ldg(jb.v1 + jb.off + m) - mr.x * mr.y * __ldg(jb.v2 + jb.off + m);
     const float4 r = __ldg(reinterpret_cast<const float4*>(jb.r + ((size_t)b * jb.Mt + jb.off + m) * pitch + t));
-    acc.x += fmaf(mr.y, r.x, c); acc.y += fmaf(mr.y, r.y, c); acc.z += fmaf(mr.y, r.z, c); acc.w += fmaf(mr.y, r.w, c);
+    const float rs = s_rstd[i], c = s_c[i];
+    acc.x += fmaf(rs, r.x, c); acc.y += fmaf(rs, r.y, c); acc.z += fmaf(rs, r.z, c); acc.w += fmaf(rs, r.w, c);
   }
   if (t + 0 >= frames) acc.x = 0.f;
   if (t + 1 >= frames) acc.y = 0.f;
