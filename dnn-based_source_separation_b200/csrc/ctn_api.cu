@@ -174,8 +174,11 @@ static int pw_dispatch(const PwArgs& a, int pro, int epi, int math, cudaStream_t
 // TCN over ws->x (padded layout) -> ws->skip.  stats region must be zeroed by the caller.
 // dil (nullable): explicit dilation per block (ctn_tcn_blocks_fwd); default 2^layer (dilated=True, tdcn.py:52-54).
 // x_final (nullable): receives a pointer to the residual stream AFTER the last block (x_n), updated in the workspace.
+// hooks (nullable): TRAINING forward through the fused kernels -- block i reads its input from x_keep[i] (x_keep[0] = the head's
+// output, filled by the caller) and leaves x_{i+1} in x_keep[i+1]; pw1 stores the PRE-activation W1 x + b1 in hpre[i], the fused
+// depthwise producer applies PReLU on load and stores its own pre-activation in upre[i] (what ctn_convtasnet_bwd consumes).
 static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnWs* ws, int B, int frames, int pitch,
-                   cudaStream_t st, const int* dil = nullptr, float** x_final = nullptr) {
+                   cudaStream_t st, const int* dil = nullptr, float** x_final = nullptr, const TcnTrainHooks* hooks = nullptr) {
   const int R = c->num_blocks, X = c->num_layers, Bc = c->bottleneck, H = c->hidden, Sc = c->skip;
   if (c->causal)  // cLN: cumulative statistics -> un-fused pipeline in the reference's operation order
     return ctn_causal_tcn(c, blocks, ws->x, ws->skip, ws->h, ws->u, B, frames, pitch, ws->causal_ws, st);
@@ -238,21 +241,27 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
       // update x += rstd2*r[:Bc] + c inside its own producer (PRO_RES) -- no separate finishing pass over x
       const bool fuse_res = c->math != CTN_MATH_FP32;
       float* xbuf[2] = {ws->x + go * Bc, ws->xalt + go * Bc};
+      if (hooks) {  // per-block buffers: x_i is read from x_keep[i] (written by block i-1 below), kept for the backward
+        if (!fuse_res || g0 != 0) return CTN_EUNSUPPORTED;
+        hbuf = hooks->hpre[i];
+      }
       a.A = fuse_res ? xbuf[(i + 1) & 1] : xbuf[0];
-      if (fuse_res && i == 0) a.A = xbuf[0];
+      if (fuse_res && i == 0) a.A = hooks ? hooks->x_keep[0] : xbuf[0];
       a.W = p.bottleneck_w; a.D = hbuf; a.B = Bg; a.M = H; a.K = Bc; a.frames = frames; a.pitch = pitch;
+      a.store_pre = hooks ? 1 : 0;
       a.bias = p.bottleneck_b; a.slope = p.prelu1; a.stats_out = st1; a.wimg = ws->wimg1[i];
       if (scaled) a.act_scale = ws->scales + 2 * i;
       int pro1 = PRO_NONE;
       if (fuse_res && i > 0) {
         // x_{i} = x_{i-1} + deferred gLN2 of block i-1;  x_{i-1} lives in xbuf[(i-1)&1], x_i goes to xbuf[i&1]
         pro1 = PRO_RES;
-        a.A = xbuf[(i - 1) & 1];
+        a.A = hooks ? hooks->x_keep[i - 1] : xbuf[(i - 1) & 1];
         a.res_r = ws->rblk[i - 1] + go * (Bc + Sc); a.res_Mt = Bc + Sc;  // block i-1 always has the out head (only the last block lacks it)
         a.res_v1 = ws->folds[i - 1].v1; a.res_v2 = ws->folds[i - 1].v2;
         a.res_stats = ws->stats + (size_t)(2 * (i - 1) + 1) * B * 2 + 2 * g0; a.res_n = (double)H * (double)frames; a.res_eps = c->eps_tcn;
-        a.res_x_out = xbuf[i & 1];
+        a.res_x_out = hooks ? hooks->x_keep[i] : xbuf[i & 1];
       }
+      if (hooks && !(c->math == CTN_MATH_F16X3 && ctn_pw_tma_supported(a, pro1, EPI_H))) return CTN_EUNSUPPORTED;
       { StageTimer tm(CTN_ST_PW1, st); CTN_TRY(pw_dispatch(a, pro1, EPI_H, c->math, st)); }
       const int Mt = has_out ? Bc + Sc : Sc;
       float* rb = ws->rblk[i] + go * Mt;
@@ -270,8 +279,13 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
         a.pro_slope = p.prelu2; a.dw_norm_g = p.norm1_g; a.dw_norm_b = p.norm1_b; a.dw_w = p.dw_w; a.dw_b = p.dw_b;
         a.dw_stats_in = st1; a.dw_stats_out = st2; a.dw_dilation = dilation; a.dw_pad_left = pad_left; a.dw_eps = c->eps_tcn;
         if (scaled) { a.act_scale = ws->scales + 2 * i + 1; a.dw_params = ws->dwp[i]; }
+        if (hooks) {
+          a.dw_in_slope = p.prelu1; a.dw_u_pre_out = hooks->upre[i];
+          if (!(c->math == CTN_MATH_F16X3 && ctn_pw_tma_supported(a, PRO_DW, EPI_RAW))) return CTN_EUNSUPPORTED;
+        }
         CTN_TRY(pw_dispatch(a, PRO_DW, EPI_RAW, c->math, st));
       } else {
+        if (hooks) return CTN_EUNSUPPORTED;
         // K_B: u = PReLU(dwconv(gLN1(h))), stats2
         { StageTimer tm(CTN_ST_DW, st);
           CTN_TRY(ctn_dw_fwd(hbuf, ubuf, p.norm1_g, p.norm1_b, p.dw_w, p.dw_b, p.prelu2, st1, st2, Bg, H, frames, pitch,
@@ -312,6 +326,61 @@ static int run_tcn(const ctn_config_t* c, const ctn_block_params_t* blocks, TcnW
                              c->eps_tcn, xl, ws->skip, B, Bc, Sc, 1, 2 /* x rows only */, frames, pitch, st));
     *x_final = xl;
   }
+  return CTN_OK;
+}
+
+// ---- training forward through the fused kernels (called by ctn_convtasnet_fwd_train, ctn_train.cu) ----------------------------
+// The training workspace carries its own copy of the small per-forward state of the TCN (folds, weight images, depthwise
+// parameter packs, operand scales) and one raw [out;skip] tensor per block; x / h_pre / u_pre live in the caller's per-block
+// buffers, the statistics in the caller's array (same [2*RX][B][2] layout the backward reads).
+static void carve_tcn_train(Carver& cv, const ctn_config_t* c, int B, int pitch, TcnWs* ws) {
+  const int RX = c->num_blocks * c->num_layers;
+  const int Mt = c->bottleneck + c->skip;
+  ws->stats = nullptr; ws->stats_bytes = 0;
+  ws->folds.resize(RX);
+  ws->wimg1.assign(RX, nullptr);
+  ws->wimg2.assign(RX, nullptr);
+  ws->dwp.assign(RX, nullptr);
+  ws->rblk.assign(RX, nullptr);
+  for (int i = 0; i < RX; ++i) {
+    ws->folds[i].Wf = cv.take<float>((size_t)Mt * c->hidden);
+    ws->folds[i].v1 = cv.take<float>(Mt);
+    ws->folds[i].v2 = cv.take<float>(Mt);
+    ws->folds[i].vb = cv.take<float>(Mt);
+    ws->wimg1[i] = cv.take<float>(ctn_umma_wimg_bytes(c->hidden, c->bottleneck, c->math) / sizeof(float));
+    ws->wimg2[i] = cv.take<float>(ctn_umma_wimg_bytes(Mt, c->hidden, c->math) / sizeof(float));
+    ws->dwp[i] = cv.take<float>((size_t)ctn_round_up(c->hidden, 16) * 8);
+    ws->rblk[i] = cv.take<float>((size_t)B * pitch * Mt);
+  }
+  ws->scales = cv.take<float>((size_t)5 * RX + 8);
+  ws->x0_bound = cv.take<float>(64);
+  ws->x0_n = 1;
+  ws->mask_slope = nullptr;
+  ws->x = ws->xalt = ws->skip = ws->h = ws->u = ws->outraw = nullptr;
+  ws->causal_ws = nullptr;
+}
+size_t ctn_tcn_train_ws_bytes(const ctn_config_t* c, int B, int pitch) {
+  Carver cv(nullptr);
+  TcnWs ws;
+  carve_tcn_train(cv, c, B, pitch, &ws);
+  return cv.off + 512;
+}
+int ctn_tcn_train_fwd(const ctn_config_t* c, const ctn_block_params_t* blocks, void* mem, size_t mem_bytes, const TcnTrainHooks* hooks,
+                      double* stats, float* skip, const float* x0_bound, int x0_n, const float* mask_slope, const float** mask_scale,
+                      int B, int frames, int pitch, cudaStream_t st) {
+  if (!c || !blocks || !mem || !hooks || !stats || !skip || (((uintptr_t)mem) & 255)) return CTN_EINVAL;
+  if (c->math != CTN_MATH_F16X3 || c->causal || c->sep_kernel != 3) return CTN_EUNSUPPORTED;
+  if (mem_bytes < ctn_tcn_train_ws_bytes(c, B, pitch)) return CTN_EWORKSPACE;
+  Carver cv(mem);
+  TcnWs ws;
+  carve_tcn_train(cv, c, B, pitch, &ws);
+  ws.stats = stats;
+  ws.skip = skip;
+  ws.x0_bound = const_cast<float*>(x0_bound);
+  ws.x0_n = x0_n;
+  ws.mask_slope = mask_slope;
+  CTN_TRY(run_tcn(c, blocks, &ws, B, frames, pitch, st, nullptr, nullptr, hooks));
+  if (mask_scale) *mask_scale = ws.scales + 2 * c->num_blocks * c->num_layers;
   return CTN_OK;
 }
 

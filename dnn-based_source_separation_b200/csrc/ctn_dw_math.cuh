@@ -6,10 +6,11 @@
 // One channel, 4 consecutive time steps.  q0,q1,q2: the three aligned 128-bit loads (d >= 4: taps t-d, t, t+d;
 // d < 4: the window [t-4, t+8)).  DCLS in {1, 2, 4(=d>=4)} selects the tap positions at compile time.
 // INTERIOR tiles (every tap of every element inside [0, frames)) fold gLN1 into the taps: 3 FMA per output.
-template <int DCLS, bool INTERIOR>
+// KEEP_PRE (training forward): also returns the PRE-activation (dwconv + bias, zero at the padded positions) through `pre`.
+template <int DCLS, bool INTERIOR, bool KEEP_PRE = false>
 __device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, const float4 q2, float gsc, float gsh, float w0,
                                              float w1, float w2, float bd, float slope, int first, int step, int tbase,
-                                             int frames, bool cvalid, float2& ls, float2& lss) {
+                                             int frames, bool cvalid, float2& ls, float2& lss, float4* pre = nullptr) {
   const float win[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
   constexpr int i0 = DCLS == 4 ? 0 : (DCLS == 2 ? 2 : 3);
   constexpr int i1 = 4;
@@ -40,6 +41,12 @@ __device__ __forceinline__ float4 dw_channel(const float4 q0, const float4 q1, c
       const float h2 = (t2 >= 0 && t2 < frames) ? fmaf(win[i2 + e], gsc, gsh) : 0.f;
       o[e] = fmaf(w2, h2, fmaf(w1, h1, fmaf(w0, h0, bd)));
     }
+  }
+  if (KEEP_PRE) {
+    float pz[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pz[e] = (!INTERIOR && (tbase + e >= frames || !cvalid)) ? 0.f : o[e];
+    *pre = make_float4(pz[0], pz[1], pz[2], pz[3]);
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {

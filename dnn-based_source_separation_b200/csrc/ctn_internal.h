@@ -67,6 +67,10 @@ struct PwArgs {
   // bound on |operand| derived from the weights alone (ctn_act_scales) so that fp16 can never saturate; undone in the epilogue
   const float* act_scale;
   const float* dw_params;  // PRO_DW, TMA-fed kernel: packed per-channel parameters [ceil16(K)][8] (ctn_act_scales)
+  // PRO_DW, training forward (TMA-fed kernel): A holds the PRE-activation h_pre = W1 x + b1 (the backward needs it), the producer
+  // applies PReLU(dw_in_slope) on load; the depthwise pre-activation u_pre is stored to dw_u_pre_out (B, K, pitch)
+  const float* dw_in_slope;
+  float* dw_u_pre_out;
   uint32_t dbg_idesc, dbg_lbo_a, dbg_sbo_a, dbg_sbo_w;  // 0 = defaults (descriptor probing from the debug entry)
 };
 
@@ -114,6 +118,13 @@ struct ScaleJobs {
 int ctn_act_scales(const ScaleJobs& jobs, cudaStream_t st);
 // max |x| over rows x frames of a pitched tensor -> *out (float, must be zeroed by the caller)
 int ctn_absmax_pitch(const float* x, int rows, int frames, int pitch, float* out, cudaStream_t st);
+
+// training forward of the TCN through the fused inference kernels (ctn_api.cu); per-block buffers owned by the training workspace
+struct TcnTrainHooks { float* const* x_keep; float* const* hpre; float* const* upre; };
+size_t ctn_tcn_train_ws_bytes(const ctn_config_t* c, int B, int pitch);
+int ctn_tcn_train_fwd(const ctn_config_t* c, const ctn_block_params_t* blocks, void* mem, size_t mem_bytes, const TcnTrainHooks* hooks,
+                      double* stats, float* skip, const float* x0_bound, int x0_n, const float* mask_slope, const float** mask_scale,
+                      int B, int frames, int pitch, cudaStream_t st);
 
 // depthwise stage: u = PReLU(dwconv(gLN1(h))) (+ stats2), all (B,H,pitch)
 int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_b, const float* dw_w, const float* dw_b,

@@ -104,8 +104,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 // shared-memory port was ~90 % busy in the single-CTA kernel: LDS/STS 41 %, TMA + bulk writes 23 %, tensor-core operand reads 27 %).
 template <int PRO, int EPI, int DWM, bool PAIR>
 __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_constant__ TmaArgs g) {
-  constexpr int DCLS = DWM == 1 ? 1 : (DWM == 2 ? 2 : 4);
-  constexpr bool THREE = DWM == 4;
+  constexpr bool TRAIN = (DWM & 8) != 0;  // training forward: PReLU on load, u_pre stored (see PwArgs::dw_in_slope)
+  constexpr int DCLS = (DWM & 7) == 1 ? 1 : ((DWM & 7) == 2 ? 2 : 4);
+  constexpr bool THREE = (DWM & 7) == 4;
   constexpr int PROD_WARPS = Roles<PRO>::PROD_WARPS, EGROUPS = Roles<PRO>::EGROUPS, FIRST_PROD = Roles<PRO>::FIRST_PROD;
   constexpr int CPW = RC / PROD_WARPS;  // channels of a raw stage per producer warp (1 or 2)
   extern __shared__ uint8_t smem_raw[];
@@ -260,8 +261,9 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
     // dependent LDS -> FMA -> cvt -> STS chains, not issue slots; four interleaved streams per warp give the scheduler the
     // instruction-level parallelism, and the fence / full-arrive / empty-wait are paid once per slab instead of per 16 channels)
     const int pw = warp - FIRST_PROD;
-    float pslope = 0.f;
+    float pslope = 0.f, in_slope = 1.f;
     if (PRO == PRO_PRELU || PRO == PRO_DW) pslope = a.pro_slope[0];
+    if (TRAIN) in_slope = a.dw_in_slope[0];
     int s = 0, rs = 0;
     uint32_t ph = 0, rph = 0;
     const int dw_wd = TM + 2 * g.dw_pad;  // PRO_DW window mode: floats per channel row of a raw stage
@@ -309,14 +311,25 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
               const int c = ks * KS + sub * RC + cl;
               const uint32_t qa = rb_s + 4u * (uint32_t)((THREE ? cl * TM : cl * dw_wd) + lane * 4);
               const uint32_t pa = rb_s + 4u * (uint32_t)((THREE ? 3 * RC * TM : RC * dw_wd) + cl * 8);
-              const float4 q0 = lds128(qa), q1 = lds128(qa + step_b), q2 = lds128(qa + 2 * step_b);
+              float4 q0 = lds128(qa), q1 = lds128(qa + step_b), q2 = lds128(qa + 2 * step_b);
               const float4 p0 = lds128(pa), p1 = lds128(pa + 16);
+              if (TRAIN) {  // the stored tensor is the pre-activation W1 x + b1
+                q0.x = prelu_f(q0.x, in_slope); q0.y = prelu_f(q0.y, in_slope); q0.z = prelu_f(q0.z, in_slope); q0.w = prelu_f(q0.w, in_slope);
+                q1.x = prelu_f(q1.x, in_slope); q1.y = prelu_f(q1.y, in_slope); q1.z = prelu_f(q1.z, in_slope); q1.w = prelu_f(q1.w, in_slope);
+                q2.x = prelu_f(q2.x, in_slope); q2.y = prelu_f(q2.y, in_slope); q2.z = prelu_f(q2.z, in_slope); q2.w = prelu_f(q2.w, in_slope);
+              }
               // fold the operand scale into the (positively homogeneous) PReLU: scale taps and bias
               const float gsc = p0.x * mr1.y, gsh = p0.y - mr1.x * mr1.y * p0.x;
               const float w0 = p0.z * act_s, w1 = p0.w * act_s, w2 = p1.x * act_s, bd = p1.y * act_s;
               // channels past K (K % 32 != 0: the last slab's second half) are rows of the NEXT sample: boundary path, zeroed
-              if (dw_interior && c < a.K) v[sub][j] = dw_channel<DCLS, true>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, true, dls, dlss);
-              else v[sub][j] = dw_channel<DCLS, false>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, c < a.K, dls, dlss);
+              float4 upre;
+              if (dw_interior && c < a.K) v[sub][j] = dw_channel<DCLS, true, TRAIN>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, true, dls, dlss, &upre);
+              else v[sub][j] = dw_channel<DCLS, false, TRAIN>(q0, q1, q2, gsc, gsh, w0, w1, w2, bd, pslope, first, tstep, tbase, a.frames, c < a.K, dls, dlss, &upre);
+              if (TRAIN && nt == 0 && live && c < a.K) {  // the taps carry the operand scale: undo it (power of two, exact)
+                const float ia = 1.f / act_s;
+                *reinterpret_cast<float4*>(a.dw_u_pre_out + ((size_t)b * a.K + c) * a.pitch + tbase) =
+                    make_float4(upre.x * ia, upre.y * ia, upre.z * ia, upre.w * ia);
+              }
               dep += v[sub][j].x + (q0.x + q1.x) + (q2.x + p1.y);
             }
           } else {
@@ -741,7 +754,8 @@ int ctn_pw_tma_supported(const PwArgs& a, int pro, int epi) {
     const int n_tile = a.M >= 256 ? 256 : ((a.M + 15) / 16) * 16;
     if (!a.dec_w || a.Nb <= 0 || a.M % a.Nb != 0 || a.Nb % n_tile != 0 || a.Nb > 1024) return 0;  // whole n-tiles per source; basis fits smem
   }
-  if (a.pitch % TM != 0 || a.store_pre) return 0;
+  if (a.pitch % TM != 0) return 0;
+  if ((a.dw_in_slope != nullptr) != (a.dw_u_pre_out != nullptr)) return 0;
   if (pro == PRO_DW && (a.dw_pad_left != a.dw_dilation || a.dw_dilation < 1 || !a.dw_params ||
                         !(a.dw_dilation == 1 || a.dw_dilation == 2 || a.dw_dilation % 4 == 0)))
     return 0;
@@ -815,6 +829,11 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
     if (grid > 2 * cl_items) grid = 2 * cl_items;
   } else if (grid > g.num_items) grid = g.num_items;
   if (pro == PRO_DW && epi == EPI_RAW) {
+    if (a.dw_in_slope) {  // training forward
+      if (g.dw_three) return launch<PRO_DW, EPI_RAW, 8 | 4>(g, smem, grid, st);
+      if (a.dw_dilation >= 4) return launch<PRO_DW, EPI_RAW, 8 | 3>(g, smem, grid, st);
+      return a.dw_dilation == 2 ? launch<PRO_DW, EPI_RAW, 8 | 2>(g, smem, grid, st) : launch<PRO_DW, EPI_RAW, 8 | 1>(g, smem, grid, st);
+    }
     if (g.dw_three) return launch<PRO_DW, EPI_RAW, 4>(g, smem, grid, st);
     if (a.dw_dilation >= 4) return launch<PRO_DW, EPI_RAW, 3>(g, smem, grid, st);
     return a.dw_dilation == 2 ? launch<PRO_DW, EPI_RAW, 2>(g, smem, grid, st) : launch<PRO_DW, EPI_RAW, 1>(g, smem, grid, st);

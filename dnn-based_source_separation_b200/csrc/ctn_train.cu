@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <math.h>
+#include <stdlib.h>
 #include "ctn_internal.h"
 
 namespace {
@@ -689,6 +691,8 @@ struct TrainWs {
   float *sp, *dsp;          // (B, Sc, pitch)
   double* sums;             // (B, 2)
   size_t stats_bytes;
+  void* tcn_mem;            // fp16-piece mode: state of the fused TCN forward (ctn_tcn_train_fwd)
+  size_t tcn_bytes;
 };
 
 size_t max_wimg_bytes(const ctn_config_t* c) {
@@ -726,7 +730,13 @@ void carve_train(Carver& cv, const ctn_config_t* c, int B, int pitch, TrainWs* w
   ws->head.Wf = cv.take<float>((size_t)Bc * N);
   ws->head.v1 = cv.take<float>(Bc);
   ws->head.v2 = cv.take<float>(Bc);
-  ws->head.vb = nullptr;
+  ws->head.vb = cv.take<float>(Bc);
+  ws->tcn_mem = nullptr;
+  ws->tcn_bytes = 0;
+  if (c->math == CTN_MATH_F16X3 && c->sep_kernel == 3) {
+    ws->tcn_bytes = ctn_tcn_train_ws_bytes(c, B, pitch);
+    ws->tcn_mem = cv.take<char>(ws->tcn_bytes);
+  }
   ws->wimg = cv.take<float>(max_wimg_bytes(c) / sizeof(float));
   size_t wmax = (size_t)(Bc + Sc) * H;
   if ((size_t)S * N * Sc > wmax) wmax = (size_t)S * N * Sc;
@@ -884,7 +894,7 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
   CTN_TRY(ctn_encoder_fwd(x, p->enc_w, ws.w, B, T, pl, pr, N, c->kernel_size, c->stride, c->enc_relu, pitch, ws.stats0, stream));
   // head: x_0 = Wb gLN0(w) + bb (conv_tasnet.py:370-371), gLN0 folded into the contraction like the inference path
   {
-    CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws.head, 0, st));
+    CTN_TRY(ctn_fold_conv(p->bn_w, p->bn_b, p->norm0_g, p->norm0_b, Bc, N, ws.head, 0, st, sqrtf((float)N * (float)frames) * 1.0001f));
     PwArgs a;
     memset(&a, 0, sizeof(a));
     a.A = ws.w; a.W = ws.head.Wf; a.D = ws.x[0]; a.B = B; a.M = Bc; a.K = N; a.frames = frames; a.pitch = pitch;
@@ -902,7 +912,21 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
   const double nH = (double)H * (double)frames;
   // un-normalised operands (x_i, skip sum) without operand scales: tf32 pieces (8-bit exponent) in the fp16-piece mode
   const int fmath = c->math == CTN_MATH_F16X3 ? CTN_MATH_TF32X3 : c->math;
-  for (int i = 0; i < R * X; ++i) {
+  // fp16-piece mode: the TCN runs through the SAME fused TMA-fed kernels as inference (pw1 with the residual update fused,
+  // depthwise producer feeding the [out;skip] contraction), which additionally leave x_i, W1 x + b1 and the depthwise
+  // pre-activation behind for the backward -- 2 launches per block instead of 7, no u / gLN2(u) round trips
+  bool fused = false;
+  const float* mask_scale = nullptr;
+  static const char* env_unf = getenv("CTN_TRAIN_UNFUSED");
+  if (ws.tcn_mem && !(env_unf && atoi(env_unf))) {
+    TcnTrainHooks hk{ws.x.data(), ws.hpre.data(), ws.upre.data()};
+    const int rc = ctn_tcn_train_fwd(c, p->blocks, ws.tcn_mem, ws.tcn_bytes, &hk, ws.stats, ws.skip, ws.head.vb, Bc, p->prelu_out, &mask_scale,
+                                     B, frames, pitch, st);
+    if (rc == CTN_OK) fused = true;
+    else if (rc != CTN_EUNSUPPORTED) return rc;
+    else if ((e = cudaMemsetAsync(ws.stats, 0, ws.stats_bytes, st)) != cudaSuccess) return (int)e;  // shapes outside the fused envelope
+  }
+  for (int i = 0; i < (fused ? 0 : R * X); ++i) {
     const ctn_block_params_t& q = p->blocks[i];
     const bool has_out = q.out_w != nullptr;
     if (!has_out && i != R * X - 1) return CTN_EINVAL;
@@ -951,9 +975,11 @@ extern "C" int ctn_convtasnet_fwd_train(const ctn_config_t* c, const ctn_params_
     if (c->math == CTN_MATH_FP32) {
       CTN_TRY(ctn_pw_simt(a, PRO_PRELU, EPI_MASK, st));
     } else {
-      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, fmath, ws.wimg, st));
+      const int mmath = fused ? CTN_MATH_F16X3 : fmath;  // the fused forward also produced the operand scale of PReLU(skip sum)
+      if (fused) a.act_scale = mask_scale;
+      CTN_TRY(ctn_umma_build_wimg(p->mask_w, S * N, Sc, mmath, ws.wimg, st));
       a.wimg = ws.wimg;
-      CTN_TRY(ctn_pw_umma(a, PRO_PRELU, EPI_MASK, fmath, st));
+      CTN_TRY(ctn_pw_umma(a, PRO_PRELU, EPI_MASK, mmath, st));
     }
   }
   CTN_TRY(ctn_decoder_fwd(ws.what, p->dec_w, out, B * S, N, frames, pitch, c->kernel_size, c->stride, pl, T, stream));
