@@ -481,7 +481,7 @@ static int check_model_cfg(const ctn_config_t* c) {
   CTN_TRY(check_tcn_cfg(c));
   if (c->n_basis <= 0 || c->kernel_size <= 0 || c->stride <= 0 || c->n_sources <= 0) return CTN_EINVAL;
   if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
-  if (c->mask_softmax) return CTN_EUNSUPPORTED;
+  if (c->mask_softmax && c->mask_softmax != 1) return CTN_EINVAL;
   return CTN_OK;
 }
 
@@ -557,6 +557,14 @@ static int run_separator(const ctn_config_t* c, const ctn_params_t* p, ModelWs* 
   if (c->math == CTN_MATH_F16X3 && !c->causal) a.act_scale = ws->tcn.scales + 2 * c->num_blocks * c->num_layers;
   // causal models: no operand scales (un-fused pipeline) -> the mask contraction stays on the tf32 pieces
   const int mask_math = (c->causal && c->math == CTN_MATH_F16X3) ? CTN_MATH_TF32X3 : c->math;
+  if (c->mask_softmax) {
+    // nn.Softmax(dim=1) over ALL S*N mask channels (conv_tasnet.py:345-357 quirk): logits first, then one normalising pass
+    StageTimer tm(CTN_ST_MASK, st);
+    a.mask_logits = 1;
+    a.mask_out = nullptr;
+    CTN_TRY(pw_dispatch(a, PRO_PRELU, EPI_MASK, mask_math, st));
+    return ctn_softmax_mask(ws->what, ws->w, mask_out, B, S * N, N, frames, pitch, st);
+  }
   if (dec && !mask_out && mask_math == CTN_MATH_F16X3 && c->kernel_size == 16 && c->stride == 8) {
     PwArgs f = a;
     f.D = dec->out; f.dec_w = p->dec_w; f.dec_crop_left = dec->crop_left; f.dec_T_out = dec->T_out;

@@ -47,6 +47,7 @@ struct PwArgs {
   const float* wenc;       // EPI_MASK: encoder output (B, Nb, pitch)
   int Nb;                  // EPI_MASK: n_basis
   float* mask_out;         // EPI_MASK: optional raw mask output (B, M, pitch)
+  int mask_logits;         // EPI_MASK: 1 = store the LOGITS (W A + bias) to D, no sigmoid, no w product (softmax masks take a second pass)
   // EPI_MASKDEC (TMA-fed kernel): mask 1x1 + sigmoid + w*mask + transposed-conv decoder + crop in one epilogue; w_hat is never
   // materialised.  D = estimates (B, M/Nb, dec_T_out) contiguous, ZERO-initialised by the caller (tile seams are red.add'ed)
   const float* dec_w;      // (Nb, 1, 16) decoder basis, kernel 16 / stride 8
@@ -125,6 +126,10 @@ size_t ctn_tcn_train_ws_bytes(const ctn_config_t* c, int B, int pitch);
 int ctn_tcn_train_fwd(const ctn_config_t* c, const ctn_block_params_t* blocks, void* mem, size_t mem_bytes, const TcnTrainHooks* hooks,
                       double* stats, float* skip, const float* x0_bound, int x0_n, const float* mask_slope, const float** mask_scale,
                       int B, int frames, int pitch, cudaStream_t st);
+
+// mask_nonlinear = 'softmax' (src/models/conv_tasnet.py:345-357, 375-376: nn.Softmax(dim=1) over ALL S*N channels before the view):
+// in place on the logits (B, M, pitch): what = softmax_m(logits) * w[m % Nb]; mask_out (nullable) receives the softmax itself
+int ctn_softmax_mask(float* logits_what, const float* wenc, float* mask_out, int B, int M, int Nb, int frames, int pitch, cudaStream_t st);
 
 // depthwise stage: u = PReLU(dwconv(gLN1(h))) (+ stats2), all (B,H,pitch)
 int ctn_dw_fwd(const float* h, float* u, const float* norm_g, const float* norm_b, const float* dw_w, const float* dw_b,

@@ -258,9 +258,14 @@ __global__ void __launch_bounds__(256) k_pw_simt(const PwArgs a) {
       if (EPI == EPI_HEAD) v = mr.y * v + (a.v1[m] - mr.x * mr.y * a.v2[m]);
       if (EPI == EPI_H) v = prelu_f(v + a.bias[m], eslope);
       if (EPI == EPI_MASK) {
-        v = 1.f / (1.f + expf(-(v + a.bias[m])));
-        mk[j] = v;
-        v *= wv[j];
+        if (a.mask_logits) {
+          v += a.bias[m];
+          mk[j] = v;
+        } else {
+          v = 1.f / (1.f + expf(-(v + a.bias[m])));
+          mk[j] = v;
+          v *= wv[j];
+        }
       }
       if (t + j >= a.frames) { v = 0.f; mk[j] = 0.f; }
       o[j] = v;
@@ -293,6 +298,35 @@ int ctn_pw_simt(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   PW_LAUNCH(PRO_PRELU, EPI_MASK)
 #undef PW_LAUNCH
   return CTN_EUNSUPPORTED;
+}
+
+// softmax over ALL M = S*N mask channels per frame, then * w: thread = one frame (coalesced along t), three passes over the channels
+__global__ void __launch_bounds__(128) k_softmax_mask(float* __restrict__ x, const float* __restrict__ wenc, float* __restrict__ mask_out, int M,
+                                                      int Nb, int frames, int pitch) {
+  const int b = blockIdx.y, t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= pitch) return;
+  float* col = x + (size_t)b * M * pitch + t;
+  if (t >= frames) {
+    for (int m = 0; m < M; ++m) { col[(size_t)m * pitch] = 0.f; if (mask_out) mask_out[((size_t)b * M + m) * pitch + t] = 0.f; }
+    return;
+  }
+  float mx = -INFINITY;
+  for (int m = 0; m < M; ++m) mx = fmaxf(mx, col[(size_t)m * pitch]);
+  float sum = 0.f;
+  for (int m = 0; m < M; ++m) sum += expf(col[(size_t)m * pitch] - mx);
+  const float inv = 1.f / sum;
+  const float* wc = wenc + (size_t)b * Nb * pitch + t;
+  for (int m = 0; m < M; ++m) {
+    const float p = expf(col[(size_t)m * pitch] - mx) * inv;
+    if (mask_out) mask_out[((size_t)b * M + m) * pitch + t] = p;
+    col[(size_t)m * pitch] = p * wc[(size_t)(m % Nb) * pitch];
+  }
+}
+int ctn_softmax_mask(float* logits_what, const float* wenc, float* mask_out, int B, int M, int Nb, int frames, int pitch, cudaStream_t st) {
+  k_softmax_mask<<<dim3((pitch + 127) / 128, B), 128, 0, st>>>(logits_what, wenc, mask_out, M, Nb, frames, pitch);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

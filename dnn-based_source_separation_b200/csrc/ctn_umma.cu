@@ -546,8 +546,14 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_umma(const UmmaAr
               if (full) { ls += act; lss = fmaf(act, act, lss); }  // gLN statistics are always those of PReLU(.)
             }
             if (EPI == EPI_MASK) {
-              mk[j] = __fdividef(1.f, 1.f + __expf(-(F16 ? fmaf(v, osc, pvv[jj]) : v + pvv[jj])));
-              v = mk[j] * wv[j];
+              const float logit = F16 ? fmaf(v, osc, pvv[jj]) : v + pvv[jj];
+              if (a.mask_logits) {  // softmax masks: the normalisation over all S*N channels is a second pass (ctn_softmax_mask)
+                mk[j] = logit;
+                v = logit;
+              } else {
+                mk[j] = __fdividef(1.f, 1.f + __expf(-logit));
+                v = mk[j] * wv[j];
+              }
             }
             o[j] = v;
           }

@@ -56,7 +56,7 @@ class Separator(nn.Module):
         if mask_nonlinear == 'sigmoid':
             self.mask_softmax = False
         elif mask_nonlinear == 'softmax':
-            raise NotImplementedError("mask_nonlinear='softmax' is outside the sm_100a kernel envelope")
+            self.mask_softmax = True   # nn.Softmax(dim=1) over ALL n_sources*num_features channels (conv_tasnet.py:345-357); inference only
         else:
             raise ValueError("Cannot support {}".format(mask_nonlinear))
         self.math = None
@@ -65,7 +65,7 @@ class Separator(nn.Module):
     def native_config(self, kernel_size=1, stride=1, enc_relu=False):
         mode = self.math if self.math is not None else (DEFAULT_MATH if DEFAULT_MATH is not None else _tdcn.DEFAULT_MATH)
         cfg = self.tdcn.native_config(n_basis=self.num_features, kernel_size=kernel_size, stride=stride,
-                                      n_sources=self.n_sources, enc_relu=int(enc_relu), mask_softmax=0)
+                                      n_sources=self.n_sources, enc_relu=int(enc_relu), mask_softmax=int(self.mask_softmax))
         cfg.math = resolve_math(mode)
         cfg.eps = float(self.eps)
         return cfg

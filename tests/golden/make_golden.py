@@ -275,6 +275,11 @@ def module_cases():
 def main():
     paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
                  sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
+    if len(sys.argv) > 1 and sys.argv[1] == "softmax":
+        tiny = dict(n_basis=16, kernel_size=4, sep_hidden_channels=16, sep_bottleneck_channels=8, sep_skip_channels=8,
+                    sep_num_blocks=2, sep_num_layers=3)
+        model_case("tiny_softmax", O.OracleConfig(**tiny, causal=False, mask_nonlinear="softmax"), batch=2, T=203, wseed=14, xseed=24)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ckpt":
         checkpoint_case()
         return
@@ -288,6 +293,7 @@ def main():
                 sep_num_blocks=2, sep_num_layers=3)
     model_case("tiny_gln", O.OracleConfig(**tiny, causal=False), batch=2, T=203, wseed=11, xseed=21)
     model_case("tiny_cln", O.OracleConfig(**tiny, causal=True), batch=2, T=203, wseed=12, xseed=22)
+    model_case("tiny_softmax", O.OracleConfig(**tiny, causal=False, mask_nonlinear="softmax"), batch=2, T=203, wseed=14, xseed=24)
     small = dict(n_basis=64, kernel_size=16, sep_hidden_channels=96, sep_bottleneck_channels=32, sep_skip_channels=48,
                  sep_num_blocks=2, sep_num_layers=5)
     model_case("small_relu_3spk", O.OracleConfig(**small, causal=False, n_sources=3, enc_nonlinear="relu"),

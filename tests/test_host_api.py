@@ -74,8 +74,9 @@ def test_workspace_bytes_and_envelope():
     # per-sample activations at pitch 4096: w(512)+what(1024)+x(128)+skip(128)+h(512)+u(512) rows + 24 blocks x r(256)
     rows = 512 + 1024 + 128 + 128 + 512 + 512 + 24 * 256
     assert b32 >= 32 * rows * 4096 * 4
-    cb = _cfg(mask_softmax=1)
-    assert N.ctn_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
+    cb = _cfg(mask_softmax=1)   # softmax masks: forward built (logits + one normalising pass), training path not
+    assert N.ctn_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == 0 and need.value > 0
+    assert N.ctn_train_workspace_bytes(C.byref(cb), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
     cc = _cfg(causal=1)   # cLN models: forward built (un-fused pipeline), training path not
     assert N.ctn_workspace_bytes(C.byref(cc), 1, 32000, C.byref(need)) == 0 and need.value > 0
     assert N.ctn_train_workspace_bytes(C.byref(cc), 1, 32000, C.byref(need)) == N.CTN_EUNSUPPORTED
@@ -160,8 +161,7 @@ def test_constructor_envelope_errors():
                    enc_onesided=True, enc_return_complex=True)
     with pytest.raises(NotImplementedError):
         ConvTasNet(64, 16, enc_basis='trainable', dec_basis='pinv')
-    with pytest.raises(NotImplementedError):
-        _paper(mask_nonlinear='softmax')
+    assert _paper(mask_nonlinear='softmax').separator.mask_softmax is True
     with pytest.raises(ValueError):
         _paper(mask_nonlinear='tanh')
     with pytest.raises(NotImplementedError):

@@ -15,7 +15,7 @@ def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
 
 
-@pytest.mark.parametrize("name", ["tiny_gln", "tiny_cln", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
+@pytest.mark.parametrize("name", ["tiny_gln", "tiny_cln", "tiny_softmax", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
 def test_model_cases(golden_dir, name):
     rec = _load(golden_dir, name)
     cfg = O.OracleConfig(**rec["cfg"])

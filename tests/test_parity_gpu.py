@@ -169,7 +169,7 @@ def test_causal_model_vs_oracle(mode):
 # whole model vs golden (reference outputs)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("name", ["tiny_gln", "tiny_cln", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
+@pytest.mark.parametrize("name", ["tiny_gln", "tiny_cln", "tiny_softmax", "small_relu_3spk", "paper_2spk", "paper_3spk_short"])
 def test_model_golden(golden_dir, name, mode):
     rec = _load(golden_dir, name)
     cfg = O.OracleConfig(**rec["cfg"])
@@ -566,3 +566,28 @@ def test_sisdr_autograd_matches_oracle():
     loss.backward()
     torch.testing.assert_close(loss.detach().cpu(), O.neg_sisdr(est, tgt), rtol=0, atol=1e-4)
     torch.testing.assert_close(e.grad.cpu(), e_ref.grad, rtol=1e-4, atol=1e-5 * float(e_ref.grad.abs().max()))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_softmax_mask_vs_oracle(mode):
+    """mask_nonlinear='softmax': nn.Softmax(dim=1) over ALL S*N mask channels before the view (conv_tasnet.py:345-357 quirk), N = 512 so
+    that the 1024-channel reduction spans several n-tiles; Separator.forward returns the mask itself."""
+    cfg = O.OracleConfig(n_basis=512, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=1, sep_num_layers=3, causal=False, n_sources=2, mask_nonlinear="softmax")
+    sd = O.synth_state_dict(cfg, seed=71)
+    model = build_model(cfg, sd, math=mode)
+    mixture, _ = O.synth_batch(2, 2, 2000, seed=72)
+    with torch.no_grad():
+        out, latent = model.extract_latent(mixture.cuda())
+        fwd = model(mixture.cuda())
+        ref, ref_lat = O.conv_tasnet_fwd(mixture, sd, cfg)
+        w = O.encoder_fwd(mixture, sd["encoder.conv1d.weight"], cfg.stride)
+        model.separator.math = mode
+        mask = model.separator(w.cuda())
+        ref_mask = O.separator_fwd(w, sd, cfg)
+    torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(fwd.cpu(), ref, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), ref_lat, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(mask.cpu(), ref_mask, rtol=RTOL, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        model.train()(mixture.cuda())
