@@ -778,9 +778,11 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   g.oscale = reinterpret_cast<const float*>(g.wimg + (size_t)g.n_tiles * g.k_slabs * 2 * g.n_tile * KS * sizeof(__half));
   g.act_scale = a.act_scale;
   g.dwp = a.dw_params;
-  // CTA pairs (default when the shape allows; CTN_TMA_PAIR=0 disables): N/2 rows of W per CTA must be a multiple of 16
+  // CTA pairs (opt-in with CTN_TMA_PAIR=1; N/2 rows of W per CTA must be a multiple of 16).  Parity-green, but measured SLOWER on cfg2
+  // (step 7.52 vs 6.62 ms, pw2 3.61 vs 3.06 ms, gpurun call L): the per-slab relay of the peer's "stage full" to the leader and the
+  // lock-step of two CTAs cost more than the halved weight traffic buys -- the single-CTA form stays the default.
   static const char* env_pair = getenv("CTN_TMA_PAIR");
-  g.pair = (env_pair ? atoi(env_pair) != 0 : 1) && g.n_tile % 32 == 0 && g.n_tile >= 64 && a.B * g.t_tiles >= 2 && num_sms() >= 2;
+  g.pair = (env_pair ? atoi(env_pair) != 0 : 0) && g.n_tile % 32 == 0 && g.n_tile >= 64 && a.B * g.t_tiles >= 2 && num_sms() >= 2;
   g.idesc = ptx::make_idesc_f16(g.pair ? 2 * TM : TM, g.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
   static const char* env_dbg = getenv("CTN_UMMA_DBG");
   g.dbg = env_dbg ? (uint32_t)atoi(env_dbg) : 0u;
