@@ -51,6 +51,7 @@ struct TmaArgs {
   int n_tile, n_tiles, k_slabs, t_tiles, num_items;
   int op_stages, raw_stages;
   uint32_t op_stage_bytes, raw_stage_bytes, raw_tx_bytes, w_bytes, hdr_bytes, res_tab_off, idesc;
+  int reverse;   // walk the (sample, time tile) list backwards
   int pair;      // 1: clusters of 2 CTAs, cta_group::2 MMAs (each CTA stages half of every weight slab)
   int dw_three;  // PRO_DW: 0 = one window box of 128 + 2*dw_pad frames, 1 = three boxes of 128 frames at t-d, t, t+d
   int dw_pad;    // window mode: halo frames on each side (dilation rounded up to a multiple of 4)
@@ -185,10 +186,13 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
       nt2 = J % g.n_tiles;
       Lg = J / g.n_tiles;
     }
-    const int L = Lg * CL + crank;
+    int L = Lg * CL + crank;
+    const bool in_range = L < tiles_total;
+    // reverse walk (pw2): the previous kernel (pw1, forward) wrote the LAST samples' h most recently -- start with what is still in L2
+    if (g.reverse && in_range) L = tiles_total - 1 - L;
     tt2 = L % g.t_tiles;
     b2 = L / g.t_tiles;
-    return L < tiles_total;
+    return in_range;
   };
   if (EPI == EPI_MASKDEC) {
     // decoder basis (Nb x 16 taps) resident in shared memory behind the raw ring, then the [2][128][16] combine buffer
@@ -789,6 +793,8 @@ int ctn_pw_tma(const PwArgs& a, int pro, int epi, cudaStream_t st) {
   // header: barriers + epilogue parameters (HDR_FIXED), the output scale table, then (PRO_RES) the folded bias vectors v1, v2 of the
   // previous block for all K channels (two global loads per channel and stage sat on the producers' critical path otherwise)
   g.res_tab_off = (uint32_t)(HDR_FIXED + g.n_tiles * g.n_tile * 4);
+  static const char* env_rev = getenv("CTN_TMA_REVERSE");
+  g.reverse = (pro == PRO_DW) && (env_rev ? atoi(env_rev) != 0 : 1);
   g.hdr_bytes = (uint32_t)((g.res_tab_off + (pro == PRO_RES ? 2 * g.k_slabs * KS * 4 : 0) + 1023) & ~1023u);
   g.op_stage_bytes = 2u * A_BYTES + (g.pair ? 1u : 2u) * g.w_bytes;
   uint32_t raw_data = 0;

@@ -11,7 +11,7 @@ from ctn_b200.criterion.pit import PIT1d
 from ctn_b200.criterion.sdr import NegSISDR
 from test_parity_gpu import build_model
 
-modes = sys.argv[1:] or ["tf32x3", "fp32"]
+modes = sys.argv[1:] or ["f16x3", "tf32x3", "fp32"]
 for causal in (False, True):
     cfg = O.OracleConfig(n_basis=32, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
                          sep_num_blocks=2, sep_num_layers=2, causal=causal, n_sources=2)
@@ -31,3 +31,24 @@ for causal in (False, True):
             loss.backward()
             torch.cuda.synchronize()
             print("bwd", mode, float(loss), float(sum(p.grad.abs().sum() for p in model.parameters())), flush=True)
+
+# round 2: fused mask + decoder epilogue (N = 512, crop offset != 0 and an unaligned T), block-level forward, DPRNN glue
+cfg = O.OracleConfig(n_basis=512, kernel_size=16, sep_hidden_channels=32, sep_bottleneck_channels=16, sep_skip_channels=16,
+                     sep_num_blocks=1, sep_num_layers=2, causal=False, n_sources=2)
+model = build_model(cfg, O.synth_state_dict(cfg, seed=3), math="f16x3")
+mixture, _ = O.synth_batch(2, 2, 1031, seed=4)
+with torch.no_grad():
+    out = model(mixture.cuda())
+torch.cuda.synchronize()
+print("maskdec", float(out.abs().sum()), flush=True)
+import dprnn_oracle as DO
+from ctn_b200.models.dprnn_tasnet import DPRNNTasNet
+dc = DO.DPRNNConfig(n_basis=16, kernel_size=4, sep_hidden_channels=12, sep_bottleneck_channels=8, sep_chunk_size=10, sep_hop_size=5, sep_num_blocks=1)
+dm = DPRNNTasNet(16, 4, enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None, sep_hidden_channels=12, sep_bottleneck_channels=8,
+                 sep_chunk_size=10, sep_hop_size=5, sep_num_blocks=1, causal=False)
+dm.load_state_dict(DO.synth_state_dict(dc, seed=5))
+dm = dm.cuda().eval()
+with torch.no_grad():
+    o = dm(torch.randn(2, 1, 203).cuda())
+torch.cuda.synchronize()
+print("dprnn", float(o.abs().sum()), flush=True)
