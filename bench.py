@@ -259,7 +259,7 @@ def train_leg(args, torch, N, D, dev, rank, world, S, B, steps, warmup):
                         "fwd_train + PIT + backward + all-reduce + clip(5.0) + Adam(1e-3)", "global_batch": world * B,
             "ms_per_step": ms / steps, "allreduce_ms": ar_ms, "allreduce_elems": nel, "audio_s_per_s": world * B * args.seconds * steps / (ms * 1e-3),
             "steps": steps, "gpu_launches_per_step": launches, "optimizer": "native flat clip + Adam (ctn_clip_adam_step)",
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "last_loss": float(loss)}
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "last_loss": float(loss.detach())}
 
 
 def ddp_check(torch, D, dev, rank, world):
