@@ -49,6 +49,6 @@ dm = DPRNNTasNet(16, 4, enc_basis="trainable", dec_basis="trainable", enc_nonlin
 dm.load_state_dict(DO.synth_state_dict(dc, seed=5))
 dm = dm.cuda().eval()
 with torch.no_grad():
-    o = dm(torch.randn(2, 1, 203).cuda())
+    o = dm(torch.randn(2, 1, 203, generator=torch.Generator().manual_seed(6)).cuda())
 torch.cuda.synchronize()
 print("dprnn", float(o.abs().sum()), flush=True)
