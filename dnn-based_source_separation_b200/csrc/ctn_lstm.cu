@@ -1,0 +1,673 @@
+// Bidirectional LSTM recurrence + output projection of a dual-path block (BASELINE cfg4) on tcgen05.
+// Reference: src/models/dprnn.py:82-90 / 134-142 (x -> nn.LSTM(bidirectional, batch_first) -> nn.Linear(2H, F)); the recurrence
+// itself is torch.nn.LSTM: gates (i, f, g, o) = W_ih x_t + b_ih + W_hh h_{t-1} + b_hh, c_t = f c_{t-1} + i g, h_t = o tanh(c_t).
+//
+// One CTA = 128 sequences (TMEM lanes) of ONE direction, all T steps.  Per step the pre-activations are ONE contraction
+//   [x_t | h_{t-1}] (128 x (F + H))  x  [W_ih | W_hh]^T ((F + H) x 4H)
+// run as "3xFP16" (hi/lo fp16 pieces, fp32 accumulate in TMEM): gate columns are reordered unit-major (4 gates of a hidden unit
+// adjacent) and cut into chunks of 32 units = 128 columns, so that the epilogue of chunk c (sigmoid / tanh, cell update, h_t) runs
+// while the tensor core works on chunk c + 1.  Operand placement:
+//   * h_{t-1}: in TENSOR MEMORY (tcgen05.mma "ts" form).  The epilogue thread that owns a sequence (= TMEM lane) writes h_t's
+//     fp16 hi / lo pieces straight into the A-operand columns with tcgen05.st: h never touches shared or global memory on its
+//     way back into the recurrence.  Two h buffers (h_t is produced while later chunks still read h_{t-1}).
+//   * x_t: shared memory (K-major SWIZZLE_64B), written by 4 producer warps one step ahead of the recurrence.
+//   * weights: pre-split / pre-swizzled 16 KB stage images ([128 columns x 32 k] hi + lo), streamed from L2 through a ring of
+//     shared-memory stages by bulk async copies (the whole [W_ih | W_hh | W_fc] set is 442 KB -- more than an SM holds).
+//   * the 2H -> F projection of the block (nn.Linear after the LSTM) rides along: one more chunk per step, h_{t-1} (still in
+//     TMEM) x W_fc[:, dir*H:(dir+1)*H]^T, so the (NSEQ, T, 2H) LSTM output is never materialised; each direction stores its
+//     partial projection (NSEQ, T, F) and the gLN + residual kernel adds the two and the bias.
+// TMEM columns: [0,256) two 128-column accumulators, [256,512) two h buffers (hi at +0, lo at +64 of each).
+// Warp roles: 0-7 epilogue (warp & 3 = lane quarter, warp >> 2 = column half), 8 TMEM alloc + MMA issuer, 9 weight loader,
+// 10-13 x producers.
+#include "ctn_internal.h"
+#include "ctn_umma_ptx.cuh"
+
+namespace {
+
+constexpr int LM = 128;               // sequences per CTA
+constexpr int STAGE_BYTES = 16384;    // one weight stage: [hi 128 x 64 B][lo 128 x 64 B]
+constexpr int MAX_ST = 12;
+constexpr int LSTM_THREADS = 448;
+constexpr int HDR_BYTES = 1024;
+
+struct LstmScales {                   // one per direction, written by k_lstm_scales
+  float x_mul;                        // x operand = x * x_mul            (|.| < 2^14)
+  float inv_g;                        // pre-activation = acc * inv_g + bias
+  float inv_p;                        // projection = acc * inv_p
+  float w_ih_mul, w_hh_mul, w_p_mul;  // weight images = W * mul          (|.| < 2^14)
+  float pad[2];
+};
+
+struct LstmHdr {
+  uint64_t bfull[MAX_ST], bempty[MAX_ST];
+  uint64_t accfull[2], accempty[2];
+  uint64_t hfull[2];
+  uint64_t xfull, xempty;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(LstmHdr) <= HDR_BYTES, "header");
+
+struct LstmArgs {
+  const float* z;        // (NSEQ, T, F)
+  float* P;              // (2, NSEQ, T, Fo) or null
+  float* hout;           // (NSEQ, T, 2H) or null
+  const uint8_t* img;    // [2][n_imgs][STAGE_BYTES]
+  const float* bias;     // [2][4H], chunk-column order
+  const LstmScales* sc;  // [2]
+  int NSEQ, T, Fo, n_imgs, n_st, has_proj;
+};
+
+__device__ __forceinline__ float ex2f_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf_(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float clampf_(float v, float m) { return fminf(fmaxf(v, -m), m); }
+
+// one LSTM cell update from the four pre-activations.  sigmoid(a) = 1 / (1 + e^-a), tanh(a) = (1 - e^-2a) / (1 + e^-2a); the
+// products i*g and o*tanh(c) share one reciprocal each: 5 ex2 + 3 rcp per unit.  Arguments are clamped where the function has
+// already saturated in fp32 (|a| >= 30 for sigmoid, >= 15 for tanh) so that no intermediate overflows.
+__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float& c, float& h) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float Ei = ex2f_(-L2E * clampf_(ai, 30.f)), Ef = ex2f_(-L2E * clampf_(af, 30.f));
+  const float Eg = ex2f_(-2.f * L2E * clampf_(ag, 15.f)), Eo = ex2f_(-L2E * clampf_(ao, 30.f));
+  const float ig = (1.f - Eg) * rcpf_((1.f + Ei) * (1.f + Eg));
+  c = fmaf(rcpf_(1.f + Ef), c, ig);
+  const float Ec = ex2f_(-2.f * L2E * clampf_(c, 15.f));
+  h = (1.f - Ec) * rcpf_((1.f + Eo) * (1.f + Ec));
+}
+
+// NCH = H / 32 gate chunks, KSX = F / 32 input slabs
+template <int NCH, int KSX>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
+  constexpr int H = 32 * NCH, F = 32 * KSX, KSH = NCH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  LstmHdr* hdr = reinterpret_cast<LstmHdr*>(smem);
+  float* s_bias = reinterpret_cast<float*>(smem + HDR_BYTES);            // 4H floats (<= 2 KB)
+  constexpr uint32_t XS_OFF = HDR_BYTES + 2048;                          // x operand: [hi KSX slabs][lo KSX slabs] of 8 KB
+  constexpr uint32_t RING_OFF = XS_OFF + 2 * KSX * 8192;
+  const uint32_t xs0 = base + XS_OFF, ring0 = base + RING_OFF;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dir = blockIdx.y, seq0 = blockIdx.x * LM;
+  const int T = g.T;
+  const bool proj = g.has_proj != 0;
+  const LstmScales sc = g.sc[dir];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.n_st; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->bfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->bempty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->accfull[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->accempty[i]), 8);
+      ptx::mbar_init(ptx::smem_u32(&hdr->hfull[i]), 8 * NCH);
+    }
+    ptx::mbar_init(ptx::smem_u32(&hdr->xfull), 4);
+    ptx::mbar_init(ptx::smem_u32(&hdr->xempty), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) s_bias[i] = __ldg(g.bias + (size_t)dir * 4 * H + i);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = hdr->tmem_base;
+  const uint32_t tm_h0 = tmem + 256u;  // h buffer b: tm_h0 + b * 128 (hi), + 64 (lo)
+  if (warp < 8) {
+    // h_{-1} = 0 lives in buffer 1: every epilogue warp clears its lane quarter / column half
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    for (int cc = 0; cc < 64; cc += 8) ptx::tmem_st8(tm_h0 + 128u + lane_off + (uint32_t)((warp >> 2) * 64 + cc), zero);
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  if (warp == 9) {
+    // ===================================== WEIGHT LOADER ====================================================
+    if (ptx::elect_one()) {
+      const uint8_t* img = g.img + (size_t)dir * g.n_imgs * STAGE_BYTES;
+      int s = 0;
+      uint32_t ph = 0;
+      auto load = [&](int idx, uint32_t bytes) {
+        ptx::mbar_wait(ptx::smem_u32(&hdr->bempty[s]), ph ^ 1u);
+        const uint32_t fb = ptx::smem_u32(&hdr->bfull[s]);
+        ptx::mbar_arrive_expect_tx(fb, bytes);
+        ptx::bulk_g2s(ring0 + (uint32_t)s * STAGE_BYTES, img + (size_t)idx * STAGE_BYTES, bytes, fb);
+        if (++s == g.n_st) { s = 0; ph ^= 1u; }
+      };
+      for (int t = 0; t <= T; ++t) {
+        if (t < T)
+          for (int i = 0; i < NCH * (KSX + KSH); ++i) load(i, STAGE_BYTES);
+        if (proj && t >= 1)
+          for (int k = 0; k < KSH; ++k) load(NCH * (KSX + KSH) + k, (uint32_t)g.Fo * 128u);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===================================== MMA ISSUER =======================================================
+    const bool leader = ptx::elect_one();
+    const uint64_t d_t = ptx::make_smem_desc(0, 16u, 512u, 4u);  // K-major SWIZZLE_64B rows of 32 k (x operand and weights)
+    const uint32_t idesc_g = ptx::make_idesc_f16(LM, 128, 0, 0), idesc_p = ptx::make_idesc_f16(LM, g.Fo, 0, 0);
+    int s = 0, gidx = 0;
+    uint32_t ph = 0;
+    for (int t = 0; t <= T; ++t) {
+      const uint32_t h_prev = tm_h0 + (uint32_t)((t + 1) & 1) * 128u;  // buffer holding h_{t-1}
+      if (t < T) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int slot = gidx & 1;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+          if (c == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xfull), (uint32_t)t & 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+#pragma unroll 1
+          for (int k = 0; k < KSX; ++k) {
+            ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+            ptx::tc_fence_after();
+            if (leader) {
+              const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + (8192u >> 4);
+              const uint32_t a_hi = (xs0 + (uint32_t)k * 8192u) >> 4, a_lo = a_hi + ((uint32_t)KSX * 8192u >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_hi + kk * 2), d_t | (uint64_t)(w_hi + kk * 2), idesc_g, (k | kk) ? 1u : 0u);
+                ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_lo + kk * 2), d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
+                ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_hi + kk * 2), d_t | (uint64_t)(w_lo + kk * 2), idesc_g, 1u);
+              }
+              ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+              if (c == NCH - 1 && k == KSX - 1) ptx::mma_commit(ptx::smem_u32(&hdr->xempty));  // x_t has been consumed
+            }
+            __syncwarp();
+            if (++s == g.n_st) { s = 0; ph ^= 1u; }
+          }
+          if (c == 0 && t > 0) {
+            ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
+            ptx::tc_fence_after();
+          }
+#pragma unroll 1
+          for (int k = 0; k < KSH; ++k) {
+            ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+            ptx::tc_fence_after();
+            if (leader) {
+              const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + (8192u >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t a_hi = h_prev + (uint32_t)(k * 2 + kk) * 8u, a_lo = a_hi + 64u;
+                ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
+                ptx::mma_f16_ts(d_tmem, a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
+                ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc_g, 1u);
+              }
+              ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+              if (k == KSH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+            }
+            __syncwarp();
+            if (++s == g.n_st) { s = 0; ph ^= 1u; }
+          }
+          ++gidx;
+        }
+      }
+      if (proj && t >= 1) {
+        const int slot = gidx & 1;
+        ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+        if (t == T) ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+        const uint32_t lo_off = ((uint32_t)g.Fo * 64u) >> 4;
+#pragma unroll 1
+        for (int k = 0; k < KSH; ++k) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+          ptx::tc_fence_after();
+          if (leader) {
+            const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + lo_off;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t a_hi = h_prev + (uint32_t)(k * 2 + kk) * 8u, a_lo = a_hi + 64u;
+              ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc_p, (k | kk) ? 1u : 0u);
+              ptx::mma_f16_ts(d_tmem, a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc_p, 1u);
+              ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc_p, 1u);
+            }
+            ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+            if (k == KSH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+          }
+          __syncwarp();
+          if (++s == g.n_st) { s = 0; ph ^= 1u; }
+        }
+        ++gidx;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 10) {
+    // ===================================== x PRODUCERS ======================================================
+    // thread = one sequence: x_t (F floats, contiguous) -> scaled fp16 hi / lo pieces -> K-major SWIZZLE_64B slabs
+    const int r = (warp - 10) * 32 + lane, seq = seq0 + r;
+    const bool valid = seq < g.NSEQ;
+    const float4* zrow = reinterpret_cast<const float4*>(g.z + (size_t)(valid ? seq : 0) * T * F);
+    uint8_t* xs = smem + XS_OFF;
+    const uint32_t row_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u, sw = (uint32_t)(r >> 1) & 3u;
+    float4 v[F / 4];
+    auto fetch = [&](int t) {
+      const int ti = dir ? T - 1 - t : t;
+#pragma unroll
+      for (int i = 0; i < F / 4; ++i) v[i] = valid ? __ldg(zrow + (size_t)ti * (F / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(0);
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xempty), (uint32_t)(t - 1) & 1u);
+#pragma unroll
+      for (int k = 0; k < KSX; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of the slab row: k-elements 8j .. 8j+7
+          const float4 a = v[k * 8 + j * 2], b = v[k * 8 + j * 2 + 1];
+          uint4 hi, lo;
+          ptx::split_f16x2(a.x * sc.x_mul, a.y * sc.x_mul, hi.x, lo.x);
+          ptx::split_f16x2(a.z * sc.x_mul, a.w * sc.x_mul, hi.y, lo.y);
+          ptx::split_f16x2(b.x * sc.x_mul, b.y * sc.x_mul, hi.z, lo.z);
+          ptx::split_f16x2(b.z * sc.x_mul, b.w * sc.x_mul, hi.w, lo.w);
+          const uint32_t off = (uint32_t)k * 8192u + row_off + (((uint32_t)j ^ sw) << 4);
+          *reinterpret_cast<uint4*>(xs + off) = hi;
+          *reinterpret_cast<uint4*>(xs + (uint32_t)KSX * 8192u + off) = lo;
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->xfull));
+      if (t + 1 < T) fetch(t + 1);
+    }
+  } else {
+    // ===================================== EPILOGUE =========================================================
+    const int q = warp & 3, e = warp >> 2;
+    const int r = q * 32 + lane, seq = seq0 + r;
+    const bool valid = seq < g.NSEQ;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float cst[NCH][16];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
+    int gidx = 0;
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        const int ti = dir ? T - 1 - t : t;
+        const uint32_t h_cur = tm_h0 + (uint32_t)(t & 1) * 128u;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int slot = gidx & 1;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
+          ptx::tc_fence_after();
+          float hv[16];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t a[32];
+            ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64 + half * 32), a);
+            ptx::tmem_ld_wait();
+            if (half == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+            }
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 128 + e * 64 + half * 32);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 bb = bp[u];
+              lstm_cell(fmaf(__uint_as_float(a[4 * u]), sc.inv_g, bb.x), fmaf(__uint_as_float(a[4 * u + 1]), sc.inv_g, bb.y),
+                        fmaf(__uint_as_float(a[4 * u + 2]), sc.inv_g, bb.z), fmaf(__uint_as_float(a[4 * u + 3]), sc.inv_g, bb.w),
+                        cst[c][half * 8 + u], hv[half * 8 + u]);
+            }
+          }
+          // h_t pieces for the next step: units 32c + 16e + [0,16) -> 8 packed columns of the hi image, 8 of the lo image
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ptx::split_f16x2(hv[2 * i] * 16384.f, hv[2 * i + 1] * 16384.f, hi[i], lo[i]);
+          ptx::tmem_st8(h_cur + lane_off + (uint32_t)(c * 16 + e * 8), hi);
+          ptx::tmem_st8(h_cur + lane_off + 64u + (uint32_t)(c * 16 + e * 8), lo);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->hfull[t & 1]));
+          if (g.hout && valid) {
+            float4* dst = reinterpret_cast<float4*>(g.hout + ((size_t)seq * T + ti) * (2 * H) + dir * H + c * 32 + e * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
+          }
+          ++gidx;
+        }
+      }
+      if (proj && t >= 1) {
+        const int tp = dir ? T - t : t - 1;  // time index of h_{t-1}
+        const int slot = gidx & 1;
+        ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
+        ptx::tc_fence_after();
+        const int half_cols = g.Fo >> 1;
+        float* dst = g.P + (((size_t)dir * g.NSEQ + (valid ? seq : 0)) * T + tp) * g.Fo + e * half_cols;
+        for (int c0 = 0; c0 < half_cols; c0 += 16) {
+          uint32_t a[16];
+          ptx::tmem_ld16(tmem + lane_off + (uint32_t)(slot * 128 + e * half_cols + c0), a);
+          ptx::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dst + c0)[i] =
+                  make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
+                              __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+        ++gidx;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 8) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ---- operand preparation -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_absmax_flat(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const size_t n4 = n / 4;
+  const float4* p = reinterpret_cast<const float4*>(x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
+}
+
+__device__ __forceinline__ float block_max(float m, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+// smallest e with 2^e > m (m finite, > 0); clamped
+__device__ __forceinline__ int ceil_exp(float m, int lo, int hi) {
+  int e = m > 0.f ? (int)((__float_as_uint(m) >> 23) & 255u) - 126 : lo;
+  return e < lo ? lo : (e > hi ? hi : e);
+}
+__device__ __forceinline__ float exp2i(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
+
+// grid 2 (directions), 1024 threads: power-of-two operand scales from max|x| (measured) and max|W| (this direction)
+__global__ void __launch_bounds__(1024) k_lstm_scales(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
+                                                      const float* __restrict__ wih_r, const float* __restrict__ whh_r,
+                                                      const float* __restrict__ wfc, const unsigned* __restrict__ xmax, int F, int H,
+                                                      int Fo, LstmScales* __restrict__ out) {
+  __shared__ float red[32];
+  const int d = blockIdx.x;
+  const float* wih = d ? wih_r : wih_f;
+  const float* whh = d ? whh_r : whh_f;
+  float mi = 0.f, mh = 0.f, mp = 0.f;
+  for (int i = threadIdx.x; i < 4 * H * F; i += blockDim.x) mi = fmaxf(mi, fabsf(wih[i]));
+  for (int i = threadIdx.x; i < 4 * H * H; i += blockDim.x) mh = fmaxf(mh, fabsf(whh[i]));
+  if (wfc)
+    for (int i = threadIdx.x; i < Fo * H; i += blockDim.x) mp = fmaxf(mp, fabsf(wfc[(size_t)(i / H) * 2 * H + d * H + (i % H)]));
+  mi = block_max(mi, red);
+  mh = block_max(mh, red);
+  mp = block_max(mp, red);
+  if (threadIdx.x == 0) {
+    const int ex = ceil_exp(__uint_as_float(*xmax), -40, 40);
+    const int eW = ceil_exp(fmaxf(mi * exp2i(ex), mh), -60, 60);
+    const int eP = ceil_exp(mp, -60, 60);
+    LstmScales s;
+    s.x_mul = exp2i(14 - ex);
+    s.w_ih_mul = exp2i(ex + 14 - eW);
+    s.w_hh_mul = exp2i(14 - eW);
+    s.inv_g = exp2i(eW - 28);
+    s.w_p_mul = exp2i(14 - eP);
+    s.inv_p = exp2i(eP - 28);
+    s.pad[0] = s.pad[1] = 0.f;
+    out[d] = s;
+  }
+}
+
+// grid (n_imgs, 2): one 16 KB stage image per block.  Gate stage (chunk c, slab k): column n = 64 e + 4 u + gate <-> weight row
+// gate * H + 32 c + 16 e + u, k-element 32 k + kk of [W_ih * w_ih_mul | W_hh * w_hh_mul]; projection stage k: row n = output
+// feature, W_fc[n][dir * H + 32 k + kk] * w_p_mul.  Block (0, dir) also writes the bias table in column order.
+__global__ void __launch_bounds__(256) k_lstm_build(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
+                                                    const float* __restrict__ bih_f, const float* __restrict__ bhh_f,
+                                                    const float* __restrict__ wih_r, const float* __restrict__ whh_r,
+                                                    const float* __restrict__ bih_r, const float* __restrict__ bhh_r,
+                                                    const float* __restrict__ wfc, int F, int H, int Fo, const LstmScales* __restrict__ scp,
+                                                    uint8_t* __restrict__ img, float* __restrict__ bias, int n_imgs) {
+  const int d = blockIdx.y, idx = blockIdx.x;
+  const float* wih = d ? wih_r : wih_f;
+  const float* whh = d ? whh_r : whh_f;
+  const LstmScales sc = scp[d];
+  const int KSX = F / 32, KSH = H / 32, per = KSX + KSH, n_gate = KSH * per;
+  uint8_t* dst = img + ((size_t)d * n_imgs + idx) * STAGE_BYTES;
+  if (idx == 0) {
+    const float* bi = d ? bih_r : bih_f;
+    const float* bh = d ? bhh_r : bhh_f;
+    for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) {
+      const int c = i / 128, n = i % 128, row = (n & 3) * H + 32 * c + 16 * (n >> 6) + ((n & 63) >> 2);
+      bias[(size_t)d * 4 * H + i] = bi[row] + bh[row];
+    }
+  }
+  const bool is_proj = idx >= n_gate;
+  const int rows = is_proj ? Fo : 128;
+  const uint32_t lo_base = (uint32_t)rows * 64u;
+  const int c = is_proj ? 0 : idx / per, k = is_proj ? idx - n_gate : idx % per;
+  for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {  // one pair of k-elements per iteration
+    const int n = i / 16, kk = (i % 16) * 2;
+    float v0, v1;
+    if (is_proj) {
+      const float* p = wfc + (size_t)n * 2 * H + d * H + 32 * k + kk;
+      v0 = p[0] * sc.w_p_mul;
+      v1 = p[1] * sc.w_p_mul;
+    } else {
+      const int row = (n & 3) * H + 32 * c + 16 * (n >> 6) + ((n & 63) >> 2);
+      if (k < KSX) {
+        const float* p = wih + (size_t)row * F + 32 * k + kk;
+        v0 = p[0] * sc.w_ih_mul;
+        v1 = p[1] * sc.w_ih_mul;
+      } else {
+        const float* p = whh + (size_t)row * H + 32 * (k - KSX) + kk;
+        v0 = p[0] * sc.w_hh_mul;
+        v1 = p[1] * sc.w_hh_mul;
+      }
+    }
+    uint32_t hi, lo;
+    ptx::split_f16x2(v0, v1, hi, lo);
+    const uint32_t off = (uint32_t)(n >> 3) * 512u + (uint32_t)(n & 7) * 64u + ((((uint32_t)kk >> 3) ^ (((uint32_t)n >> 1) & 3u)) << 4) +
+                         ((uint32_t)kk & 7u) * 2u;
+    *reinterpret_cast<uint32_t*>(dst + off) = hi;
+    *reinterpret_cast<uint32_t*>(dst + lo_base + off) = lo;
+  }
+}
+
+// Y = P0 + P1 + bias (the Linear of dprnn.py:87 / 139 split over the two directions): gLN statistics of it ...
+__global__ void __launch_bounds__(256) k_sample_stats2(const float* __restrict__ P0, const float* __restrict__ P1,
+                                                       const float* __restrict__ bias, size_t n, int F, double* __restrict__ stats) {
+  __shared__ double red[64];
+  const int b = blockIdx.y;
+  const float4* p0 = reinterpret_cast<const float4*>(P0 + (size_t)b * n);
+  const float4* p1 = reinterpret_cast<const float4*>(P1 + (size_t)b * n);
+  const size_t n4 = n / 4;  // F % 4 == 0
+  double s = 0.0, ss = 0.0;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x * 4; i0 < n4; i0 += (size_t)gridDim.x * blockDim.x * 4) {
+    float ls = 0.f, lss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x + threadIdx.x;
+      if (i < n4) {
+        const float4 a = __ldg(p0 + i), c = __ldg(p1 + i), bb = __ldg(reinterpret_cast<const float4*>(bias + (i * 4) % F));
+        const float x = a.x + c.x + bb.x, y = a.y + c.y + bb.y, z = a.z + c.z + bb.z, w = a.w + c.w + bb.w;
+        ls += (x + y) + (z + w);
+        lss = fmaf(x, x, fmaf(y, y, fmaf(z, z, fmaf(w, w, lss))));
+      }
+    }
+    s += ls;
+    ss += lss;
+  }
+  block_sum2_d(s, ss, red);
+  if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+}
+
+// ... and out = gLN(Y) + R, optionally stored with the two middle dimensions swapped (the layout of the other path)
+__global__ void __launch_bounds__(256) k_norm_res2(const float* __restrict__ P0, const float* __restrict__ P1, const float* __restrict__ bias,
+                                                   const float* __restrict__ R, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float* __restrict__ out, const double* __restrict__ stats,
+                                                   int D1, int D2, int F, float eps, int swap) {
+  const int b = blockIdx.y;
+  const float2 mr = gln_mean_rstd(stats + 2 * b, (double)D1 * (double)D2 * (double)F, eps);
+  const size_t cells = (size_t)D1 * D2;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (size_t c = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); c < cells; c += (size_t)gridDim.x * wpb) {
+    const int d1 = (int)(c / D2), d2 = (int)(c % D2);
+    const size_t src = ((size_t)b * cells + c) * F;
+    const size_t dst = swap ? (((size_t)b * D2 + d2) * D1 + d1) * F : src;
+    for (int f = lane * 4; f < F; f += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(P0 + src + f)), c1 = __ldg(reinterpret_cast<const float4*>(P1 + src + f));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + f)), r = __ldg(reinterpret_cast<const float4*>(R + src + f));
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + f)), be = __ldg(reinterpret_cast<const float4*>(beta + f));
+      float4 o;
+      o.x = fmaf((a.x + c1.x + bb.x - mr.x) * mr.y, gm.x, be.x) + r.x;
+      o.y = fmaf((a.y + c1.y + bb.y - mr.x) * mr.y, gm.y, be.y) + r.y;
+      o.z = fmaf((a.z + c1.z + bb.z - mr.x) * mr.y, gm.z, be.z) + r.z;
+      o.w = fmaf((a.w + c1.w + bb.w - mr.x) * mr.y, gm.w, be.w) + r.w;
+      *reinterpret_cast<float4*>(out + dst + f) = o;
+    }
+  }
+}
+
+struct LstmPlan {
+  int n_imgs, n_st;
+  size_t off_sc, off_bias, off_img, total, smem;
+};
+bool lstm_plan(int F, int H, int Fo, LstmPlan& p) {
+  if (!(H == 32 || H == 64 || H == 128) || !(F == 32 || F == 64 || F == 128)) return false;
+  if (Fo != 0 && (Fo % 32 != 0 || Fo < 32 || Fo > 128)) return false;
+  const int KSX = F / 32, KSH = H / 32;
+  p.n_imgs = KSH * (KSX + KSH) + KSH;
+  p.off_sc = 256;
+  p.off_bias = 512;
+  p.off_img = 512 + (((size_t)2 * 4 * H * sizeof(float) + 255) / 256) * 256;
+  p.total = p.off_img + (size_t)2 * p.n_imgs * STAGE_BYTES;
+  const size_t fixed = 1024 /*alignment slack*/ + HDR_BYTES + 2048 + (size_t)2 * KSX * 8192;
+  int n_st = (int)((232448 - fixed) / STAGE_BYTES);
+  if (n_st > MAX_ST) n_st = MAX_ST;
+  if (const char* e = getenv("CTN_LSTM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < n_st) n_st = v; }
+  if (n_st < 3) return false;
+  p.n_st = n_st;
+  p.smem = fixed + (size_t)n_st * STAGE_BYTES;
+  return true;
+}
+
+template <int NCH, int KSX>
+int launch_bilstm(const LstmArgs& a, size_t smem, cudaStream_t st) {
+  static bool done[CTN_MAX_DEVICES] = {};
+  const int dev = ctn_current_device();
+  if (!done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_bilstm<NCH, KSX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    done[dev] = true;
+  }
+  k_bilstm<NCH, KSX><<<dim3((a.NSEQ + LM - 1) / LM, 2), LSTM_THREADS, smem, st>>>(a);
+  return CTN_OK;
+}
+
+}  // namespace
+
+extern "C" int ctn_bilstm_supported(int F, int H, int Fo) {
+  LstmPlan p;
+  return lstm_plan(F, H, Fo, p) ? 1 : 0;
+}
+
+extern "C" size_t ctn_bilstm_workspace_bytes(int F, int H, int Fo) {
+  LstmPlan p;
+  return lstm_plan(F, H, Fo, p) ? p.total : 0;
+}
+
+extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H, const float* const* w, const float* w_fc, int Fo, float* P,
+                                   float* hout, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+  LaunchScope scope(z);
+  if (!z || !w || !workspace || NSEQ <= 0 || T <= 0) return CTN_EINVAL;
+  for (int i = 0; i < 8; ++i)
+    if (!w[i]) return CTN_EINVAL;
+  if ((w_fc == nullptr) != (P == nullptr)) return CTN_EINVAL;
+  if (!w_fc && !hout) return CTN_EINVAL;
+  LstmPlan p;
+  if (!lstm_plan(F, H, w_fc ? Fo : 0, p)) return CTN_EUNSUPPORTED;
+  if (workspace_bytes < p.total) return CTN_EWORKSPACE;
+  if ((((uintptr_t)z) | ((uintptr_t)P) | ((uintptr_t)hout) | ((uintptr_t)workspace)) & 15) return CTN_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  unsigned* xmax = reinterpret_cast<unsigned*>(ws);
+  LstmScales* sc = reinterpret_cast<LstmScales*>(ws + p.off_sc);
+  float* bias = reinterpret_cast<float*>(ws + p.off_bias);
+  uint8_t* img = ws + p.off_img;
+  cudaError_t e = cudaMemsetAsync(xmax, 0, 4, st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t n = (size_t)NSEQ * T * F;
+  int gx = (int)((n / 4 + 255) / 256);
+  if (gx > 1184) gx = 1184;
+  if (gx < 1) gx = 1;
+  k_absmax_flat<<<gx, 256, 0, st>>>(z, n, xmax);
+  CTN_COUNT_LAUNCH();
+  // w: weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then the same four with the _reverse suffix (torch.nn.LSTM names)
+  k_lstm_scales<<<2, 1024, 0, st>>>(w[0], w[1], w[4], w[5], w_fc, xmax, F, H, Fo, sc);
+  CTN_COUNT_LAUNCH();
+  const int n_build = w_fc ? p.n_imgs : p.n_imgs - H / 32;
+  k_lstm_build<<<dim3(n_build, 2), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w_fc, F, H, Fo, sc, img, bias, p.n_imgs);
+  CTN_COUNT_LAUNCH();
+  LstmArgs a;
+  a.z = z; a.P = P; a.hout = hout; a.img = img; a.bias = bias; a.sc = sc;
+  a.NSEQ = NSEQ; a.T = T; a.Fo = w_fc ? Fo : 32; a.n_imgs = p.n_imgs; a.n_st = p.n_st; a.has_proj = w_fc ? 1 : 0;
+  int rc = CTN_EUNSUPPORTED;
+  const int NCH = H / 32, KSX = F / 32;
+#define CTN_LSTM_CASE(nch, ksx) if (NCH == nch && KSX == ksx) rc = launch_bilstm<nch, ksx>(a, p.smem, st);
+  CTN_LSTM_CASE(1, 1) CTN_LSTM_CASE(2, 1) CTN_LSTM_CASE(2, 2) CTN_LSTM_CASE(4, 1) CTN_LSTM_CASE(4, 2) CTN_LSTM_CASE(4, 4)
+  CTN_LSTM_CASE(1, 2) CTN_LSTM_CASE(1, 4) CTN_LSTM_CASE(2, 4)
+#undef CTN_LSTM_CASE
+  if (rc != CTN_OK) return rc;
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, const float* R, const float* gamma, const float* beta,
+                                       float* out, int B, int D1, int D2, int F, float eps, int swap, double* scratch,
+                                       ctn_stream_t stream) {
+  LaunchScope scope(P);
+  if (!P || !fc_bias || !R || !gamma || !beta || !out || !scratch || B <= 0 || D1 <= 0 || D2 <= 0 || F <= 0 || (F & 3)) return CTN_EINVAL;
+  if (swap && out == R) return CTN_EINVAL;
+  if ((((uintptr_t)P) | ((uintptr_t)R) | ((uintptr_t)out) | ((uintptr_t)gamma) | ((uintptr_t)beta) | ((uintptr_t)fc_bias)) & 15)
+    return CTN_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t n = (size_t)D1 * D2 * F;
+  const float* P1 = P + (size_t)B * n;  // second direction
+  int gx = (int)((n / 4 + 256 * 4 - 1) / (256 * 4));
+  if (gx > 592) gx = 592;
+  if (gx < 1) gx = 1;
+  k_sample_stats2<<<dim3(gx, B), 256, 0, st>>>(P, P1, fc_bias, n, F, scratch);
+  CTN_COUNT_LAUNCH();
+  const size_t cells = (size_t)D1 * D2;
+  int gy = (int)((cells + 7) / 8);
+  if (gy > 2368) gy = 2368;
+  k_norm_res2<<<dim3(gy, B), 256, 0, st>>>(P, P1, fc_bias, R, gamma, beta, out, scratch, D1, D2, F, eps, swap);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}

@@ -4,10 +4,12 @@
 ``state_dict`` keys (``rnn.weight_ih_l0`` ..., ``fc.weight/bias``, ``norm1d.norm.weight/bias``).
 
 What runs where: the dual-path state lives CHANNELS-LAST, (batch, D1, D2, features) -- already the batch_first tensor the
-path's LSTM consumes, so none of the reference's permute().contiguous() copies exist.  The bi-LSTM recurrence is cuDNN
-(``nn.LSTM``) and the 2H -> F projection a library GEMM (``F.linear``): sequential recurrences / plain GEMMs are the one
-place a library is the right tool.  Everything between them -- gLN statistics, normalisation,
-residual add and the intra <-> inter layout swap -- is ONE native call (ctn_dprnn_norm_res_fwd, csrc/ctn_dprnn.cu).
+path's LSTM consumes, so none of the reference's permute().contiguous() copies exist.  For num_features / hidden_channels in
+{32, 64, 128} (cfg4: 64 / 128) the bi-LSTM recurrence AND the 2H -> F Linear run in one tcgen05 kernel with h resident in tensor
+memory (``ctn_bilstm_proj_fwd``, csrc/ctn_lstm.cu): the (batch*D1, D2, 2H) LSTM output is never written.  gLN statistics,
+normalisation, the sum of the two directions' partial projections + bias, the residual add and the intra <-> inter layout swap are
+one more native call (``ctn_dprnn_norm_res2_fwd``).  Other sizes fall back to cuDNN's LSTM (IEEE fp32) + a library GEMM +
+``ctn_dprnn_norm_res_fwd``; ``NATIVE_LSTM = False`` forces that path (it is the A/B baseline of bench.py --config cfg4).
 Envelope: non-causal (gLN, bidirectional inter-chunk LSTM), rnn_type='lstm', norm=True; forward only.
 """
 import contextlib
@@ -23,6 +25,7 @@ from .transform import ctn_dprnn_norm_res_fwd
 EPS = 1e-12
 
 
+NATIVE_LSTM = True  # tcgen05 recurrence (csrc/ctn_lstm.cu) where the sizes allow; False = cuDNN + library GEMM everywhere
 LSTM_TF32 = False  # cuDNN's RNN path defaults to TF32 tensor-core math (1e-3 relative): off = fp32 parity with the reference
 
 
@@ -79,13 +82,27 @@ class _ChunkRNN(nn.Module):
         """z (B, D1, D2, F) channels-last -> gLN(fc(rnn(z))) + z, stored as (B, D2, D1, F) when swap."""
         B, D1, D2, F = z.shape
         dev = N.require_cuda(z)
+        H = self.hidden_channels
+        out = torch.empty((B, D2, D1, F) if swap else (B, D1, D2, F), dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * B, dtype=torch.float64, device=dev)
+        g, b = self.norm1d.norm.weight, self.norm1d.norm.bias
+        if NATIVE_LSTM and N.ctn_bilstm_supported(F, H, F):
+            r = self.rnn
+            ptrs = (N._fp * 8)(*[t.data_ptr() for t in (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse,
+                                                         r.weight_hh_l0_reverse, r.bias_ih_l0_reverse, r.bias_hh_l0_reverse)])
+            nws = N.ctn_bilstm_workspace_bytes(F, H, F)
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            P = torch.empty((2, B, D1, D2, F), dtype=torch.float32, device=dev)
+            N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), B * D1, D2, F, H, ptrs, self.fc.weight.data_ptr(), F, P.data_ptr(), None,
+                                          ws.data_ptr(), nws, N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
+            N.check(N.ctn_dprnn_norm_res2_fwd(P.data_ptr(), self.fc.bias.data_ptr(), z.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                              B, D1, D2, F, float(self.eps), int(swap), scratch.data_ptr(), N.stream_ptr(dev)),
+                    "ctn_dprnn_norm_res2_fwd")
+            return out
         self.rnn.flatten_parameters()
         with _rnn_precision():
             y, _ = self.rnn(z.view(B * D1, D2, F))              # cuDNN bi-LSTM over D2, IEEE fp32 math
         y = F_.linear(y, self.fc.weight, self.fc.bias)           # (B*D1, D2, F)
-        out = torch.empty((B, D2, D1, F) if swap else (B, D1, D2, F), dtype=torch.float32, device=dev)
-        scratch = torch.empty(2 * B, dtype=torch.float64, device=dev)
-        g, b = self.norm1d.norm.weight, self.norm1d.norm.bias
         N.check(ctn_dprnn_norm_res_fwd(y.data_ptr(), z.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), B, D1, D2, F,
                                        float(self.eps), int(swap), scratch.data_ptr(), N.stream_ptr(dev)), "ctn_dprnn_norm_res_fwd")
         return out
