@@ -18,16 +18,20 @@
 //     partial projection (NSEQ, T, F) and the gLN + residual kernel adds the two and the bias.
 // TMEM columns: [0,256) two 128-column accumulators, [256,512) two h buffers (hi at +0, lo at +64 of each).
 // Warp roles: 0-7 epilogue (warp & 3 = lane quarter, warp >> 2 = column half), 8 TMEM alloc + MMA issuer, 9 weight loader,
-// 10-13 x producers.
+// 12-15 x producers.  The launch gives every thread 128 registers; the warpgroups then trade them (setmaxnreg): the epilogue,
+// which keeps the cell state of 64 hidden units per thread in registers, runs with 176.
 #include "ctn_internal.h"
 #include "ctn_umma_ptx.cuh"
 
 namespace {
 
 constexpr int LM = 128;               // sequences per CTA
-constexpr int STAGE_BYTES = 16384;    // one weight stage: [hi 128 x 64 B][lo 128 x 64 B]
-constexpr int MAX_ST = 12;
-constexpr int LSTM_THREADS = 448;
+constexpr int SLAB_BYTES = 16384;     // one weight slab image: [hi 128 columns x 64 B][lo 128 x 64 B] = 32 k of a 128-column chunk
+constexpr int STAGE_BYTES = 2 * SLAB_BYTES;  // a ring stage = two consecutive slabs behind one barrier
+constexpr int MAX_ST = 6;
+constexpr int PSTAGE_BYTES = 32768;   // projection store staging: 8 epilogue warps x 4 KB
+constexpr int LSTM_THREADS = 512;     // 4 warpgroups: 0-3, 4-7 epilogue | 8 MMA, 9 loader, 10-11 idle | 12-15 x producers
+constexpr int REGS_EPI = 176, REGS_CTRL = 56, REGS_PROD = 104;  // setmaxnreg budget: 128 * (2*176 + 56 + 104) = 65536
 constexpr int HDR_BYTES = 1024;
 
 struct LstmScales {                   // one per direction, written by k_lstm_scales
@@ -51,10 +55,11 @@ struct LstmArgs {
   const float* z;        // (NSEQ, T, F)
   float* P;              // (2, NSEQ, T, Fo) or null
   float* hout;           // (NSEQ, T, 2H) or null
-  const uint8_t* img;    // [2][n_imgs][STAGE_BYTES]
-  const float* bias;     // [2][4H], chunk-column order
+  const uint8_t* img;    // [2][n_imgs][SLAB_BYTES]
+  const float* bias;     // [2][4H], chunk-column order, pre-multiplied by -log2(e) (-2 log2(e) for the g gate)
   const LstmScales* sc;  // [2]
   int NSEQ, T, Fo, n_imgs, n_st, has_proj;
+  uint32_t dbg;          // CTN_LSTM_DBG (timing experiments only): 1 no cell math, 2 no MMAs, 4 no weight copies, 8 no x loads
 };
 
 __device__ __forceinline__ float ex2f_(float x) {
@@ -67,18 +72,32 @@ __device__ __forceinline__ float rcpf_(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float clampf_(float v, float m) { return fminf(fmaxf(v, -m), m); }
 
-// one LSTM cell update from the four pre-activations.  sigmoid(a) = 1 / (1 + e^-a), tanh(a) = (1 - e^-2a) / (1 + e^-2a); the
-// products i*g and o*tanh(c) share one reciprocal each: 5 ex2 + 3 rcp per unit.  Arguments are clamped where the function has
-// already saturated in fp32 (|a| >= 30 for sigmoid, >= 15 for tanh) so that no intermediate overflows.
-__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float& c, float& h) {
-  constexpr float L2E = 1.4426950408889634f;
-  const float Ei = ex2f_(-L2E * clampf_(ai, 30.f)), Ef = ex2f_(-L2E * clampf_(af, 30.f));
-  const float Eg = ex2f_(-2.f * L2E * clampf_(ag, 15.f)), Eo = ex2f_(-L2E * clampf_(ao, 30.f));
-  const float ig = (1.f - Eg) * rcpf_((1.f + Ei) * (1.f + Eg));
-  c = fmaf(rcpf_(1.f + Ef), c, ig);
-  const float Ec = ex2f_(-2.f * L2E * clampf_(c, 15.f));
+
+// timeline probe (CTN_LSTM_DBG bit 16): cycle stamps of CTA (0,0), steps [100,104): [step][role: 0 issuer, 1 epilogue warp 0][chunk 0..4][4]
+__device__ unsigned long long g_lstm_tl[4 * 2 * 5 * 4];
+__device__ __forceinline__ void tl_mark(bool on, int t, int role, int c, int k) {
+  if (on && t >= 100 && t < 104) g_lstm_tl[(((t - 100) * 2 + role) * 5 + c) * 4 + k] = clock64();
+}
+
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// One LSTM cell update.  Inputs are the ex2 ARGUMENTS of the four gates, xi = -log2(e) a_i, xf, xo likewise, xg = -2 log2(e) a_g
+// (the scale and the bias are folded into one FFMA by the caller), so that E = 2^x = e^-a (e^-2a for g):
+//   sigmoid(a) = 1 / (1 + E),  tanh(a) = (1 - E) / (1 + E).
+// f, i*g share ONE reciprocal, o*tanh(c) another: 5 ex2 + 2 rcp per unit (the MUFU pipe, 16 lanes/clk/SM, is what bounds the
+// epilogue).  Arguments are capped where the function has saturated in fp32 (E <= e^20 for the sigmoids, e^30 for tanh) so that
+// the products of denominators stay finite (< 2.4e30).
+__device__ __forceinline__ void lstm_cell(float xi, float xf, float xg, float xo, float& c, float& h) {
+  constexpr float CAP_S = 28.853901f, CAP_T = 43.280851f;  // 20 log2(e), 30 log2(e)
+  const float Ei = ex2f_(fminf(xi, CAP_S)), Ef = ex2f_(fminf(xf, CAP_S)), Eg = ex2f_(fminf(xg, CAP_T)), Eo = ex2f_(fminf(xo, CAP_S));
+  const float pf = 1.f + Ef, pig = (1.f + Ei) * (1.f + Eg);
+  const float r = rcpf_(pig * pf);
+  c = fmaf(r * pig, c, (1.f - Eg) * (r * pf));
+  const float Ec = ex2f_(fminf(c * -2.8853901f, CAP_T));
   h = (1.f - Ec) * rcpf_((1.f + Eo) * (1.f + Ec));
 }
 
@@ -93,7 +112,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
   LstmHdr* hdr = reinterpret_cast<LstmHdr*>(smem);
   float* s_bias = reinterpret_cast<float*>(smem + HDR_BYTES);            // 4H floats (<= 2 KB)
   constexpr uint32_t XS_OFF = HDR_BYTES + 2048;                          // x operand: [hi KSX slabs][lo KSX slabs] of 8 KB
-  constexpr uint32_t RING_OFF = XS_OFF + 2 * KSX * 8192;
+  constexpr uint32_t PST_OFF = XS_OFF + 2 * KSX * 8192;                  // projection store staging
+  constexpr uint32_t RING_OFF = PST_OFF + PSTAGE_BYTES;
   const uint32_t xs0 = base + XS_OFF, ring0 = base + RING_OFF;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir = blockIdx.y, seq0 = blockIdx.x * LM;
@@ -133,123 +153,143 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
   __syncthreads();
   ptx::tc_fence_after();
 
+  if (warp >= 8 && warp < 12) reg_dec<REGS_CTRL>();
   if (warp == 9) {
     // ===================================== WEIGHT LOADER ====================================================
+    // a ring stage holds TWO consecutive slabs of a sequence (gate slabs of a step / projection slabs of a step), one barrier
     if (ptx::elect_one()) {
-      const uint8_t* img = g.img + (size_t)dir * g.n_imgs * STAGE_BYTES;
+      const uint8_t* img = g.img + (size_t)dir * g.n_imgs * SLAB_BYTES;
       int s = 0;
       uint32_t ph = 0;
-      auto load = [&](int idx, uint32_t bytes) {
-        ptx::mbar_wait(ptx::smem_u32(&hdr->bempty[s]), ph ^ 1u);
-        const uint32_t fb = ptx::smem_u32(&hdr->bfull[s]);
-        ptx::mbar_arrive_expect_tx(fb, bytes);
-        ptx::bulk_g2s(ring0 + (uint32_t)s * STAGE_BYTES, img + (size_t)idx * STAGE_BYTES, bytes, fb);
-        if (++s == g.n_st) { s = 0; ph ^= 1u; }
+      auto load_seq = [&](int first, int count, uint32_t bytes) {
+        for (int i = 0; i < count; i += 2) {
+          const int n = count - i < 2 ? count - i : 2;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->bempty[s]), ph ^ 1u);
+          const uint32_t fb = ptx::smem_u32(&hdr->bfull[s]);
+          ptx::mbar_arrive_expect_tx(fb, bytes * n);
+          for (int j = 0; j < n; ++j) {
+            if (!(g.dbg & 4u))
+              ptx::bulk_g2s(ring0 + (uint32_t)s * STAGE_BYTES + (uint32_t)j * SLAB_BYTES, img + (size_t)(first + i + j) * SLAB_BYTES, bytes, fb);
+            else
+              asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
+          }
+          if (++s == g.n_st) { s = 0; ph ^= 1u; }
+        }
       };
       for (int t = 0; t <= T; ++t) {
-        if (t < T)
-          for (int i = 0; i < NCH * (KSX + KSH); ++i) load(i, STAGE_BYTES);
-        if (proj && t >= 1)
-          for (int k = 0; k < KSH; ++k) load(NCH * (KSX + KSH) + k, (uint32_t)g.Fo * 128u);
+        if (t < T) load_seq(0, NCH * (KSX + KSH), SLAB_BYTES);
+        if (proj && t >= 1) load_seq(NCH * (KSX + KSH), KSH, (uint32_t)g.Fo * 128u);
       }
     }
     __syncwarp();
   } else if (warp == 8) {
     // ===================================== MMA ISSUER =======================================================
-    const bool leader = ptx::elect_one();
-    const uint64_t d_t = ptx::make_smem_desc(0, 16u, 512u, 4u);  // K-major SWIZZLE_64B rows of 32 k (x operand and weights)
-    const uint32_t idesc_g = ptx::make_idesc_f16(LM, 128, 0, 0), idesc_p = ptx::make_idesc_f16(LM, g.Fo, 0, 0);
-    int s = 0, gidx = 0;
-    uint32_t ph = 0;
-    for (int t = 0; t <= T; ++t) {
-      const uint32_t h_prev = tm_h0 + (uint32_t)((t + 1) & 1) * 128u;  // buffer holding h_{t-1}
-      if (t < T) {
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          const int slot = gidx & 1;
-          ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
-          if (c == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xfull), (uint32_t)t & 1u);
+    // ONE thread runs the whole loop (waits included): nothing but the barrier waits stands between two groups of MMAs
+    if (ptx::elect_one()) {
+      const bool do_mma = !(g.dbg & 2u);
+      const bool tl = (g.dbg & 16u) && blockIdx.x == 0 && blockIdx.y == 0;
+      const uint64_t d_t = ptx::make_smem_desc(0, 16u, 512u, 4u);  // K-major SWIZZLE_64B rows of 32 k (x operand and weights)
+      const uint32_t idesc_g = ptx::make_idesc_f16(LM, 128, 0, 0), idesc_p = ptx::make_idesc_f16(LM, g.Fo, 0, 0);
+      int s = 0, gidx = 0;
+      uint32_t ph = 0;
+      // slab i of a sequence of `count`: wait for its stage on the first slab, hand the stage back after the last
+      auto acquire = [&](int i) -> uint32_t {
+        if (!(i & 1)) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+        }
+        return (ring0 + (uint32_t)s * STAGE_BYTES + (uint32_t)(i & 1) * SLAB_BYTES) >> 4;
+      };
+      auto release = [&](int i, int count) {
+        if ((i & 1) || i == count - 1) {
+          ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+          if (++s == g.n_st) { s = 0; ph ^= 1u; }
+        }
+      };
+      for (int t = 0; t <= T; ++t) {
+        const uint32_t h_prev = tm_h0 + (uint32_t)((t + 1) & 1) * 128u;  // buffer holding h_{t-1}
+        if (t < T) {
 #pragma unroll 1
-          for (int k = 0; k < KSX; ++k) {
-            ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+          for (int c = 0; c < NCH; ++c) {
+            const int slot = gidx & 1;
+            ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+            if (c == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xfull), (uint32_t)t & 1u);
             ptx::tc_fence_after();
-            if (leader) {
-              const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + (8192u >> 4);
+            tl_mark(tl, t, 0, c, 0);
+            const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+#pragma unroll 1
+            for (int k = 0; k < KSX; ++k) {
+              const int i = c * (KSX + KSH) + k;
+              const uint32_t w_hi = acquire(i), w_lo = w_hi + (8192u >> 4);
               const uint32_t a_hi = (xs0 + (uint32_t)k * 8192u) >> 4, a_lo = a_hi + ((uint32_t)KSX * 8192u >> 4);
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
+                if (!do_mma) break;
                 ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_hi + kk * 2), d_t | (uint64_t)(w_hi + kk * 2), idesc_g, (k | kk) ? 1u : 0u);
                 ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_lo + kk * 2), d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
                 ptx::mma_f16(d_tmem, d_t | (uint64_t)(a_hi + kk * 2), d_t | (uint64_t)(w_lo + kk * 2), idesc_g, 1u);
               }
-              ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+              release(i, NCH * (KSX + KSH));
               if (c == NCH - 1 && k == KSX - 1) ptx::mma_commit(ptx::smem_u32(&hdr->xempty));  // x_t has been consumed
             }
-            __syncwarp();
-            if (++s == g.n_st) { s = 0; ph ^= 1u; }
-          }
-          if (c == 0 && t > 0) {
-            ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
-            ptx::tc_fence_after();
-          }
+            tl_mark(tl, t, 0, c, 1);
+            if (c == 0 && t > 0) {
+              ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
+              ptx::tc_fence_after();
+            }
+            tl_mark(tl, t, 0, c, 2);
 #pragma unroll 1
-          for (int k = 0; k < KSH; ++k) {
-            ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
-            ptx::tc_fence_after();
-            if (leader) {
-              const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + (8192u >> 4);
+            for (int k = 0; k < KSH; ++k) {
+              const int i = c * (KSX + KSH) + KSX + k;
+              const uint32_t w_hi = acquire(i), w_lo = w_hi + (8192u >> 4);
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
+                if (!do_mma) break;
                 const uint32_t a_hi = h_prev + (uint32_t)(k * 2 + kk) * 8u, a_lo = a_hi + 64u;
                 ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
                 ptx::mma_f16_ts(d_tmem, a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc_g, 1u);
                 ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc_g, 1u);
               }
-              ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
-              if (k == KSH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+              release(i, NCH * (KSX + KSH));
             }
-            __syncwarp();
-            if (++s == g.n_st) { s = 0; ph ^= 1u; }
+            ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+            tl_mark(tl, t, 0, c, 3);
+            ++gidx;
           }
-          ++gidx;
         }
-      }
-      if (proj && t >= 1) {
-        const int slot = gidx & 1;
-        ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
-        if (t == T) ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
-        const uint32_t lo_off = ((uint32_t)g.Fo * 64u) >> 4;
-#pragma unroll 1
-        for (int k = 0; k < KSH; ++k) {
-          ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+        if (proj && t >= 1) {
+          const int slot = gidx & 1;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+          if (t == T) ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[(t + 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
           ptx::tc_fence_after();
-          if (leader) {
-            const uint32_t w_hi = (ring0 + (uint32_t)s * STAGE_BYTES) >> 4, w_lo = w_hi + lo_off;
+          tl_mark(tl, t, 0, 4, 0);
+          const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+          const uint32_t lo_off = ((uint32_t)g.Fo * 64u) >> 4;
+#pragma unroll 1
+          for (int k = 0; k < KSH; ++k) {
+            const uint32_t w_hi = acquire(k), w_lo = w_hi + lo_off;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
+              if (!do_mma) break;
               const uint32_t a_hi = h_prev + (uint32_t)(k * 2 + kk) * 8u, a_lo = a_hi + 64u;
               ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc_p, (k | kk) ? 1u : 0u);
               ptx::mma_f16_ts(d_tmem, a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc_p, 1u);
               ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc_p, 1u);
             }
-            ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
-            if (k == KSH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+            release(k, KSH);
           }
-          __syncwarp();
-          if (++s == g.n_st) { s = 0; ph ^= 1u; }
+          ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+          tl_mark(tl, t, 0, 4, 3);
+          ++gidx;
         }
-        ++gidx;
       }
     }
     __syncwarp();
-  } else if (warp >= 10) {
+  } else if (warp >= 12) {
     // ===================================== x PRODUCERS ======================================================
     // thread = one sequence: x_t (F floats, contiguous) -> scaled fp16 hi / lo pieces -> K-major SWIZZLE_64B slabs
-    const int r = (warp - 10) * 32 + lane, seq = seq0 + r;
+    reg_dec<REGS_PROD>();
+    const int r = (warp - 12) * 32 + lane, seq = seq0 + r;
     const bool valid = seq < g.NSEQ;
     const float4* zrow = reinterpret_cast<const float4*>(g.z + (size_t)(valid ? seq : 0) * T * F);
     uint8_t* xs = smem + XS_OFF;
@@ -258,7 +298,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
     auto fetch = [&](int t) {
       const int ti = dir ? T - 1 - t : t;
 #pragma unroll
-      for (int i = 0; i < F / 4; ++i) v[i] = valid ? __ldg(zrow + (size_t)ti * (F / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < F / 4; ++i)
+        v[i] = (valid && !(g.dbg & 8u)) ? __ldg(zrow + (size_t)ti * (F / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     fetch(0);
     for (int t = 0; t < T; ++t) {
@@ -283,9 +324,12 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->xfull));
       if (t + 1 < T) fetch(t + 1);
     }
-  } else {
+  } else if (warp < 8) {
     // ===================================== EPILOGUE =========================================================
+    reg_inc<REGS_EPI>();
     const int q = warp & 3, e = warp >> 2;
+    const float sg = -1.4426950408889634f * sc.inv_g, sg2 = 2.f * sg;  // acc -> ex2 argument (bias table is pre-scaled alike)
+    const bool tl = (g.dbg & 16u) && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
     const int r = q * 32 + lane, seq = seq0 + r;
     const bool valid = seq < g.NSEQ;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -304,26 +348,36 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
           const int slot = gidx & 1;
           ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
           ptx::tc_fence_after();
+          tl_mark(tl, t, 1, c, 0);
           float hv[16];
+          uint32_t a0[32], a1[32];
+          ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64), a0);
+          ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64 + 32), a1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));  // the accumulator is in registers: slot free
+          tl_mark(tl, t, 1, c, 1);
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 128 + e * 64);
+          if (g.dbg & 1u) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t a[32];
-            ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64 + half * 32), a);
-            ptx::tmem_ld_wait();
-            if (half == 1) {
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
-            }
-            const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 128 + e * 64 + half * 32);
+            for (int u = 0; u < 16; ++u) hv[u] = 1e-6f * __uint_as_float(u < 8 ? a0[4 * u] : a1[4 * (u - 8)]);
+          } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 bb = bp[u];
-              lstm_cell(fmaf(__uint_as_float(a[4 * u]), sc.inv_g, bb.x), fmaf(__uint_as_float(a[4 * u + 1]), sc.inv_g, bb.y),
-                        fmaf(__uint_as_float(a[4 * u + 2]), sc.inv_g, bb.z), fmaf(__uint_as_float(a[4 * u + 3]), sc.inv_g, bb.w),
-                        cst[c][half * 8 + u], hv[half * 8 + u]);
-            }
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = bp[u];
+            lstm_cell(fmaf(__uint_as_float(a0[4 * u]), sg, bb.x), fmaf(__uint_as_float(a0[4 * u + 1]), sg, bb.y),
+                      fmaf(__uint_as_float(a0[4 * u + 2]), sg2, bb.z), fmaf(__uint_as_float(a0[4 * u + 3]), sg, bb.w), cst[c][u], hv[u]);
           }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = bp[8 + u];
+            lstm_cell(fmaf(__uint_as_float(a1[4 * u]), sg, bb.x), fmaf(__uint_as_float(a1[4 * u + 1]), sg, bb.y),
+                      fmaf(__uint_as_float(a1[4 * u + 2]), sg2, bb.z), fmaf(__uint_as_float(a1[4 * u + 3]), sg, bb.w), cst[c][8 + u],
+                      hv[8 + u]);
+          }
+          }
+          tl_mark(tl, t, 1, c, 2);
           // h_t pieces for the next step: units 32c + 16e + [0,16) -> 8 packed columns of the hi image, 8 of the lo image
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -334,6 +388,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->hfull[t & 1]));
+          tl_mark(tl, t, 1, c, 3);
           if (g.hout && valid) {
             float4* dst = reinterpret_cast<float4*>(g.hout + ((size_t)seq * T + ti) * (2 * H) + dir * H + c * 32 + e * 16);
 #pragma unroll
@@ -347,23 +402,53 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
         const int slot = gidx & 1;
         ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
         ptx::tc_fence_after();
+        tl_mark(tl, t, 1, 4, 0);
+        // this warp's 32 rows x (Fo/2) columns, in pieces of 32 (or 16) columns: registers (thread = row) -> swizzled shared
+        // staging -> global with 8 (4) consecutive lanes covering one row's 128 (64) contiguous bytes
         const int half_cols = g.Fo >> 1;
-        float* dst = g.P + (((size_t)dir * g.NSEQ + (valid ? seq : 0)) * T + tp) * g.Fo + e * half_cols;
-        for (int c0 = 0; c0 < half_cols; c0 += 16) {
-          uint32_t a[16];
-          ptx::tmem_ld16(tmem + lane_off + (uint32_t)(slot * 128 + e * half_cols + c0), a);
+        float4* pst = reinterpret_cast<float4*>(smem + PST_OFF + warp * 4096);
+        const size_t row_base = ((size_t)dir * g.NSEQ + seq0 + q * 32) * T + tp;  // + row * T
+        for (int c0 = 0; c0 < half_cols; c0 += 32) {
+          const int w = half_cols - c0 >= 32 ? 32 : 16;
+          uint32_t a[32];
+          if (w == 32) ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * half_cols + c0), a);
+          else ptx::tmem_ld16(tmem + lane_off + (uint32_t)(slot * 128 + e * half_cols + c0), reinterpret_cast<uint32_t(&)[16]>(a));
           ptx::tmem_ld_wait();
-          if (valid) {
+          if (c0 + 32 >= half_cols) {  // last piece: the accumulator is in registers
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+          }
+          if (w == 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pst[lane * 8 + (i ^ (lane & 7))] = make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
+                                                             __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int row = j * 4 + (lane >> 3), qq = lane & 7;
+              const float4 v = pst[row * 8 + (qq ^ (row & 7))];
+              if (seq0 + q * 32 + row < g.NSEQ)
+                *reinterpret_cast<float4*>(g.P + (row_base + (size_t)row * T) * g.Fo + e * half_cols + c0 + qq * 4) = v;
+            }
+          } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(dst + c0)[i] =
-                  make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
-                              __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+              pst[lane * 4 + (i ^ (lane & 3))] = make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
+                                                             __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int row = j * 8 + (lane >> 2), qq = lane & 3;
+              const float4 v = pst[row * 4 + (qq ^ (row & 3))];
+              if (seq0 + q * 32 + row < g.NSEQ)
+                *reinterpret_cast<float4*>(g.P + (row_base + (size_t)row * T) * g.Fo + e * half_cols + c0 + qq * 4) = v;
+            }
           }
+          __syncwarp();
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+        tl_mark(tl, t, 1, 4, 3);
         ++gidx;
       }
     }
@@ -440,7 +525,7 @@ __global__ void __launch_bounds__(1024) k_lstm_scales(const float* __restrict__ 
   }
 }
 
-// grid (n_imgs, 2): one 16 KB stage image per block.  Gate stage (chunk c, slab k): column n = 64 e + 4 u + gate <-> weight row
+// grid (n_imgs, 2): one 16 KB slab image per block.  Gate stage (chunk c, slab k): column n = 64 e + 4 u + gate <-> weight row
 // gate * H + 32 c + 16 e + u, k-element 32 k + kk of [W_ih * w_ih_mul | W_hh * w_hh_mul]; projection stage k: row n = output
 // feature, W_fc[n][dir * H + 32 k + kk] * w_p_mul.  Block (0, dir) also writes the bias table in column order.
 __global__ void __launch_bounds__(256) k_lstm_build(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
@@ -454,13 +539,14 @@ __global__ void __launch_bounds__(256) k_lstm_build(const float* __restrict__ wi
   const float* whh = d ? whh_r : whh_f;
   const LstmScales sc = scp[d];
   const int KSX = F / 32, KSH = H / 32, per = KSX + KSH, n_gate = KSH * per;
-  uint8_t* dst = img + ((size_t)d * n_imgs + idx) * STAGE_BYTES;
+  uint8_t* dst = img + ((size_t)d * n_imgs + idx) * SLAB_BYTES;
   if (idx == 0) {
     const float* bi = d ? bih_r : bih_f;
     const float* bh = d ? bhh_r : bhh_f;
     for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) {
       const int c = i / 128, n = i % 128, row = (n & 3) * H + 32 * c + 16 * (n >> 6) + ((n & 63) >> 2);
-      bias[(size_t)d * 4 * H + i] = bi[row] + bh[row];
+      // stored as the ex2 argument's additive term: -log2(e) b for i, f, o; -2 log2(e) b for g (gate index 2)
+      bias[(size_t)d * 4 * H + i] = (bi[row] + bh[row]) * ((n & 3) == 2 ? -2.8853900817779268f : -1.4426950408889634f);
     }
   }
   const bool is_proj = idx >= n_gate;
@@ -562,12 +648,12 @@ bool lstm_plan(int F, int H, int Fo, LstmPlan& p) {
   p.off_sc = 256;
   p.off_bias = 512;
   p.off_img = 512 + (((size_t)2 * 4 * H * sizeof(float) + 255) / 256) * 256;
-  p.total = p.off_img + (size_t)2 * p.n_imgs * STAGE_BYTES;
-  const size_t fixed = 1024 /*alignment slack*/ + HDR_BYTES + 2048 + (size_t)2 * KSX * 8192;
+  p.total = p.off_img + (size_t)2 * p.n_imgs * SLAB_BYTES;
+  const size_t fixed = 1024 /*alignment slack*/ + HDR_BYTES + 2048 + (size_t)2 * KSX * 8192 + PSTAGE_BYTES;
   int n_st = (int)((232448 - fixed) / STAGE_BYTES);
   if (n_st > MAX_ST) n_st = MAX_ST;
   if (const char* e = getenv("CTN_LSTM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < n_st) n_st = v; }
-  if (n_st < 3) return false;
+  if (n_st < 2) return false;
   p.n_st = n_st;
   p.smem = fixed + (size_t)n_st * STAGE_BYTES;
   return true;
@@ -587,6 +673,13 @@ int launch_bilstm(const LstmArgs& a, size_t smem, cudaStream_t st) {
 }
 
 }  // namespace
+
+// debug: copies the timeline probe (see g_lstm_tl) to the host; n <= 160
+extern "C" int ctn_debug_lstm_timeline(unsigned long long* out, int n) {
+  if (!out || n <= 0 || n > 160) return CTN_EINVAL;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_lstm_tl, sizeof(unsigned long long) * n);
+  return e == cudaSuccess ? CTN_OK : (int)e;
+}
 
 extern "C" int ctn_bilstm_supported(int F, int H, int Fo) {
   LstmPlan p;
@@ -633,6 +726,8 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   LstmArgs a;
   a.z = z; a.P = P; a.hout = hout; a.img = img; a.bias = bias; a.sc = sc;
   a.NSEQ = NSEQ; a.T = T; a.Fo = w_fc ? Fo : 32; a.n_imgs = p.n_imgs; a.n_st = p.n_st; a.has_proj = w_fc ? 1 : 0;
+  a.dbg = 0;
+  if (const char* e = getenv("CTN_LSTM_DBG")) a.dbg = (uint32_t)atoi(e);
   int rc = CTN_EUNSUPPORTED;
   const int NCH = H / 32, KSX = F / 32;
 #define CTN_LSTM_CASE(nch, ksx) if (NCH == nch && KSX == ksx) rc = launch_bilstm<nch, ksx>(a, p.smem, st);

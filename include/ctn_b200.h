@@ -188,6 +188,7 @@ int ctn_dprnn_norm_res_fwd(const float* Y, const float* R, const float* gamma, c
  * output itself (forward direction in [:H], reverse in [H:]).  Envelope: F, H in {32,64,128}, Fo in {32,64,96,128}
  * (ctn_bilstm_supported); workspace >= ctn_bilstm_workspace_bytes(F,H,Fo), 256-byte aligned. */
 int ctn_bilstm_supported(int F, int H, int Fo);
+int ctn_debug_lstm_timeline(unsigned long long* out, int n); /* debug: cycle stamps of one CTA (CTN_LSTM_DBG=16), tools/lstm_time.py */
 size_t ctn_bilstm_workspace_bytes(int F, int H, int Fo);
 int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H, const float* const* w, const float* w_fc, int Fo, float* P,
                         float* hout, void* workspace, size_t workspace_bytes, ctn_stream_t stream);
