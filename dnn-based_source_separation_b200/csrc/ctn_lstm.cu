@@ -459,6 +459,405 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
   if (warp == 8) ptx::tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================================
+// 2-CTA form.  A cluster of two CTAs shares the 128 sequences of one direction: CTA `rank` owns hidden units
+// [rank H/2, (rank+1) H/2) -- their gate columns (CH = H/64 chunks), their cell state, and half of the projection's output
+// features -- so both the tensor-core time and the sigmoid/tanh time of a step halve, and twice as many SMs work on the
+// (small) cfg4 batch.  Each step the two CTAs exchange their halves of h_t:
+//   * own half: TMEM A operand, written by the epilogue with tcgen05.st as in the 1-CTA kernel;
+//   * the SAME pieces are also stored to a shared-memory staging slab in operand layout (K-major SWIZZLE_64B, 128 x 32 k,
+//     hi + lo = 16 KB per chunk) and a sender warp pushes each slab into the peer's shared memory with one bulk
+//     shared::cta -> shared::cluster copy that completes on the PEER's mbarrier (complete_tx): the peer's MMAs read it as a
+//     shared-memory A operand, async proxy end to end.
+//   * buffer reuse: the peer's in-buffer b is overwritten every other step; the reader side says when it is done with it by a
+//     tcgen05.commit multicast onto the sender's `pfree[b]` barrier (arrives when the reading MMAs have completed).
+// x_t now lives in TMEM too (the x producers own one lane each): shared memory holds only weights (ring), the two exchange
+// buffers and the store staging.  K order of a gate chunk: [x | own h | peer h] -- the peer's half arrives last.
+// TMEM columns: [0,256) accumulators, [256,384) own-h buffers (64 each: hi +0, lo +32), [384,512) x (hi +0, lo +64).
+struct PairHdr {
+  uint64_t bfull[MAX_ST], bempty[MAX_ST];
+  uint64_t accfull[2], accempty[2];
+  uint64_t hfull[2];
+  uint64_t xfull, xempty;
+  uint64_t outfull[2][2];  // [buffer][piece]: the 8 epilogue warps -> sender warp
+  uint64_t pin[2][2];      // [buffer][piece]: the peer's piece has landed in my in-buffer (transaction bytes)
+  uint64_t pfree[2];       // the PEER no longer reads ITS in-buffer b (arrives from the peer's tcgen05.commit)
+  uint32_t tmem_base;
+};
+static_assert(sizeof(PairHdr) <= HDR_BYTES, "header");
+constexpr int PAIR_MAX_ST = 8;
+
+template <int NCH, int KSX>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs g) {
+  constexpr int CH = NCH / 2, H = 32 * NCH, HL = 32 * CH, F = 32 * KSX, GSL = KSX + NCH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  PairHdr* hdr = reinterpret_cast<PairHdr*>(smem);
+  float* s_bias = reinterpret_cast<float*>(smem + HDR_BYTES);  // 4 * HL floats (<= 1 KB)
+  constexpr uint32_t PST_OFF = 2 * HDR_BYTES;
+  const uint32_t out_off = PST_OFF + 256u * (uint32_t)g.Fo;     // store staging: 8 warps x 32 rows x Fo/4 floats
+  const uint32_t in_off = out_off + 2u * CH * SLAB_BYTES, ring_off = in_off + 2u * CH * SLAB_BYTES;
+  const uint32_t out0 = base + out_off, in0 = base + in_off, ring0 = base + ring_off;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank(), peer = rank ^ 1;
+  const int dir = blockIdx.y, seq0 = (int)(blockIdx.x >> 1) * LM;
+  const int T = g.T;
+  const bool proj = g.has_proj != 0;
+  const LstmScales sc = g.sc[dir];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.n_st; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->bfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->bempty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&hdr->accfull[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&hdr->accempty[i]), 8);
+      ptx::mbar_init(ptx::smem_u32(&hdr->hfull[i]), 8 * CH);
+      ptx::mbar_init(ptx::smem_u32(&hdr->pfree[i]), 1);
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(ptx::smem_u32(&hdr->outfull[i][c]), 8);
+        ptx::mbar_init(ptx::smem_u32(&hdr->pin[i][c]), 1);
+      }
+    }
+    ptx::mbar_init(ptx::smem_u32(&hdr->xfull), 4);
+    ptx::mbar_init(ptx::smem_u32(&hdr->xempty), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(ptx::smem_u32(&hdr->tmem_base), 512);
+  for (int i = threadIdx.x; i < 4 * HL; i += blockDim.x) s_bias[i] = __ldg(g.bias + (size_t)(dir * 2 + rank) * 4 * HL + i);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  ptx::cluster_sync_all();  // both CTAs' barriers exist before any remote copy / arrive / commit
+  const uint32_t tmem = hdr->tmem_base;
+  const uint32_t tm_h0 = tmem + 256u, tm_x = tmem + 384u;
+
+  if (warp >= 8 && warp < 12) reg_dec<REGS_CTRL>();
+  if (warp == 9) {
+    // ===================================== WEIGHT LOADER ====================================================
+    if (ptx::elect_one()) {
+      const uint8_t* img = g.img + (size_t)(dir * 2 + rank) * g.n_imgs * SLAB_BYTES;
+      int s = 0;
+      uint32_t ph = 0;
+      auto load = [&](int idx, uint32_t bytes) {
+        ptx::mbar_wait(ptx::smem_u32(&hdr->bempty[s]), ph ^ 1u);
+        const uint32_t fb = ptx::smem_u32(&hdr->bfull[s]);
+        ptx::mbar_arrive_expect_tx(fb, bytes);
+        if (!(g.dbg & 4u)) ptx::bulk_g2s(ring0 + (uint32_t)s * SLAB_BYTES, img + (size_t)idx * SLAB_BYTES, bytes, fb);
+        else asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
+        if (++s == g.n_st) { s = 0; ph ^= 1u; }
+      };
+      for (int t = 0; t <= T; ++t) {
+        if (t < T)
+          for (int c = 0; c < CH; ++c)
+            for (int k = 0; k < (t == 0 ? KSX : GSL); ++k) load(c * GSL + k, SLAB_BYTES);  // h_{-1} = 0: no h slabs at t = 0
+        if (proj && t >= 1)
+          for (int k = 0; k < NCH; ++k) load(CH * GSL + k, (uint32_t)g.Fo * 64u);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===================================== MMA ISSUER =======================================================
+    if (ptx::elect_one()) {
+      const bool do_mma = !(g.dbg & 2u);
+      const uint64_t d_t = ptx::make_smem_desc(0, 16u, 512u, 4u);
+      const uint32_t idesc_g = ptx::make_idesc_f16(LM, 128, 0, 0), idesc_p = ptx::make_idesc_f16(LM, g.Fo >> 1, 0, 0);
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < CH; ++c) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&hdr->pin[b][c]), SLAB_BYTES);
+      int s = 0, gidx = 0;
+      uint32_t ph = 0;
+      auto acquire = [&]() -> uint32_t {
+        ptx::mbar_wait(ptx::smem_u32(&hdr->bfull[s]), ph);
+        ptx::tc_fence_after();
+        return (ring0 + (uint32_t)s * SLAB_BYTES) >> 4;
+      };
+      auto release = [&]() {
+        ptx::mma_commit(ptx::smem_u32(&hdr->bempty[s]));
+        if (++s == g.n_st) { s = 0; ph ^= 1u; }
+      };
+      // three passes of one 32-k slab: A pieces either in TMEM (taddr of the hi piece, lo `a_lo_off` columns further) ...
+      auto slab_ts = [&](uint32_t d_tmem, uint32_t a_hi0, uint32_t a_lo_off, uint32_t w_hi, uint32_t w_lo, uint32_t idesc, bool first) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (!do_mma) break;
+          const uint32_t a_hi = a_hi0 + (uint32_t)kk * 8u, a_lo = a_hi + a_lo_off;
+          ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+          ptx::mma_f16_ts(d_tmem, a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc, 1u);
+          ptx::mma_f16_ts(d_tmem, a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc, 1u);
+        }
+      };
+      // ... or in shared memory (descriptor address >> 4 of the hi image, lo image 8 KB further)
+      auto slab_ss = [&](uint32_t d_tmem, uint32_t a_hi0, uint32_t w_hi, uint32_t w_lo, uint32_t idesc, bool first) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (!do_mma) break;
+          const uint32_t a_hi = a_hi0 + (uint32_t)kk * 2u, a_lo = a_hi + (8192u >> 4);
+          ptx::mma_f16(d_tmem, d_t | (uint64_t)a_hi, d_t | (uint64_t)(w_hi + kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+          ptx::mma_f16(d_tmem, d_t | (uint64_t)a_lo, d_t | (uint64_t)(w_hi + kk * 2), idesc, 1u);
+          ptx::mma_f16(d_tmem, d_t | (uint64_t)a_hi, d_t | (uint64_t)(w_lo + kk * 2), idesc, 1u);
+        }
+      };
+      for (int t = 0; t <= T; ++t) {
+        const int hb = (t + 1) & 1;  // buffer index of h_{t-1}
+        const uint32_t h_own = tm_h0 + (uint32_t)hb * 64u, h_peer = (in0 + (uint32_t)hb * CH * SLAB_BYTES) >> 4;
+        bool h_ready = false;
+        auto need_h = [&]() {
+          if (h_ready) return;
+          const uint32_t par = (uint32_t)((t - 1) >> 1) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->hfull[hb]), par);
+          for (int c = 0; c < CH; ++c) {
+            ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->pin[hb][c]), par);
+            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&hdr->pin[hb][c]), SLAB_BYTES);  // arm the next use (h_{t+1})
+          }
+          ptx::tc_fence_after();
+          h_ready = true;
+        };
+        if (t < T) {
+#pragma unroll 1
+          for (int c = 0; c < CH; ++c) {
+            const int slot = gidx & 1;
+            ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+            if (c == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xfull), (uint32_t)t & 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+#pragma unroll 1
+            for (int k = 0; k < KSX; ++k) {
+              const uint32_t w_hi = acquire();
+              slab_ts(d_tmem, tm_x + (uint32_t)k * 16u, 64u, w_hi, w_hi + (8192u >> 4), idesc_g, k == 0);
+              release();
+            }
+            if (c == CH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->xempty));  // x_t has been consumed
+            if (t > 0) {
+              need_h();
+#pragma unroll 1
+              for (int k = 0; k < CH; ++k) {
+                const uint32_t w_hi = acquire();
+                slab_ts(d_tmem, h_own + (uint32_t)k * 16u, 32u, w_hi, w_hi + (8192u >> 4), idesc_g, false);
+                release();
+              }
+#pragma unroll 1
+              for (int k = 0; k < CH; ++k) {
+                const uint32_t w_hi = acquire();
+                slab_ss(d_tmem, h_peer + (uint32_t)k * (SLAB_BYTES >> 4), w_hi, w_hi + (8192u >> 4), idesc_g, false);
+                release();
+              }
+            }
+            ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+            ++gidx;
+          }
+        }
+        if (proj && t >= 1) {
+          const int slot = gidx & 1;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
+          need_h();
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
+          const uint32_t lo_off = ((uint32_t)g.Fo * 32u) >> 4;  // hi image: Fo/2 rows x 64 B
+#pragma unroll 1
+          for (int k = 0; k < NCH; ++k) {
+            const uint32_t w_hi = acquire();
+            if (k < CH) slab_ts(d_tmem, h_own + (uint32_t)k * 16u, 32u, w_hi, w_hi + lo_off, idesc_p, k == 0);
+            else slab_ss(d_tmem, h_peer + (uint32_t)(k - CH) * (SLAB_BYTES >> 4), w_hi, w_hi + lo_off, idesc_p, false);
+            release();
+          }
+          ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+          ++gidx;
+        }
+        // every MMA that reads in-buffer hb has been issued: when they complete the peer may overwrite it (with h_{t+1})
+        if (t >= 1 && t + 1 < T) ptx::mma_commit_multicast(ptx::smem_u32(&hdr->pfree[hb]), (uint16_t)(1u << peer));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ===================================== SENDER ===========================================================
+    if (ptx::elect_one()) {
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        if (t >= 2) ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->pfree[b]), (uint32_t)((t >> 1) - 1) & 1u);
+        for (int c = 0; c < CH; ++c) {
+          ptx::mbar_wait(ptx::smem_u32(&hdr->outfull[b][c]), (uint32_t)(t >> 1) & 1u);
+          const uint32_t off = (uint32_t)(b * CH + c) * SLAB_BYTES;
+          ptx::bulk_s2peer(in0 + off, out0 + off, SLAB_BYTES, ptx::smem_u32(&hdr->pin[b][c]), (uint32_t)peer);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 12) {
+    // ===================================== x PRODUCERS ======================================================
+    // thread = one sequence = one TMEM lane: x_t -> scaled fp16 hi / lo pieces -> tcgen05.st into the x operand columns
+    reg_dec<REGS_PROD>();
+    const int r = (warp - 12) * 32 + lane, seq = seq0 + r;
+    const bool valid = seq < g.NSEQ;
+    const float4* zrow = reinterpret_cast<const float4*>(g.z + (size_t)(valid ? seq : 0) * T * F);
+    const uint32_t lane_off = (uint32_t)((warp - 12) * 32) << 16;
+    float4 v[F / 4];
+    auto fetch = [&](int t) {
+      const int ti = dir ? T - 1 - t : t;
+#pragma unroll
+      for (int i = 0; i < F / 4; ++i)
+        v[i] = (valid && !(g.dbg & 8u)) ? __ldg(zrow + (size_t)ti * (F / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(0);
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) {
+        ptx::mbar_wait(ptx::smem_u32(&hdr->xempty), (uint32_t)(t - 1) & 1u);
+        ptx::tc_fence_after();
+      }
+#pragma unroll
+      for (int i = 0; i < F / 16; ++i) {  // 16 k-elements = 8 packed columns per store
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = v[i * 4 + j];
+          ptx::split_f16x2(a.x * sc.x_mul, a.y * sc.x_mul, hi[2 * j], lo[2 * j]);
+          ptx::split_f16x2(a.z * sc.x_mul, a.w * sc.x_mul, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        ptx::tmem_st8(tm_x + lane_off + (uint32_t)i * 8u, hi);
+        ptx::tmem_st8(tm_x + lane_off + 64u + (uint32_t)i * 8u, lo);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->xfull));
+      if (t + 1 < T) fetch(t + 1);
+    }
+  } else if (warp < 8) {
+    // ===================================== EPILOGUE =========================================================
+    reg_inc<REGS_EPI>();
+    const int q = warp & 3, e = warp >> 2;
+    const int r = q * 32 + lane, seq = seq0 + r;
+    const bool valid = seq < g.NSEQ;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float sg = -1.4426950408889634f * sc.inv_g, sg2 = 2.f * sg;
+    const uint32_t st_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u, sw = (uint32_t)(r >> 1) & 3u;
+    float cst[CH][16];
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int u = 0; u < 16; ++u) cst[c][u] = 0.f;
+    int gidx = 0;
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        const int ti = dir ? T - 1 - t : t;
+        const int b = t & 1;
+        const uint32_t h_cur = tm_h0 + (uint32_t)b * 64u;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int slot = gidx & 1;
+          ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
+          ptx::tc_fence_after();
+          float hv[16];
+          uint32_t a0[32], a1[32];
+          ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64), a0);
+          ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64 + 32), a1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 128 + e * 64);
+          if (g.dbg & 1u) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) hv[u] = 1e-6f * __uint_as_float(u < 8 ? a0[4 * u] : a1[4 * (u - 8)]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 bb = bp[u];
+              lstm_cell(fmaf(__uint_as_float(a0[4 * u]), sg, bb.x), fmaf(__uint_as_float(a0[4 * u + 1]), sg, bb.y),
+                        fmaf(__uint_as_float(a0[4 * u + 2]), sg2, bb.z), fmaf(__uint_as_float(a0[4 * u + 3]), sg, bb.w), cst[c][u], hv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 bb = bp[8 + u];
+              lstm_cell(fmaf(__uint_as_float(a1[4 * u]), sg, bb.x), fmaf(__uint_as_float(a1[4 * u + 1]), sg, bb.y),
+                        fmaf(__uint_as_float(a1[4 * u + 2]), sg2, bb.z), fmaf(__uint_as_float(a1[4 * u + 3]), sg, bb.w), cst[c][8 + u],
+                        hv[8 + u]);
+            }
+          }
+          // h_t pieces: (1) the peer's copy -- operand-layout staging slab, units 16e + [0,16) of this chunk = 16-byte chunks 2e, 2e+1
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ptx::split_f16x2(hv[2 * i] * 16384.f, hv[2 * i + 1] * 16384.f, hi[i], lo[i]);
+          uint8_t* piece = smem + out_off + (uint32_t)(b * CH + c) * SLAB_BYTES + st_off;
+          *reinterpret_cast<uint4*>(piece + (((uint32_t)(2 * e) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(piece + (((uint32_t)(2 * e + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(piece + 8192 + (((uint32_t)(2 * e) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(piece + 8192 + (((uint32_t)(2 * e + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          ptx::fence_proxy_async_smem();
+          // (2) my own copy: TMEM A-operand columns of buffer b
+          ptx::tmem_st8(h_cur + lane_off + (uint32_t)(c * 16 + e * 8), hi);
+          ptx::tmem_st8(h_cur + lane_off + 32u + (uint32_t)(c * 16 + e * 8), lo);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(ptx::smem_u32(&hdr->outfull[b][c]));
+            ptx::mbar_arrive(ptx::smem_u32(&hdr->hfull[b]));
+          }
+          if (g.hout && valid) {
+            float4* dst = reinterpret_cast<float4*>(g.hout + ((size_t)seq * T + ti) * (2 * H) + dir * H + (rank * CH + c) * 32 + e * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
+          }
+          ++gidx;
+        }
+      }
+      if (proj && t >= 1) {
+        const int tp = dir ? T - t : t - 1;  // time index of h_{t-1}
+        const int slot = gidx & 1;
+        ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
+        ptx::tc_fence_after();
+        // this CTA's Fo/2 output features; this warp: 32 rows x QC = Fo/4 of them (16 or 32)
+        const int QC = g.Fo >> 2;
+        float4* pst = reinterpret_cast<float4*>(smem + PST_OFF + warp * (32 * QC * 4));
+        const size_t row_base = ((size_t)dir * g.NSEQ + seq0 + q * 32) * T + tp;
+        const int col0 = rank * (g.Fo >> 1) + e * QC;
+        uint32_t a[32];
+        if (QC == 32) ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * QC), a);
+        else ptx::tmem_ld16(tmem + lane_off + (uint32_t)(slot * 128 + e * QC), reinterpret_cast<uint32_t(&)[16]>(a));
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+        if (QC == 32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pst[lane * 8 + (i ^ (lane & 7))] = make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
+                                                           __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = j * 4 + (lane >> 3), qq = lane & 7;
+            const float4 v = pst[row * 8 + (qq ^ (row & 7))];
+            if (seq0 + q * 32 + row < g.NSEQ) *reinterpret_cast<float4*>(g.P + (row_base + (size_t)row * T) * g.Fo + col0 + qq * 4) = v;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pst[lane * 4 + (i ^ (lane & 3))] = make_float4(__uint_as_float(a[4 * i]) * sc.inv_p, __uint_as_float(a[4 * i + 1]) * sc.inv_p,
+                                                           __uint_as_float(a[4 * i + 2]) * sc.inv_p, __uint_as_float(a[4 * i + 3]) * sc.inv_p);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = j * 8 + (lane >> 2), qq = lane & 3;
+            const float4 v = pst[row * 4 + (qq ^ (row & 3))];
+            if (seq0 + q * 32 + row < g.NSEQ) *reinterpret_cast<float4*>(g.P + (row_base + (size_t)row * T) * g.Fo + col0 + qq * 4) = v;
+          }
+        }
+        __syncwarp();
+        ++gidx;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  ptx::cluster_sync_all();  // nobody leaves while the peer may still copy into / arrive on this CTA
+  if (warp == 8) ptx::tmem_dealloc(tmem, 512);
+}
+
 // ---- operand preparation -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_absmax_flat(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
   float m = 0.f;
@@ -525,49 +924,52 @@ __global__ void __launch_bounds__(1024) k_lstm_scales(const float* __restrict__ 
   }
 }
 
-// grid (n_imgs, 2): one 16 KB slab image per block.  Gate stage (chunk c, slab k): column n = 64 e + 4 u + gate <-> weight row
-// gate * H + 32 c + 16 e + u, k-element 32 k + kk of [W_ih * w_ih_mul | W_hh * w_hh_mul]; projection stage k: row n = output
-// feature, W_fc[n][dir * H + 32 k + kk] * w_p_mul.  Block (0, dir) also writes the bias table in column order.
+// grid (n_imgs, 2 directions, ranks): one 16 KB slab image per block.  Gate slab (chunk c, slab k): column n = 64 e + 4 u + gate <->
+// weight row gate * H + 32 cg + 16 e + u (cg = global chunk), k-elements of [W_ih * w_ih_mul | W_hh * w_hh_mul]; projection slab k: row n =
+// output feature, W_fc[n][dir * H + ...] * w_p_mul.  1-CTA kernel (ranks = 1): chunks 0..KSH-1, h slabs in natural order.  2-CTA
+// kernel (ranks = 2): CTA `rank` gets chunks rank*CH + [0,CH), its h slabs ordered [own half | peer half], and rows
+// rank*Fo/2 + [0,Fo/2) of the projection.  Block (0, dir, rank) also writes the bias table (pre-scaled ex2 arguments).
 __global__ void __launch_bounds__(256) k_lstm_build(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
                                                     const float* __restrict__ bih_f, const float* __restrict__ bhh_f,
                                                     const float* __restrict__ wih_r, const float* __restrict__ whh_r,
                                                     const float* __restrict__ bih_r, const float* __restrict__ bhh_r,
                                                     const float* __restrict__ wfc, int F, int H, int Fo, const LstmScales* __restrict__ scp,
                                                     uint8_t* __restrict__ img, float* __restrict__ bias, int n_imgs) {
-  const int d = blockIdx.y, idx = blockIdx.x;
+  const int d = blockIdx.y, idx = blockIdx.x, rank = blockIdx.z, R = gridDim.z;
   const float* wih = d ? wih_r : wih_f;
   const float* whh = d ? whh_r : whh_f;
   const LstmScales sc = scp[d];
-  const int KSX = F / 32, KSH = H / 32, per = KSX + KSH, n_gate = KSH * per;
-  uint8_t* dst = img + ((size_t)d * n_imgs + idx) * SLAB_BYTES;
+  const int KSX = F / 32, KSH = H / 32, CH = KSH / R, per = KSX + KSH, n_gate = CH * per;
+  uint8_t* dst = img + ((size_t)(d * R + rank) * n_imgs + idx) * SLAB_BYTES;
+  auto hslab = [&](int kh) { return R == 1 ? kh : (kh < CH ? rank * CH + kh : (1 - rank) * CH + (kh - CH)); };
   if (idx == 0) {
     const float* bi = d ? bih_r : bih_f;
     const float* bh = d ? bhh_r : bhh_f;
-    for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) {
-      const int c = i / 128, n = i % 128, row = (n & 3) * H + 32 * c + 16 * (n >> 6) + ((n & 63) >> 2);
+    for (int i = threadIdx.x; i < 128 * CH; i += blockDim.x) {
+      const int c = i / 128, n = i % 128, row = (n & 3) * H + 32 * (rank * CH + c) + 16 * (n >> 6) + ((n & 63) >> 2);
       // stored as the ex2 argument's additive term: -log2(e) b for i, f, o; -2 log2(e) b for g (gate index 2)
-      bias[(size_t)d * 4 * H + i] = (bi[row] + bh[row]) * ((n & 3) == 2 ? -2.8853900817779268f : -1.4426950408889634f);
+      bias[(size_t)(d * R + rank) * 128 * CH + i] = (bi[row] + bh[row]) * ((n & 3) == 2 ? -2.8853900817779268f : -1.4426950408889634f);
     }
   }
   const bool is_proj = idx >= n_gate;
-  const int rows = is_proj ? Fo : 128;
+  const int rows = is_proj ? Fo / R : 128;
   const uint32_t lo_base = (uint32_t)rows * 64u;
   const int c = is_proj ? 0 : idx / per, k = is_proj ? idx - n_gate : idx % per;
   for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {  // one pair of k-elements per iteration
     const int n = i / 16, kk = (i % 16) * 2;
     float v0, v1;
     if (is_proj) {
-      const float* p = wfc + (size_t)n * 2 * H + d * H + 32 * k + kk;
+      const float* p = wfc + (size_t)(rank * (Fo / R) + n) * 2 * H + d * H + 32 * hslab(k) + kk;
       v0 = p[0] * sc.w_p_mul;
       v1 = p[1] * sc.w_p_mul;
     } else {
-      const int row = (n & 3) * H + 32 * c + 16 * (n >> 6) + ((n & 63) >> 2);
+      const int row = (n & 3) * H + 32 * (rank * CH + c) + 16 * (n >> 6) + ((n & 63) >> 2);
       if (k < KSX) {
         const float* p = wih + (size_t)row * F + 32 * k + kk;
         v0 = p[0] * sc.w_ih_mul;
         v1 = p[1] * sc.w_ih_mul;
       } else {
-        const float* p = whh + (size_t)row * H + 32 * (k - KSX) + kk;
+        const float* p = whh + (size_t)row * H + 32 * hslab(k - KSX) + kk;
         v0 = p[0] * sc.w_hh_mul;
         v1 = p[1] * sc.w_hh_mul;
       }
@@ -637,25 +1039,37 @@ __global__ void __launch_bounds__(256) k_norm_res2(const float* __restrict__ P0,
 }
 
 struct LstmPlan {
-  int n_imgs, n_st;
+  int n_imgs, n_st, pair;
   size_t off_sc, off_bias, off_img, total, smem;
 };
-bool lstm_plan(int F, int H, int Fo, LstmPlan& p) {
+bool lstm_plan(int F, int H, int Fo, LstmPlan& p, bool allow_pair = true) {
   if (!(H == 32 || H == 64 || H == 128) || !(F == 32 || F == 64 || F == 128)) return false;
   if (Fo != 0 && (Fo % 32 != 0 || Fo < 32 || Fo > 128)) return false;
   const int KSX = F / 32, KSH = H / 32;
-  p.n_imgs = KSH * (KSX + KSH) + KSH;
+  // 2-CTA form: H >= 64 (each CTA needs whole 32-unit chunks) and Fo/4 a multiple of 16 (store granularity of a warp)
+  p.pair = (allow_pair && KSH >= 2 && (Fo == 0 || Fo == 64 || Fo == 128)) ? 1 : 0;
+  if (const char* e = getenv("CTN_LSTM_PAIR")) p.pair = p.pair && atoi(e) != 0;
+  const int R = p.pair ? 2 : 1, CH = KSH / R;
+  p.n_imgs = CH * (KSX + KSH) + KSH;
   p.off_sc = 256;
   p.off_bias = 512;
   p.off_img = 512 + (((size_t)2 * 4 * H * sizeof(float) + 255) / 256) * 256;
-  p.total = p.off_img + (size_t)2 * p.n_imgs * SLAB_BYTES;
-  const size_t fixed = 1024 /*alignment slack*/ + HDR_BYTES + 2048 + (size_t)2 * KSX * 8192 + PSTAGE_BYTES;
-  int n_st = (int)((232448 - fixed) / STAGE_BYTES);
-  if (n_st > MAX_ST) n_st = MAX_ST;
+  p.total = p.off_img + (size_t)2 * R * p.n_imgs * SLAB_BYTES;
+  size_t fixed;
+  int n_st;
+  if (p.pair) {
+    fixed = 1024 /*alignment slack*/ + 2 * HDR_BYTES + (size_t)256 * (Fo ? Fo : 64) + (size_t)4 * CH * SLAB_BYTES;
+    n_st = (int)((232448 - fixed) / SLAB_BYTES);
+    if (n_st > PAIR_MAX_ST) n_st = PAIR_MAX_ST;
+  } else {
+    fixed = 1024 + HDR_BYTES + 2048 + (size_t)2 * KSX * 8192 + PSTAGE_BYTES;
+    n_st = (int)((232448 - fixed) / STAGE_BYTES);
+    if (n_st > MAX_ST) n_st = MAX_ST;
+  }
   if (const char* e = getenv("CTN_LSTM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < n_st) n_st = v; }
   if (n_st < 2) return false;
   p.n_st = n_st;
-  p.smem = fixed + (size_t)n_st * STAGE_BYTES;
+  p.smem = fixed + (size_t)n_st * (p.pair ? SLAB_BYTES : STAGE_BYTES);
   return true;
 }
 
@@ -670,6 +1084,31 @@ int launch_bilstm(const LstmArgs& a, size_t smem, cudaStream_t st) {
   }
   k_bilstm<NCH, KSX><<<dim3((a.NSEQ + LM - 1) / LM, 2), LSTM_THREADS, smem, st>>>(a);
   return CTN_OK;
+}
+
+template <int NCH, int KSX>
+int launch_bilstm_pair(const LstmArgs& a, size_t smem, cudaStream_t st) {
+  static bool done[CTN_MAX_DEVICES] = {};
+  const int dev = ctn_current_device();
+  if (!done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_bilstm_pair<NCH, KSX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    done[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * ((a.NSEQ + LM - 1) / LM), 2);
+  cfg.blockDim = dim3(LSTM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_bilstm_pair<NCH, KSX>, a);
+  return e == cudaSuccess ? CTN_OK : (int)e;
 }
 
 }  // namespace
@@ -702,6 +1141,13 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   LstmPlan p;
   if (!lstm_plan(F, H, w_fc ? Fo : 0, p)) return CTN_EUNSUPPORTED;
   if (workspace_bytes < p.total) return CTN_EWORKSPACE;
+  if (p.pair && !getenv("CTN_LSTM_PAIR")) {
+    // the 2-CTA form halves the time of a step but needs twice the CTAs: worth it only while they all fit on the GPU at once
+    static int sms[CTN_MAX_DEVICES] = {};
+    const int dev = ctn_current_device();
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (4 * ((NSEQ + LM - 1) / LM) > sms[dev] && !lstm_plan(F, H, w_fc ? Fo : 0, p, false)) return CTN_EUNSUPPORTED;
+  }
   if ((((uintptr_t)z) | ((uintptr_t)P) | ((uintptr_t)hout) | ((uintptr_t)workspace)) & 15) return CTN_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -721,7 +1167,7 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   k_lstm_scales<<<2, 1024, 0, st>>>(w[0], w[1], w[4], w[5], w_fc, xmax, F, H, Fo, sc);
   CTN_COUNT_LAUNCH();
   const int n_build = w_fc ? p.n_imgs : p.n_imgs - H / 32;
-  k_lstm_build<<<dim3(n_build, 2), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w_fc, F, H, Fo, sc, img, bias, p.n_imgs);
+  k_lstm_build<<<dim3(n_build, 2, p.pair ? 2 : 1), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w_fc, F, H, Fo, sc, img, bias, p.n_imgs);
   CTN_COUNT_LAUNCH();
   LstmArgs a;
   a.z = z; a.P = P; a.hout = hout; a.img = img; a.bias = bias; a.sc = sc;
@@ -731,9 +1177,16 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   int rc = CTN_EUNSUPPORTED;
   const int NCH = H / 32, KSX = F / 32;
 #define CTN_LSTM_CASE(nch, ksx) if (NCH == nch && KSX == ksx) rc = launch_bilstm<nch, ksx>(a, p.smem, st);
-  CTN_LSTM_CASE(1, 1) CTN_LSTM_CASE(2, 1) CTN_LSTM_CASE(2, 2) CTN_LSTM_CASE(4, 1) CTN_LSTM_CASE(4, 2) CTN_LSTM_CASE(4, 4)
-  CTN_LSTM_CASE(1, 2) CTN_LSTM_CASE(1, 4) CTN_LSTM_CASE(2, 4)
+#define CTN_LSTM_PAIR_CASE(nch, ksx) if (NCH == nch && KSX == ksx) rc = launch_bilstm_pair<nch, ksx>(a, p.smem, st);
+  if (p.pair) {
+    CTN_LSTM_PAIR_CASE(2, 1) CTN_LSTM_PAIR_CASE(2, 2) CTN_LSTM_PAIR_CASE(2, 4) CTN_LSTM_PAIR_CASE(4, 1) CTN_LSTM_PAIR_CASE(4, 2)
+    CTN_LSTM_PAIR_CASE(4, 4)
+  } else {
+    CTN_LSTM_CASE(1, 1) CTN_LSTM_CASE(2, 1) CTN_LSTM_CASE(2, 2) CTN_LSTM_CASE(4, 1) CTN_LSTM_CASE(4, 2) CTN_LSTM_CASE(4, 4)
+    CTN_LSTM_CASE(1, 2) CTN_LSTM_CASE(1, 4) CTN_LSTM_CASE(2, 4)
+  }
 #undef CTN_LSTM_CASE
+#undef CTN_LSTM_PAIR_CASE
   if (rc != CTN_OK) return rc;
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();

@@ -99,6 +99,20 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// bulk copy from this CTA's shared memory into the SAME offsets of CTA `rank` of the cluster (distributed shared memory), completing
+// on the mbarrier at `bar` (CTA-relative address) in that CTA: the transfer runs in the async proxy on both sides, so the
+// receiver's tcgen05.mma may read the data right after its mbarrier wait.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_smem, uint32_t src_smem, uint32_t bytes, uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rd, rb;\n\t"
+      "mapa.shared::cluster.u32 rd, %0, %4;\n\t"
+      "mapa.shared::cluster.u32 rb, %3, %4;\n\t"
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [rd], [%1], %2, [rb];\n\t"
+      "}" ::"r"(dst_smem), "r"(src_smem), "r"(bytes), "r"(bar), "r"(rank)
+      : "memory");
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
