@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
     // ===================================== MMA ISSUER =======================================================
     if (ptx::elect_one()) {
       const bool do_mma = !(g.dbg & 2u);
+      const bool tl = (g.dbg & 16u) && blockIdx.x == 0 && blockIdx.y == 0;
       const uint64_t d_t = ptx::make_smem_desc(0, 16u, 512u, 4u);
       const uint32_t idesc_g = ptx::make_idesc_f16(LM, 128, 0, 0), idesc_p = ptx::make_idesc_f16(LM, g.Fo >> 1, 0, 0);
       for (int b = 0; b < 2; ++b)
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
             ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
             if (c == 0) ptx::mbar_wait(ptx::smem_u32(&hdr->xfull), (uint32_t)t & 1u);
             ptx::tc_fence_after();
+            tl_mark(tl, t, 0, c, 0);
             const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
 #pragma unroll 1
             for (int k = 0; k < KSX; ++k) {
@@ -630,8 +632,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
               release();
             }
             if (c == CH - 1) ptx::mma_commit(ptx::smem_u32(&hdr->xempty));  // x_t has been consumed
+            tl_mark(tl, t, 0, c, 1);
             if (t > 0) {
               need_h();
+              tl_mark(tl, t, 0, c, 2);
 #pragma unroll 1
               for (int k = 0; k < CH; ++k) {
                 const uint32_t w_hi = acquire();
@@ -646,6 +650,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
               }
             }
             ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+            tl_mark(tl, t, 0, c, 3);
             ++gidx;
           }
         }
@@ -654,6 +659,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
           ptx::mbar_wait(ptx::smem_u32(&hdr->accempty[slot]), ((uint32_t)(gidx >> 1) & 1u) ^ 1u);
           need_h();
           ptx::tc_fence_after();
+          tl_mark(tl, t, 0, 4, 0);
           const uint32_t d_tmem = tmem + (uint32_t)slot * 128u;
           const uint32_t lo_off = ((uint32_t)g.Fo * 32u) >> 4;  // hi image: Fo/2 rows x 64 B
 #pragma unroll 1
@@ -664,6 +670,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
             release();
           }
           ptx::mma_commit(ptx::smem_u32(&hdr->accfull[slot]));
+          tl_mark(tl, t, 0, 4, 3);
           ++gidx;
         }
         // every MMA that reads in-buffer hb has been issued: when they complete the peer may overwrite it (with h_{t+1})
@@ -732,6 +739,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
     const bool valid = seq < g.NSEQ;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float sg = -1.4426950408889634f * sc.inv_g, sg2 = 2.f * sg;
+    const bool tl = (g.dbg & 16u) && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
     const uint32_t st_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u, sw = (uint32_t)(r >> 1) & 3u;
     float cst[CH][16];
 #pragma unroll
@@ -749,6 +757,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
           const int slot = gidx & 1;
           ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
           ptx::tc_fence_after();
+          tl_mark(tl, t, 1, c, 0);
           float hv[16];
           uint32_t a0[32], a1[32];
           ptx::tmem_ld32(tmem + lane_off + (uint32_t)(slot * 128 + e * 64), a0);
@@ -757,6 +766,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&hdr->accempty[slot]));
+          tl_mark(tl, t, 1, c, 1);
           const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 128 + e * 64);
           if (g.dbg & 1u) {
 #pragma unroll
@@ -776,6 +786,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
                         hv[8 + u]);
             }
           }
+          tl_mark(tl, t, 1, c, 2);
           // h_t pieces: (1) the peer's copy -- operand-layout staging slab, units 16e + [0,16) of this chunk = 16-byte chunks 2e, 2e+1
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -786,16 +797,22 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
           *reinterpret_cast<uint4*>(piece + 8192 + (((uint32_t)(2 * e) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(piece + 8192 + (((uint32_t)(2 * e + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           ptx::fence_proxy_async_smem();
+          tl_mark(tl, t, 1, c + 2, 0);
           // (2) my own copy: TMEM A-operand columns of buffer b
-          ptx::tmem_st8(h_cur + lane_off + (uint32_t)(c * 16 + e * 8), hi);
-          ptx::tmem_st8(h_cur + lane_off + 32u + (uint32_t)(c * 16 + e * 8), lo);
+          if (!(g.dbg & 32u)) {
+            ptx::tmem_st8(h_cur + lane_off + (uint32_t)(c * 16 + e * 8), hi);
+            ptx::tmem_st8(h_cur + lane_off + 32u + (uint32_t)(c * 16 + e * 8), lo);
+          }
+          tl_mark(tl, t, 1, c + 2, 1);
           ptx::tmem_st_wait();
+          tl_mark(tl, t, 1, c + 2, 2);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             ptx::mbar_arrive(ptx::smem_u32(&hdr->outfull[b][c]));
             ptx::mbar_arrive(ptx::smem_u32(&hdr->hfull[b]));
           }
+          tl_mark(tl, t, 1, c, 3);
           if (g.hout && valid) {
             float4* dst = reinterpret_cast<float4*>(g.hout + ((size_t)seq * T + ti) * (2 * H) + dir * H + (rank * CH + c) * 32 + e * 16);
 #pragma unroll
@@ -809,6 +826,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
         const int slot = gidx & 1;
         ptx::mbar_wait(ptx::smem_u32(&hdr->accfull[slot]), (uint32_t)(gidx >> 1) & 1u);
         ptx::tc_fence_after();
+        tl_mark(tl, t, 1, 4, 0);
         // this CTA's Fo/2 output features; this warp: 32 rows x QC = Fo/4 of them (16 or 32)
         const int QC = g.Fo >> 2;
         float4* pst = reinterpret_cast<float4*>(smem + PST_OFF + warp * (32 * QC * 4));
@@ -847,6 +865,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
           }
         }
         __syncwarp();
+        tl_mark(tl, t, 1, 4, 3);
         ++gidx;
       }
     }
