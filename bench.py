@@ -390,6 +390,10 @@ def main():
         for _ in range(max(args.warmup, 3)):
             loss, perm = step_resident()
         launches_per_step = getattr(model, "last_launches", 0) + N.ctn_last_launch_count()
+        if args.config == "cfg4":   # the DPRNN path is made of many entry calls: count one whole step
+            n0 = N.ctn_total_launch_count()
+            step_resident()
+            launches_per_step = int(N.ctn_total_launch_count() - n0)
         torch.cuda.synchronize()
         # ---- timed: device-resident, stage timers OFF ---------------------------------------------------------
         N.ctn_profile_enable(0)
@@ -473,31 +477,51 @@ def main():
         roof["step"] = {"ms": ms / args.steps, "moved_bytes_model": step_bytes,
                         "hbm_frac_on_moved_bytes": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]}
     else:
-        # cfg4: the segment / overlap-add / gLN glue kernels are HBM-bound; the LSTM recurrences (cuDNN) dominate the step
-        F_, K_, P_ = CFG4["sep_bottleneck_channels"], CFG4["sep_chunk_size"], CFG4["sep_hop_size"]
+        # cfg4: the step is 12 bi-LSTM + projection calls (tcgen05 kernel, csrc/ctn_lstm.cu) plus HBM-bound glue (segment, overlap-add,
+        # gLN + residual + path swap).  Dominant kernel = the LSTM: timed alone here at the intra-chunk shape of the step.
+        from ctn_b200.models import dprnn as dprnn_mod
+        F_, K_, P_, H_ = CFG4["sep_bottleneck_channels"], CFG4["sep_chunk_size"], CFG4["sep_hop_size"], CFG4["sep_hidden_channels"]
         Sn = (frames + ((P_ - (frames - K_) % P_) % P_) - K_) // P_ + 1
         state = B * Sn * K_ * F_ * 4.0
-        glue_bytes = 12 * 4 * state + 2 * state + 2 * B * F_ * frames * 4.0   # 12 x (stats read + Y,R read + out write) + segment + overlap-add
-        # the dominant kernel of OUR part of the path, timed alone on tensors of the cfg4 state shape (CUDA events, burst peak applies)
-        Y = torch.randn(B, Sn, K_, F_, device=dev)
-        R0 = torch.randn(B, Sn, K_, F_, device=dev)
-        O_ = torch.empty(B, K_, Sn, F_, device=dev)
-        gam, bet = torch.ones(F_, device=dev), torch.zeros(F_, device=dev)
-        scr = torch.empty(2 * B, dtype=torch.float64, device=dev)
+        glue_bytes = 12 * 5 * state + 2 * state + 2 * B * F_ * frames * 4.0   # 12 x (P0,P1 read twice... see DESIGN 4.7) + segment + overlap-add
+        blk = model.separator.dprnn.net[0].intra_chunk_block
+        z = torch.randn(B * Sn, K_, F_, device=dev)
+        Pbuf = torch.empty(2, B * Sn, K_, F_, device=dev)
+        r_ = blk.rnn
+        ptrs = (N._fp * 8)(*[t_.data_ptr() for t_ in (r_.weight_ih_l0, r_.weight_hh_l0, r_.bias_ih_l0, r_.bias_hh_l0, r_.weight_ih_l0_reverse,
+                                                        r_.weight_hh_l0_reverse, r_.bias_ih_l0_reverse, r_.bias_hh_l0_reverse)])
+        nws = N.ctn_bilstm_workspace_bytes(F_, H_, F_)
+        wsb = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
 
-        def glue():
-            N.check(N.ctn_dprnn_norm_res_fwd(Y.data_ptr(), R0.data_ptr(), gam.data_ptr(), bet.data_ptr(), O_.data_ptr(), B, Sn, K_, F_, 1e-12, 1,
-                                             scr.data_ptr(), N.stream_ptr(dev)), "ctn_dprnn_norm_res_fwd")
-        for _ in range(3):
-            glue()
-        ms_glue, _, _ = cuda_time(glue, 10, torch, D, dev)
-        per_call = 4 * state   # Y read twice (statistics, apply), R read, out written
-        ach = per_call / (ms_glue / 10 * 1e-3) / 1e9
-        roof = {"kernel": "ctn_dprnn_norm_res_fwd (gLN + residual + path swap; 12 calls per step)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
-                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "ms_per_call": ms_glue / 10, "algorithmic_bytes_per_call": per_call,
-                "glue_bytes_per_step": glue_bytes, "glue_ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
-                "note": "our kernels on this path are HBM-bound data movement; the step time is dominated by the 12 cuDNN bi-LSTM recurrences "
-                        "(library code, IEEE fp32 for parity with the reference; ctn_b200.models.dprnn.LSTM_TF32 = True trades parity for speed)"}
+        def lstm_call():
+            N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), B * Sn, K_, F_, H_, ptrs, blk.fc.weight.data_ptr(), F_, Pbuf.data_ptr(), None, wsb.data_ptr(),
+                                          nws, N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
+        native = bool(dprnn_mod.NATIVE_LSTM and N.ctn_bilstm_supported(F_, H_, F_))
+        if native:
+            for _ in range(3):
+                lstm_call()
+            ms_lstm, _, _ = cuda_time(lstm_call, 10, torch, D, dev)
+            ms_lstm /= 10
+            flops = 2.0 * (B * Sn) * K_ * (2.0 * (F_ + H_) * 4 * H_ + 2.0 * H_ * F_)   # both directions: gates + projection
+            ach = flops / (ms_lstm * 1e-3) / 1e12
+            # A/B: the same step with the library recurrence (cuDNN LSTM in IEEE fp32 + library GEMM for the Linear)
+            dprnn_mod.NATIVE_LSTM = False
+            try:
+                with torch.no_grad():
+                    step_resident()
+                    ms_lib, _, _ = cuda_time(step_resident, 2, torch, D, dev)
+            finally:
+                dprnn_mod.NATIVE_LSTM = True
+            roof = {"kernel": "k_bilstm_pair (bi-LSTM recurrence + 2H->F projection, 2-CTA clusters, h in tensor memory; 12 calls per step)",
+                    "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                    "ms_per_call": ms_lstm, "algorithmic_flops_per_call": flops,
+                    "peak_note": "fp16 dense = bf16_tflops_sustained of measured (MEASURED_PEAKS.json); algorithmic flops (the 3-pass hi/lo split issues "
+                                 "3x that); a recurrence: 250 dependent steps per call, " + str(4 * ((B * Sn + 127) // 128)) + " CTAs",
+                    "glue_bytes_per_step": glue_bytes, "glue_ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
+                    "library_lstm_ms_per_step": ms_lib / 2, "native_lstm_ms_per_step": ms / args.steps,
+                    "note": "library_lstm_ms_per_step = the same step with cuDNN's LSTM (IEEE fp32, as parity with the reference needs) + a library GEMM"}
+        else:
+            roof = {"kernel": "cuDNN LSTM (library)", "bound": "tensor", "achieved": None, "peak": tf32_peak, "unit": "TFLOP/s", "frac": None, "traffic": None}
 
     line = {
         "metric": METRIC if args.config == "cfg2" else METRIC.replace("Conv-TasNet 2spk 4s@8kHz", workload_config(args, world)["workload"].split(",")[0]),

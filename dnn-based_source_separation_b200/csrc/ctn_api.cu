@@ -5,6 +5,7 @@
 #include "ctn_internal.h"
 
 thread_local int g_ctn_launches = 0;
+thread_local long long g_ctn_total_launches = 0;
 thread_local int g_ctn_depth = 0;
 thread_local int g_ctn_last_launches = 0;
 
@@ -53,6 +54,7 @@ extern "C" int ctn_profile_read(double* ms, int* launches) {
 
 extern "C" int ctn_version(void) { return CTN_VERSION; }
 extern "C" int ctn_last_launch_count(void) { return g_ctn_last_launches; }
+extern "C" long long ctn_total_launch_count(void) { return g_ctn_total_launches; }
 
 extern "C" const char* ctn_strerror(int s) {
   switch (s) {

@@ -8,9 +8,10 @@
 
 // launch counter (thread local) -- bench.py reports it as gpu_launches
 extern thread_local int g_ctn_launches;
+extern thread_local long long g_ctn_total_launches;
 extern thread_local int g_ctn_depth;
 extern thread_local int g_ctn_last_launches;
-#define CTN_COUNT_LAUNCH() (++g_ctn_launches)
+#define CTN_COUNT_LAUNCH() (++g_ctn_total_launches, ++g_ctn_launches)
 // every extern "C" entry opens one; the outermost scope resets / publishes the launch count and makes the device that owns
 // `devptr` (any device pointer argument of the call) current for the duration of the call: kernels, memsets and function
 // attributes always go to the tensors' GPU, whatever the caller's current device is (restored on exit)

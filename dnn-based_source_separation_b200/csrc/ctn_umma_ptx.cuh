@@ -113,6 +113,17 @@ __device__ __forceinline__ void bulk_s2peer(uint32_t dst_smem, uint32_t src_smem
       : "memory");
 }
 
+// 16-byte store into the shared memory of CTA `rank` of the cluster, same CTA-relative address (generic proxy, DSMEM)
+__device__ __forceinline__ void st_peer_v4(uint32_t local_addr, uint32_t rank, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n\t"
+      "}" ::"r"(local_addr), "r"(rank), "r"(a), "r"(b), "r"(c), "r"(d)
+      : "memory");
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");

@@ -289,6 +289,8 @@ int ctn_debug_timeline(unsigned long long* host, int n);
 
 /* number of kernel launches the last ctn_* call on this thread enqueued (for bench.py's gpu_launches) */
 int ctn_last_launch_count(void);
+/* kernels launched by this thread through the library since it was loaded (paths made of several entry calls: DPRNN) */
+long long ctn_total_launch_count(void);
 
 /* Stage timing with CUDA events recorded on the launching stream (bench.py's roofline leg).  ctn_profile_enable(1)
  * makes every following ctn_* call on this thread bracket its kernel groups with events; ctn_profile_read

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+for d in 0 128; do CTN_LSTM_DBG=$d timeout 120 python tools/lstm_time.py 2>&1 | grep dbg | head -1; done
+CTN_LSTM_DBG=$((16 + 128)) timeout 120 python tools/lstm_time.py 2>&1 | grep "step 101 chunk [014]"
