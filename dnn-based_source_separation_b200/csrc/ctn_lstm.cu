@@ -910,37 +910,45 @@ __device__ __forceinline__ int ceil_exp(float m, int lo, int hi) {
 }
 __device__ __forceinline__ float exp2i(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
-// grid 2 (directions), 1024 threads: power-of-two operand scales from max|x| (measured) and max|W| (this direction)
-__global__ void __launch_bounds__(1024) k_lstm_scales(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
-                                                      const float* __restrict__ wih_r, const float* __restrict__ whh_r,
-                                                      const float* __restrict__ wfc, const unsigned* __restrict__ xmax, int F, int H,
-                                                      int Fo, LstmScales* __restrict__ out) {
+// max|W_ih|, max|W_hh|, max|W_fc[:, dir half]| per direction: grid (16, 2), atomicMax on the bit patterns into wmax[dir*3 + {0,1,2}]
+__global__ void __launch_bounds__(256) k_lstm_wmax(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
+                                                   const float* __restrict__ wih_r, const float* __restrict__ whh_r,
+                                                   const float* __restrict__ wfc, int F, int H, int Fo, unsigned* __restrict__ wmax) {
   __shared__ float red[32];
-  const int d = blockIdx.x;
+  const int d = blockIdx.y;
   const float* wih = d ? wih_r : wih_f;
   const float* whh = d ? whh_r : whh_f;
   float mi = 0.f, mh = 0.f, mp = 0.f;
-  for (int i = threadIdx.x; i < 4 * H * F; i += blockDim.x) mi = fmaxf(mi, fabsf(wih[i]));
-  for (int i = threadIdx.x; i < 4 * H * H; i += blockDim.x) mh = fmaxf(mh, fabsf(whh[i]));
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = t0; i < 4 * H * F; i += nt) mi = fmaxf(mi, fabsf(wih[i]));
+  for (int i = t0; i < 4 * H * H; i += nt) mh = fmaxf(mh, fabsf(whh[i]));
   if (wfc)
-    for (int i = threadIdx.x; i < Fo * H; i += blockDim.x) mp = fmaxf(mp, fabsf(wfc[(size_t)(i / H) * 2 * H + d * H + (i % H)]));
+    for (int i = t0; i < Fo * H; i += nt) mp = fmaxf(mp, fabsf(wfc[(size_t)(i / H) * 2 * H + d * H + (i % H)]));
   mi = block_max(mi, red);
   mh = block_max(mh, red);
   mp = block_max(mp, red);
   if (threadIdx.x == 0) {
-    const int ex = ceil_exp(__uint_as_float(*xmax), -40, 40);
-    const int eW = ceil_exp(fmaxf(mi * exp2i(ex), mh), -60, 60);
-    const int eP = ceil_exp(mp, -60, 60);
-    LstmScales s;
-    s.x_mul = exp2i(14 - ex);
-    s.w_ih_mul = exp2i(ex + 14 - eW);
-    s.w_hh_mul = exp2i(14 - eW);
-    s.inv_g = exp2i(eW - 28);
-    s.w_p_mul = exp2i(14 - eP);
-    s.inv_p = exp2i(eP - 28);
-    s.pad[0] = s.pad[1] = 0.f;
-    out[d] = s;
+    if (mi > 0.f) atomicMax(wmax + d * 3 + 0, __float_as_uint(mi));
+    if (mh > 0.f) atomicMax(wmax + d * 3 + 1, __float_as_uint(mh));
+    if (mp > 0.f) atomicMax(wmax + d * 3 + 2, __float_as_uint(mp));
   }
+}
+
+// power-of-two operand scales from max|x| (measured on this call's input) and this direction's max|W|
+__device__ __forceinline__ LstmScales lstm_scales(const unsigned* __restrict__ xmax, const unsigned* __restrict__ wmax, int d) {
+  const float mi = __uint_as_float(wmax[d * 3 + 0]), mh = __uint_as_float(wmax[d * 3 + 1]), mp = __uint_as_float(wmax[d * 3 + 2]);
+  const int ex = ceil_exp(__uint_as_float(*xmax), -40, 40);
+  const int eW = ceil_exp(fmaxf(mi * exp2i(ex), mh), -60, 60);
+  const int eP = ceil_exp(mp, -60, 60);
+  LstmScales s;
+  s.x_mul = exp2i(14 - ex);
+  s.w_ih_mul = exp2i(ex + 14 - eW);
+  s.w_hh_mul = exp2i(14 - eW);
+  s.inv_g = exp2i(eW - 28);
+  s.w_p_mul = exp2i(14 - eP);
+  s.inv_p = exp2i(eP - 28);
+  s.pad[0] = s.pad[1] = 0.f;
+  return s;
 }
 
 // grid (n_imgs, 2 directions, ranks): one 16 KB slab image per block.  Gate slab (chunk c, slab k): column n = 64 e + 4 u + gate <->
@@ -952,12 +960,14 @@ __global__ void __launch_bounds__(256) k_lstm_build(const float* __restrict__ wi
                                                     const float* __restrict__ bih_f, const float* __restrict__ bhh_f,
                                                     const float* __restrict__ wih_r, const float* __restrict__ whh_r,
                                                     const float* __restrict__ bih_r, const float* __restrict__ bhh_r,
-                                                    const float* __restrict__ wfc, int F, int H, int Fo, const LstmScales* __restrict__ scp,
+                                                    const float* __restrict__ wfc, int F, int H, int Fo, const unsigned* __restrict__ xmax,
+                                                    const unsigned* __restrict__ wmax, LstmScales* __restrict__ scp,
                                                     uint8_t* __restrict__ img, float* __restrict__ bias, int n_imgs) {
   const int d = blockIdx.y, idx = blockIdx.x, rank = blockIdx.z, R = gridDim.z;
   const float* wih = d ? wih_r : wih_f;
   const float* whh = d ? whh_r : whh_f;
-  const LstmScales sc = scp[d];
+  const LstmScales sc = lstm_scales(xmax, wmax, d);
+  if (idx == 0 && rank == 0 && threadIdx.x == 0) scp[d] = sc;  // the recurrence kernel reads them from here
   const int KSX = F / 32, KSH = H / 32, CH = KSH / R, per = KSX + KSH, n_gate = CH * per;
   uint8_t* dst = img + ((size_t)(d * R + rank) * n_imgs + idx) * SLAB_BYTES;
   auto hslab = [&](int kh) { return R == 1 ? kh : (kh < CH ? rank * CH + kh : (1 - rank) * CH + (kh - CH)); };
@@ -1030,29 +1040,47 @@ __global__ void __launch_bounds__(256) k_sample_stats2(const float* __restrict__
   if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
 }
 
-// ... and out = gLN(Y) + R, optionally stored with the two middle dimensions swapped (the layout of the other path)
+// ... and out = gLN(Y) + R, optionally stored with the two middle dimensions swapped (the layout of the other path).
+// grid (D1, B), block (F/4, 256/(F/4)): one block per (b, d1) row of D2 x F floats (contiguous on the read side: a warp reads 512
+// consecutive bytes of each operand); 4 independent cells per thread in flight; on the swapped side every cell is one 4F-byte run.
 __global__ void __launch_bounds__(256) k_norm_res2(const float* __restrict__ P0, const float* __restrict__ P1, const float* __restrict__ bias,
                                                    const float* __restrict__ R, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, float* __restrict__ out, const double* __restrict__ stats,
                                                    int D1, int D2, int F, float eps, int swap) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, d1 = blockIdx.x, f = threadIdx.x * 4;
   const float2 mr = gln_mean_rstd(stats + 2 * b, (double)D1 * (double)D2 * (double)F, eps);
-  const size_t cells = (size_t)D1 * D2;
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (size_t c = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); c < cells; c += (size_t)gridDim.x * wpb) {
-    const int d1 = (int)(c / D2), d2 = (int)(c % D2);
-    const size_t src = ((size_t)b * cells + c) * F;
-    const size_t dst = swap ? (((size_t)b * D2 + d2) * D1 + d1) * F : src;
-    for (int f = lane * 4; f < F; f += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(P0 + src + f)), c1 = __ldg(reinterpret_cast<const float4*>(P1 + src + f));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + f)), r = __ldg(reinterpret_cast<const float4*>(R + src + f));
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + f)), be = __ldg(reinterpret_cast<const float4*>(beta + f));
-      float4 o;
-      o.x = fmaf((a.x + c1.x + bb.x - mr.x) * mr.y, gm.x, be.x) + r.x;
-      o.y = fmaf((a.y + c1.y + bb.y - mr.x) * mr.y, gm.y, be.y) + r.y;
-      o.z = fmaf((a.z + c1.z + bb.z - mr.x) * mr.y, gm.z, be.z) + r.z;
-      o.w = fmaf((a.w + c1.w + bb.w - mr.x) * mr.y, gm.w, be.w) + r.w;
-      *reinterpret_cast<float4*>(out + dst + f) = o;
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + f)), gm = __ldg(reinterpret_cast<const float4*>(gamma + f)),
+               be = __ldg(reinterpret_cast<const float4*>(beta + f));
+  // y_norm = (p0 + p1 + bias - mean) * rstd * gamma + beta  ==  (p0 + p1) * sc + sh
+  const float4 sc = make_float4(mr.y * gm.x, mr.y * gm.y, mr.y * gm.z, mr.y * gm.w);
+  const float4 sh = make_float4(fmaf(bb.x - mr.x, sc.x, be.x), fmaf(bb.y - mr.x, sc.y, be.y), fmaf(bb.z - mr.x, sc.z, be.z),
+                                fmaf(bb.w - mr.x, sc.w, be.w));
+  const size_t row = ((size_t)b * D1 + d1) * D2;
+  const int TY = blockDim.y;
+  for (int d20 = threadIdx.y; d20 < D2; d20 += 4 * TY) {
+    float4 a[4], c[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int d2 = d20 + u * TY;
+      if (d2 < D2) {
+        const size_t src = (row + d2) * F + f;
+        a[u] = __ldg(reinterpret_cast<const float4*>(P0 + src));
+        c[u] = __ldg(reinterpret_cast<const float4*>(P1 + src));
+        r[u] = __ldg(reinterpret_cast<const float4*>(R + src));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int d2 = d20 + u * TY;
+      if (d2 < D2) {
+        const size_t dst = (swap ? ((size_t)b * D2 + d2) * D1 + d1 : row + d2) * F + f;
+        float4 o;
+        o.x = fmaf(a[u].x + c[u].x, sc.x, sh.x) + r[u].x;
+        o.y = fmaf(a[u].y + c[u].y, sc.y, sh.y) + r[u].y;
+        o.z = fmaf(a[u].z + c[u].z, sc.z, sh.z) + r[u].z;
+        o.w = fmaf(a[u].w + c[u].w, sc.w, sh.w) + r[u].w;
+        *reinterpret_cast<float4*>(out + dst) = o;
+      }
     }
   }
 }
@@ -1174,7 +1202,8 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   LstmScales* sc = reinterpret_cast<LstmScales*>(ws + p.off_sc);
   float* bias = reinterpret_cast<float*>(ws + p.off_bias);
   uint8_t* img = ws + p.off_img;
-  cudaError_t e = cudaMemsetAsync(xmax, 0, 4, st);
+  unsigned* wmax = xmax + 1;  // [2][3]
+  cudaError_t e = cudaMemsetAsync(xmax, 0, 32, st);
   if (e != cudaSuccess) return (int)e;
   const size_t n = (size_t)NSEQ * T * F;
   int gx = (int)((n / 4 + 255) / 256);
@@ -1183,10 +1212,10 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   k_absmax_flat<<<gx, 256, 0, st>>>(z, n, xmax);
   CTN_COUNT_LAUNCH();
   // w: weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then the same four with the _reverse suffix (torch.nn.LSTM names)
-  k_lstm_scales<<<2, 1024, 0, st>>>(w[0], w[1], w[4], w[5], w_fc, xmax, F, H, Fo, sc);
+  k_lstm_wmax<<<dim3(16, 2), 256, 0, st>>>(w[0], w[1], w[4], w[5], w_fc, F, H, Fo, wmax);
   CTN_COUNT_LAUNCH();
   const int n_build = w_fc ? p.n_imgs : p.n_imgs - H / 32;
-  k_lstm_build<<<dim3(n_build, 2, p.pair ? 2 : 1), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w_fc, F, H, Fo, sc, img, bias, p.n_imgs);
+  k_lstm_build<<<dim3(n_build, 2, p.pair ? 2 : 1), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w_fc, F, H, Fo, xmax, wmax, sc, img, bias, p.n_imgs);
   CTN_COUNT_LAUNCH();
   LstmArgs a;
   a.z = z; a.P = P; a.hout = hout; a.img = img; a.bias = bias; a.sc = sc;
@@ -1217,6 +1246,7 @@ extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, con
                                        ctn_stream_t stream) {
   LaunchScope scope(P);
   if (!P || !fc_bias || !R || !gamma || !beta || !out || !scratch || B <= 0 || D1 <= 0 || D2 <= 0 || F <= 0 || (F & 3)) return CTN_EINVAL;
+  if (F > 1024 || D1 > 65535 * 32 || B > 65535) return CTN_EUNSUPPORTED;
   if (swap && out == R) return CTN_EINVAL;
   if ((((uintptr_t)P) | ((uintptr_t)R) | ((uintptr_t)out) | ((uintptr_t)gamma) | ((uintptr_t)beta) | ((uintptr_t)fc_bias)) & 15)
     return CTN_EALIGN;
@@ -1230,10 +1260,8 @@ extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, con
   if (gx < 1) gx = 1;
   k_sample_stats2<<<dim3(gx, B), 256, 0, st>>>(P, P1, fc_bias, n, F, scratch);
   CTN_COUNT_LAUNCH();
-  const size_t cells = (size_t)D1 * D2;
-  int gy = (int)((cells + 7) / 8);
-  if (gy > 2368) gy = 2368;
-  k_norm_res2<<<dim3(gy, B), 256, 0, st>>>(P, P1, fc_bias, R, gamma, beta, out, scratch, D1, D2, F, eps, swap);
+  const int q = F / 4;
+  k_norm_res2<<<dim3(D1, B), dim3(q, 256 / q >= 1 ? 256 / q : 1), 0, st>>>(P, P1, fc_bias, R, gamma, beta, out, scratch, D1, D2, F, eps, swap);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
