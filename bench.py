@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--n-sources", type=int, default=None)
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32x3", "tf32", "f16x3"])
     ap.add_argument("--cpu-batch", type=int, default=None, help="mixtures per CPU-arm step (default: the full per-GPU batch)")
+    ap.add_argument("--no-lib-ab", action="store_true", help="cfg4: skip the A/B step on the library (cuDNN) recurrence")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-block", action="store_true")
     ap.add_argument("--train", action="store_true", help="time the TRAINING step only; prints its own line")
@@ -505,20 +506,22 @@ def main():
             flops = 2.0 * (B * Sn) * K_ * (2.0 * (F_ + H_) * 4 * H_ + 2.0 * H_ * F_)   # both directions: gates + projection
             ach = flops / (ms_lstm * 1e-3) / 1e12
             # A/B: the same step with the library recurrence (cuDNN LSTM in IEEE fp32 + library GEMM for the Linear)
-            dprnn_mod.NATIVE_LSTM = False
-            try:
-                with torch.no_grad():
-                    step_resident()
-                    ms_lib, _, _ = cuda_time(step_resident, 2, torch, D, dev)
-            finally:
-                dprnn_mod.NATIVE_LSTM = True
+            ms_lib = float("nan")
+            if not args.no_lib_ab:
+                dprnn_mod.NATIVE_LSTM = False
+                try:
+                    with torch.no_grad():
+                        step_resident()
+                        ms_lib, _, _ = cuda_time(step_resident, 2, torch, D, dev)
+                finally:
+                    dprnn_mod.NATIVE_LSTM = True
             roof = {"kernel": "k_bilstm_pair (bi-LSTM recurrence + 2H->F projection, 2-CTA clusters, h in tensor memory; 12 calls per step)",
                     "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
                     "ms_per_call": ms_lstm, "algorithmic_flops_per_call": flops,
                     "peak_note": "fp16 dense = bf16_tflops_sustained of measured (MEASURED_PEAKS.json); algorithmic flops (the 3-pass hi/lo split issues "
                                  "3x that); a recurrence: 250 dependent steps per call, " + str(4 * ((B * Sn + 127) // 128)) + " CTAs",
                     "glue_bytes_per_step": glue_bytes, "glue_ideal_ms_at_peak": glue_bytes / (pk["hbm"] * 1e9) * 1e3,
-                    "library_lstm_ms_per_step": ms_lib / 2, "native_lstm_ms_per_step": ms / args.steps,
+                    "library_lstm_ms_per_step": (ms_lib / 2 if ms_lib == ms_lib else None), "native_lstm_ms_per_step": ms / args.steps,
                     "note": "library_lstm_ms_per_step = the same step with cuDNN's LSTM (IEEE fp32, as parity with the reference needs) + a library GEMM"}
         else:
             roof = {"kernel": "cuDNN LSTM (library)", "bound": "tensor", "achieved": None, "peak": tf32_peak, "unit": "TFLOP/s", "frac": None, "traffic": None}

@@ -52,3 +52,19 @@ with torch.no_grad():
     o = dm(torch.randn(2, 1, 203, generator=torch.Generator().manual_seed(6)).cuda())
 torch.cuda.synchronize()
 print("dprnn", float(o.abs().sum()), flush=True)
+# tcgen05 bi-LSTM + projection: the 2-CTA cluster kernel (F = 64, H = 128) and the 1-CTA kernel (H = 32), ragged row groups
+from ctn_b200 import _native as NN
+for Fi, H_, nseq, tt in ((64, 128, 70, 5), (32, 32, 40, 4)):
+    g_ = torch.Generator().manual_seed(7)
+    ws_ = [((torch.rand(s_, generator=g_) * 2 - 1) * 0.1).cuda() for s_ in ((4 * H_, Fi), (4 * H_, H_), (4 * H_,), (4 * H_,)) * 2]
+    fc_ = ((torch.rand(Fi, 2 * H_, generator=g_) * 2 - 1) * 0.1).cuda()
+    z_ = torch.randn(nseq, tt, Fi, generator=g_).cuda()
+    nb_ = NN.ctn_bilstm_workspace_bytes(Fi, H_, Fi)
+    wsb_ = torch.empty(nb_, dtype=torch.uint8, device="cuda")
+    P_ = torch.empty(2, nseq, tt, Fi, device="cuda")
+    ho_ = torch.empty(nseq, tt, 2 * H_, device="cuda")
+    ptrs_ = (NN._fp * 8)(*[t_.data_ptr() for t_ in ws_])
+    NN.check(NN.ctn_bilstm_proj_fwd(z_.data_ptr(), nseq, tt, Fi, H_, ptrs_, fc_.data_ptr(), Fi, P_.data_ptr(), ho_.data_ptr(), wsb_.data_ptr(), nb_,
+                                    NN.stream_ptr(z_.device)), "ctn_bilstm_proj_fwd")
+    torch.cuda.synchronize()
+    print("lstm", Fi, H_, float(P_.abs().sum()), float(ho_.abs().sum()), flush=True)
