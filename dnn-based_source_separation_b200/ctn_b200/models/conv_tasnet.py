@@ -318,8 +318,13 @@ class ConvTasNet(nn.Module):
         if n_dims == 3:
             assert input.size(1) == 1, "input.size() is expected (?, 1, ?), but given {}".format(input.size())
         elif n_dims == 4:
+            # (batch, 1, n_mics, T) -> view (batch, n_mics, T) (conv_tasnet.py:138-141): the encoder consumes n_mics = in_channels
+            # channels; the kernels are single-channel, so n_mics must be 1 and the output gets the mic axis back (:167-168)
             assert input.size(1) == 1, "input.size() is expected (?, 1, ?, ?), but given {}".format(input.size())
-            raise NotImplementedError("multichannel (4-D) input is outside the sm_100a kernel envelope")
+            if input.size(2) != 1:
+                raise NotImplementedError("multichannel input (n_mics = in_channels > 1) is outside the sm_100a kernel envelope")
+            out, latent = self._run(input.reshape(input.size(0), 1, input.size(3)), want_latent)
+            return out.unsqueeze(2), latent
         else:
             raise ValueError("Not support {} dimension input".format(n_dims))
         x = input.contiguous()

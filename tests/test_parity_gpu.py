@@ -182,7 +182,12 @@ def test_model_golden(golden_dir, name, mode):
         out2 = model(mixture.cuda())
         loss, perm = crit(out, sources.cuda())
         loss_b, perm_b = crit(out, sources.cuda(), batch_mean=False)
+        # 4-D input (batch, 1, n_mics = 1, T) -> (batch, n_sources, n_mics, T), conv_tasnet.py:138-141, 167-168
+        out4 = model(mixture.cuda().unsqueeze(2))
+        with pytest.raises(NotImplementedError):
+            model(torch.cat([mixture, mixture], dim=1).cuda().unsqueeze(1))   # n_mics = 2: the kernels are single-channel
     assert out.shape == (rec["batch"], cfg.n_sources, rec["T"])
+    assert out4.shape == (rec["batch"], cfg.n_sources, 1, rec["T"]) and torch.equal(out4.squeeze(2), out2)
     assert torch.allclose(out, out2, rtol=0, atol=1e-6)
     out, latent = out.cpu(), latent.cpu()
     if "out_stride" in rec:
