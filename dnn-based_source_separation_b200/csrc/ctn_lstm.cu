@@ -474,8 +474,9 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm(const LstmArgs g) {
 // x_t now lives in TMEM too (the x producers own one lane each): shared memory holds only weights (ring), the two exchange
 // buffers and the store staging.  K order of a gate chunk: [x | own h | peer h] -- the peer's half arrives last.
 // TMEM columns: [0,256) accumulators, [256,384) own-h buffers (64 each: hi +0, lo +32), [384,512) x (hi +0, lo +64).
+constexpr int PAIR_MAX_ST = 8;
 struct PairHdr {
-  uint64_t bfull[MAX_ST], bempty[MAX_ST];
+  uint64_t bfull[PAIR_MAX_ST], bempty[PAIR_MAX_ST];
   uint64_t accfull[2], accempty[2];
   uint64_t hfull[2];
   uint64_t xfull, xempty;
@@ -485,7 +486,6 @@ struct PairHdr {
   uint32_t tmem_base;
 };
 static_assert(sizeof(PairHdr) <= HDR_BYTES, "header");
-constexpr int PAIR_MAX_ST = 8;
 
 template <int NCH, int KSX>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs g) {

@@ -14,8 +14,10 @@ __version__ = "0.1.0"
 
 
 def set_default_math(mode: str) -> None:
-    """'tf32x3' (tcgen05 3-pass split, fp32-parity; default when built), 'tf32' (single pass) or 'fp32' (FFMA)."""
-    from .models import conv_tasnet
+    """'f16x3' (tcgen05 3-pass fp16 split, fp32-parity; the default when the tcgen05 family is built), 'tf32x3' (3-pass TF32 split),
+    'tf32' (single pass, looser tolerance) or 'fp32' (CUDA-core FFMA).  One switch for every model class (ConvTasNet, DPRNNTasNet,
+    stand-alone TimeDilatedConvNet / Separator): it lives in models.tdcn.DEFAULT_MATH."""
+    from .models import tdcn
     if mode not in _native.MATH_NAMES:
         raise ValueError(f"unknown math mode {mode!r}; choose from {sorted(_native.MATH_NAMES)}")
-    conv_tasnet.DEFAULT_MATH = mode
+    tdcn.DEFAULT_MATH = mode

@@ -68,13 +68,22 @@ class ConvTasNetTrainFn(torch.autograd.Function):
         N.check(N.ctn_convtasnet_fwd_train(C.byref(cfg), C.byref(params), x.data_ptr(), B, T, out.data_ptr(), base,
                                            ws.numel() - (base - ws.data_ptr()), N.stream_ptr(dev)), "ctn_convtasnet_fwd_train")
         model.last_launches = N.ctn_last_launch_count()
-        ctx.cfg, ctx.ws, ctx.x, ctx.slots, ctx.n_blocks, ctx.model = cfg, ws, x, slots, n_blocks, model
-        ctx.tensors = tensors
+        # x and the parameters go through save_for_backward: an in-place update between forward and backward is detected by autograd
+        # (version counters) instead of silently changing the weights the backward kernels see
+        ctx.save_for_backward(x, *[t for t in tensors if t is not None])
+        ctx.present = [t is not None for t in tensors]
+        ctx.cfg, ctx.ws, ctx.slots, ctx.n_blocks, ctx.model = cfg, ws, slots, n_blocks, model
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, ws, cfg, tensors = ctx.x, ctx.ws, ctx.cfg, ctx.tensors
+        if ctx.ws is None:
+            raise RuntimeError("ConvTasNetTrainFn: backward was already run on this graph; the saved activations are released after the "
+                               "first backward (retain_graph is not supported by the native training path)")
+        saved = list(ctx.saved_tensors)
+        x, it = saved[0], iter(saved[1:])
+        tensors = tuple(next(it) if pres else None for pres in ctx.present)
+        ws, cfg = ctx.ws, ctx.cfg
         dev = x.device
         B, _, T = x.shape
         d_out = d_out.contiguous()
@@ -98,5 +107,7 @@ class ConvTasNetTrainFn(torch.autograd.Function):
 
 
 def run_train(model, x):
+    if x.requires_grad:
+        raise NotImplementedError("gradient w.r.t. the mixture is not built (the native backward stops at the encoder weights)")
     tensors = [t for _, t in param_list(model)]
     return ConvTasNetTrainFn.apply(model, x, *tensors)

@@ -63,7 +63,7 @@ class Separator(nn.Module):
 
     # ---- native plumbing -------------------------------------------------------------------------
     def native_config(self, kernel_size=1, stride=1, enc_relu=False):
-        mode = self.math if self.math is not None else (DEFAULT_MATH if DEFAULT_MATH is not None else _tdcn.DEFAULT_MATH)
+        mode = self.math if self.math is not None else (DEFAULT_MATH if DEFAULT_MATH is not None else _tdcn.DEFAULT_MATH)  # DEFAULT_MATH here: legacy override
         cfg = self.tdcn.native_config(n_basis=self.num_features, kernel_size=kernel_size, stride=stride,
                                       n_sources=self.n_sources, enc_relu=int(enc_relu), mask_softmax=int(self.mask_softmax))
         cfg.math = resolve_math(mode)

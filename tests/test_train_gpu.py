@@ -123,6 +123,28 @@ def test_training_step_decreases_loss():
     assert losses[-1] < losses[0], losses
 
 
+def test_autograd_node_contract():
+    """The native training node behaves like an autograd node should: an in-place parameter update between forward and backward
+    is detected (saved-tensor version check), a second backward on the same graph and a mixture that requires grad fail loudly."""
+    cfg = O.OracleConfig(n_basis=32, kernel_size=16, sep_hidden_channels=64, sep_bottleneck_channels=32, sep_skip_channels=32,
+                         sep_num_blocks=1, sep_num_layers=2, causal=False, n_sources=2)
+    model = build_model(cfg, O.synth_state_dict(cfg, seed=3)).train()
+    mixture, sources = O.synth_batch(2, 2, 2000, seed=8)
+    mixture, sources = mixture.cuda(), sources.cuda()
+    crit = PIT1d(NegSISDR(), 2)
+    loss, _ = crit(model(mixture), sources)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+    loss, _ = crit(model(mixture), sources)
+    with torch.no_grad():
+        next(model.parameters()).add_(1.0)
+    with pytest.raises(RuntimeError):          # "one of the variables needed for gradient computation has been modified"
+        loss.backward()
+    with pytest.raises(NotImplementedError):
+        model(mixture.clone().requires_grad_(True))
+
+
 PAPER = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128, sep_skip_channels=128,
              sep_num_blocks=3, sep_num_layers=8)
 
