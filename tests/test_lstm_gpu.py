@@ -77,6 +77,29 @@ def test_bilstm_vs_fp64_oracle(Fi, H, Fo, NSEQ, T):
     torch.testing.assert_close(y.double(), y64, rtol=1e-4, atol=2e-5 * float(y64.abs().max()))
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("stages", [None, "2"])
+def test_bilstm_support_matrix(pair, stages, monkeypatch):
+    """every (F, H, Fo) of the envelope, in the 2-CTA form where it exists (CTN_LSTM_PAIR=1) and in the 1-CTA form (=0), also with the
+    weight ring squeezed to 2 stages: same tolerance as above"""
+    monkeypatch.setenv("CTN_LSTM_PAIR", pair)
+    if stages:
+        monkeypatch.setenv("CTN_LSTM_STAGES", stages)
+    NSEQ, T = 150, 4
+    for Fi in (32, 64, 128):
+        for H in (32, 64, 128):
+            for Fo in (32, 64, 96, 128):
+                if not N.ctn_bilstm_supported(Fi, H, Fo):
+                    continue
+                sd = _weights(Fi, H, Fo, seed=Fi + H + Fo)
+                z = torch.randn(NSEQ, T, Fi, generator=torch.Generator().manual_seed(Fo)) * 1.2
+                h, P = _run(z, sd, H, Fo)
+                h64, y64 = _ref(z, sd, torch.float64)
+                assert float((h.double() - h64).abs().max()) <= 2e-5, (Fi, H, Fo)
+                y = P[0] + P[1] + sd["fc.bias"]
+                torch.testing.assert_close(y.double(), y64, rtol=1e-4, atol=2e-5 * float(y64.abs().max()), msg=lambda m: f"{(Fi, H, Fo)}: {m}")
+
+
 @pytest.mark.parametrize("xscale,wscale,atol", [(1e3, 1.0, 1e-3), (1e-3, 1.0, 2e-5), (1.0, 8.0, 2e-5), (30.0, 0.05, 2e-5), (0.0, 1.0, 2e-5)])
 def test_bilstm_operand_scales(xscale, wscale, atol):
     """the fp16 pieces are rescaled by powers of two measured on the data (x) and the weights: any magnitude is fine.  (x ~ 1e3:
