@@ -495,7 +495,7 @@ def main():
         wsb = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
 
         def lstm_call():
-            N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), B * Sn, K_, F_, H_, ptrs, blk.fc.weight.data_ptr(), F_, Pbuf.data_ptr(), None, wsb.data_ptr(),
+            N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), B * Sn, K_, F_, H_, ptrs, blk.fc.weight.data_ptr(), F_, Pbuf.data_ptr(), None, None, wsb.data_ptr(),
                                           nws, N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
         native = bool(dprnn_mod.NATIVE_LSTM and N.ctn_bilstm_supported(F_, H_, F_))
         if native:

@@ -1046,8 +1046,9 @@ __global__ void __launch_bounds__(256) k_sample_stats2(const float* __restrict__
 __global__ void __launch_bounds__(256) k_norm_res2(const float* __restrict__ P0, const float* __restrict__ P1, const float* __restrict__ bias,
                                                    const float* __restrict__ R, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, float* __restrict__ out, const double* __restrict__ stats,
-                                                   int D1, int D2, int F, float eps, int swap) {
+                                                   int D1, int D2, int F, float eps, int swap, unsigned* __restrict__ absmax) {
   const int b = blockIdx.y, d1 = blockIdx.x, f = threadIdx.x * 4;
+  float amax = 0.f;
   const float2 mr = gln_mean_rstd(stats + 2 * b, (double)D1 * (double)D2 * (double)F, eps);
   const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + f)), gm = __ldg(reinterpret_cast<const float4*>(gamma + f)),
                be = __ldg(reinterpret_cast<const float4*>(beta + f));
@@ -1080,8 +1081,14 @@ __global__ void __launch_bounds__(256) k_norm_res2(const float* __restrict__ P0,
         o.z = fmaf(a[u].z + c[u].z, sc.z, sh.z) + r[u].z;
         o.w = fmaf(a[u].w + c[u].w, sc.w, sh.w) + r[u].w;
         *reinterpret_cast<float4*>(out + dst) = o;
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       }
     }
+  }
+  if (absmax) {  // max|out|: the operand scale of the next path's LSTM (saves its own pass over the state)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && amax > 0.f) atomicMax(absmax, __float_as_uint(amax));
   }
 }
 
@@ -1178,7 +1185,7 @@ extern "C" size_t ctn_bilstm_workspace_bytes(int F, int H, int Fo) {
 }
 
 extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H, const float* const* w, const float* w_fc, int Fo, float* P,
-                                   float* hout, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
+                                   float* hout, const unsigned* z_absmax, void* workspace, size_t workspace_bytes, ctn_stream_t stream) {
   LaunchScope scope(z);
   if (!z || !w || !workspace || NSEQ <= 0 || T <= 0) return CTN_EINVAL;
   for (int i = 0; i < 8; ++i)
@@ -1209,8 +1216,12 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
   int gx = (int)((n / 4 + 255) / 256);
   if (gx > 1184) gx = 1184;
   if (gx < 1) gx = 1;
-  k_absmax_flat<<<gx, 256, 0, st>>>(z, n, xmax);
-  CTN_COUNT_LAUNCH();
+  if (z_absmax) {
+    xmax = const_cast<unsigned*>(z_absmax);  // supplied by the producer of z (ctn_dprnn_norm_res2_fwd): bit pattern of max|z|
+  } else {
+    k_absmax_flat<<<gx, 256, 0, st>>>(z, n, xmax);
+    CTN_COUNT_LAUNCH();
+  }
   // w: weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then the same four with the _reverse suffix (torch.nn.LSTM names)
   k_lstm_wmax<<<dim3(16, 2), 256, 0, st>>>(w[0], w[1], w[4], w[5], w_fc, F, H, Fo, wmax);
   CTN_COUNT_LAUNCH();
@@ -1242,7 +1253,7 @@ extern "C" int ctn_bilstm_proj_fwd(const float* z, int NSEQ, int T, int F, int H
 }
 
 extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, const float* R, const float* gamma, const float* beta,
-                                       float* out, int B, int D1, int D2, int F, float eps, int swap, double* scratch,
+                                       float* out, int B, int D1, int D2, int F, float eps, int swap, double* scratch, unsigned* out_absmax,
                                        ctn_stream_t stream) {
   LaunchScope scope(P);
   if (!P || !fc_bias || !R || !gamma || !beta || !out || !scratch || B <= 0 || D1 <= 0 || D2 <= 0 || F <= 0 || (F & 3)) return CTN_EINVAL;
@@ -1253,6 +1264,7 @@ extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, con
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, st);
   if (e != cudaSuccess) return (int)e;
+  if (out_absmax && (e = cudaMemsetAsync(out_absmax, 0, sizeof(unsigned), st)) != cudaSuccess) return (int)e;
   const size_t n = (size_t)D1 * D2 * F;
   const float* P1 = P + (size_t)B * n;  // second direction
   int gx = (int)((n / 4 + 256 * 4 - 1) / (256 * 4));
@@ -1261,7 +1273,7 @@ extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, con
   k_sample_stats2<<<dim3(gx, B), 256, 0, st>>>(P, P1, fc_bias, n, F, scratch);
   CTN_COUNT_LAUNCH();
   const int q = F / 4;
-  k_norm_res2<<<dim3(D1, B), dim3(q, 256 / q >= 1 ? 256 / q : 1), 0, st>>>(P, P1, fc_bias, R, gamma, beta, out, scratch, D1, D2, F, eps, swap);
+  k_norm_res2<<<dim3(D1, B), dim3(q, 256 / q >= 1 ? 256 / q : 1), 0, st>>>(P, P1, fc_bias, R, gamma, beta, out, scratch, D1, D2, F, eps, swap, out_absmax);
   CTN_COUNT_LAUNCH();
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;

@@ -78,8 +78,9 @@ class _ChunkRNN(nn.Module):
         self.norm1d = choose_layer_norm('gLN', num_features, causal=False, eps=eps)
         self.eps = eps
 
-    def _step(self, z, swap):
-        """z (B, D1, D2, F) channels-last -> gLN(fc(rnn(z))) + z, stored as (B, D2, D1, F) when swap."""
+    def _step(self, z, swap, z_absmax=None):
+        """z (B, D1, D2, F) channels-last -> gLN(fc(rnn(z))) + z, stored as (B, D2, D1, F) when swap.  z_absmax: optional device
+        word with the bit pattern of max|z| (left by the previous block's step); the output's is left in ``self.last_absmax``."""
         B, D1, D2, F = z.shape
         dev = N.require_cuda(z)
         H = self.hidden_channels
@@ -93,12 +94,15 @@ class _ChunkRNN(nn.Module):
             nws = N.ctn_bilstm_workspace_bytes(F, H, F)
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
             P = torch.empty((2, B, D1, D2, F), dtype=torch.float32, device=dev)
+            amax = torch.empty(1, dtype=torch.int32, device=dev)
             N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), B * D1, D2, F, H, ptrs, self.fc.weight.data_ptr(), F, P.data_ptr(), None,
-                                          ws.data_ptr(), nws, N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
+                                          N.ptr(z_absmax), ws.data_ptr(), nws, N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
             N.check(N.ctn_dprnn_norm_res2_fwd(P.data_ptr(), self.fc.bias.data_ptr(), z.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(),
-                                              B, D1, D2, F, float(self.eps), int(swap), scratch.data_ptr(), N.stream_ptr(dev)),
+                                              B, D1, D2, F, float(self.eps), int(swap), scratch.data_ptr(), amax.data_ptr(), N.stream_ptr(dev)),
                     "ctn_dprnn_norm_res2_fwd")
+            self.last_absmax = amax
             return out
+        self.last_absmax = None
         self.rnn.flatten_parameters()
         with _rnn_precision():
             y, _ = self.rnn(z.view(B * D1, D2, F))              # cuDNN bi-LSTM over D2, IEEE fp32 math
@@ -141,9 +145,13 @@ class DPRNNBlock(nn.Module):
     def forward(self, input):
         return self.inter_chunk_block(self.intra_chunk_block(input))
 
-    def forward_channels_last(self, z):
-        """z (B, S, K, F) -> (B, S, K, F): intra (swap to (B, K, S, F)), inter (swap back)"""
-        return self.inter_chunk_block._step(self.intra_chunk_block._step(z, swap=True), swap=True)
+    def forward_channels_last(self, z, z_absmax=None):
+        """z (B, S, K, F) -> (B, S, K, F): intra (swap to (B, K, S, F)), inter (swap back).  max|z| travels along as a device word
+        (each gLN + residual kernel leaves it for the next LSTM's operand scale)."""
+        y = self.intra_chunk_block._step(z, swap=True, z_absmax=z_absmax)
+        y = self.inter_chunk_block._step(y, swap=True, z_absmax=self.intra_chunk_block.last_absmax)
+        self.last_absmax = self.inter_chunk_block.last_absmax
+        return y
 
 
 class DPRNN(nn.Module):
@@ -160,6 +168,8 @@ class DPRNN(nn.Module):
         return self.forward_channels_last(z).permute(0, 3, 1, 2).contiguous()
 
     def forward_channels_last(self, z):
+        amax = None
         for blk in self.net:
-            z = blk.forward_channels_last(z)
+            z = blk.forward_channels_last(z, amax)
+            amax = blk.last_absmax
         return z

@@ -45,7 +45,7 @@ def _run(z, sd, H, Fo, want_h=True, want_p=True):
     P = torch.full((2, NSEQ, T, Fo), float("nan"), device=dev) if want_p else None
     hout = torch.full((NSEQ, T, 2 * H), float("nan"), device=dev) if want_h else None
     N.check(N.ctn_bilstm_proj_fwd(zc.data_ptr(), NSEQ, T, Fi, H, ptrs, fc.data_ptr() if want_p else None, Fo,
-                                  P.data_ptr() if want_p else None, hout.data_ptr() if want_h else None, ws.data_ptr(), nws,
+                                  P.data_ptr() if want_p else None, hout.data_ptr() if want_h else None, None, ws.data_ptr(), nws,
                                   N.stream_ptr(dev)), "ctn_bilstm_proj_fwd")
     torch.cuda.synchronize()
     return (hout.cpu() if want_h else None), (P.cpu() if want_p else None)
@@ -133,9 +133,9 @@ def test_bilstm_outputs_optional_and_errors():
     w = [sd["rnn." + n].cuda() for n in NAMES]
     ptrs = (N._fp * 8)(*[t.data_ptr() for t in w])
     out = torch.empty(33, 7, 2 * H, device="cuda")
-    assert N.ctn_bilstm_proj_fwd(zc.data_ptr(), 33, 7, Fi, H, ptrs, None, Fo, None, out.data_ptr(), ws.data_ptr(), 1024,
+    assert N.ctn_bilstm_proj_fwd(zc.data_ptr(), 33, 7, Fi, H, ptrs, None, Fo, None, out.data_ptr(), None, ws.data_ptr(), 1024,
                                  N.stream_ptr(zc.device)) == N.CTN_EWORKSPACE
-    assert N.ctn_bilstm_proj_fwd(zc.data_ptr(), 33, 7, 8, 12, ptrs, None, Fo, None, out.data_ptr(), ws.data_ptr(), 1024,
+    assert N.ctn_bilstm_proj_fwd(zc.data_ptr(), 33, 7, 8, 12, ptrs, None, Fo, None, out.data_ptr(), None, ws.data_ptr(), 1024,
                                  N.stream_ptr(zc.device)) == N.CTN_EUNSUPPORTED
 
 

@@ -18,7 +18,7 @@ def run(NSEQ, T, Fi=64, H=128, Fo=64, reps=5):
     P = torch.empty(2, NSEQ, T, Fo, device=dev)
     st = N.stream_ptr(dev)
     def call():
-        N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), NSEQ, T, Fi, H, ptrs, fc.data_ptr(), Fo, P.data_ptr(), None, ws.data_ptr(), nws, st), "lstm")
+        N.check(N.ctn_bilstm_proj_fwd(z.data_ptr(), NSEQ, T, Fi, H, ptrs, fc.data_ptr(), Fo, P.data_ptr(), None, None, ws.data_ptr(), nws, st), "lstm")
     for _ in range(2):
         call()
     torch.cuda.synchronize()

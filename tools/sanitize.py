@@ -64,7 +64,7 @@ for Fi, H_, nseq, tt in ((64, 128, 70, 5), (32, 32, 40, 4)):
     P_ = torch.empty(2, nseq, tt, Fi, device="cuda")
     ho_ = torch.empty(nseq, tt, 2 * H_, device="cuda")
     ptrs_ = (NN._fp * 8)(*[t_.data_ptr() for t_ in ws_])
-    NN.check(NN.ctn_bilstm_proj_fwd(z_.data_ptr(), nseq, tt, Fi, H_, ptrs_, fc_.data_ptr(), Fi, P_.data_ptr(), ho_.data_ptr(), wsb_.data_ptr(), nb_,
+    NN.check(NN.ctn_bilstm_proj_fwd(z_.data_ptr(), nseq, tt, Fi, H_, ptrs_, fc_.data_ptr(), Fi, P_.data_ptr(), ho_.data_ptr(), None, wsb_.data_ptr(), nb_,
                                     NN.stream_ptr(z_.device)), "ctn_bilstm_proj_fwd")
     torch.cuda.synchronize()
     print("lstm", Fi, H_, float(P_.abs().sum()), float(ho_.abs().sum()), flush=True)
