@@ -277,6 +277,54 @@ extern "C" int ctn_sisdr_fwd(const float* est, const float* tgt, int rows, int T
 }
 
 
+// ---- plain SDR (src/criterion/sdr.py:6-20): 10 log10((|t|^2 + eps) / (|t - x|^2 + eps)) per row -------------------------
+// The residual is accumulated explicitly (not as |t|^2 - 2<x,t> + |x|^2, which cancels catastrophically at high SDR), in double.
+__global__ void __launch_bounds__(256) k_sdr_partial(const float* __restrict__ est, const float* __restrict__ tgt, int T,
+                                                     double* __restrict__ scratch) {
+  __shared__ double red[64];
+  const int r = blockIdx.y;
+  const float* x = est + (size_t)r * T;
+  const float* t = tgt + (size_t)r * T;
+  double tt = 0.0, ee = 0.0;
+  const bool vec = ((((uintptr_t)x) | ((uintptr_t)t)) & 15) == 0;
+  const int n4 = vec ? T / 4 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i), b = __ldg(reinterpret_cast<const float4*>(t) + i);
+    const float d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
+    tt += (double)(fmaf(b.x, b.x, b.y * b.y) + fmaf(b.z, b.z, b.w * b.w));
+    ee += (double)(fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3));
+  }
+  for (int i = n4 * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const float b = t[i], d = b - x[i];
+    tt += (double)b * b;
+    ee += (double)d * d;
+  }
+  block_sum2_d(tt, ee, red);
+  if (threadIdx.x == 0) { atomicAdd(&scratch[2 * r], tt); atomicAdd(&scratch[2 * r + 1], ee); }
+}
+__global__ void k_sdr_finalize(const double* __restrict__ scratch, int rows, float eps, float* __restrict__ out) {
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  if (r >= rows) return;
+  out[r] = 10.f * log10f(((float)scratch[2 * r] + eps) / ((float)scratch[2 * r + 1] + eps));
+}
+
+extern "C" int ctn_sdr_fwd(const float* est, const float* tgt, int rows, int T, float eps, float* out, double* scratch, ctn_stream_t stream) {
+  LaunchScope scope(est);
+  if (!est || !tgt || !out || !scratch || rows <= 0 || T <= 0 || rows > 65535) return CTN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * rows, st);
+  if (e != cudaSuccess) return (int)e;
+  int gx = (T / 4 + 1023) / 1024;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  k_sdr_partial<<<dim3(gx, rows), 256, 0, st>>>(est, tgt, T, scratch);
+  CTN_COUNT_LAUNCH();
+  k_sdr_finalize<<<(rows + 127) / 128, 128, 0, st>>>(scratch, rows, eps, out);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward of PIT(NegSISDR) through the SELECTED permutation (pit.py:36-44: the indices carry no gradient).
 //   SI-SDR = k (ln P - ln Q),  P = alpha^2 |t|^2 + eps,  Q = |alpha t - x|^2 + eps,  alpha = <x,t> / (|t|^2 + eps)

@@ -1,5 +1,7 @@
-"""SI-SDR criteria on sm_100a kernels, mirroring src/criterion/sdr.py: ``sisdr`` (:122-139), ``SISDR`` (:141-185),
-``NegSISDR`` (:187-231).  Inputs (batch_size, T), (batch_size, n_sources, T) or (batch_size, n_sources, n_mics, T)."""
+"""SDR-family criteria on sm_100a kernels, mirroring src/criterion/sdr.py: ``sdr`` / ``SDR`` / ``NegSDR`` (:6-110), ``sisdr``
+(:122-139), ``SISDR`` (:141-185), ``NegSISDR`` (:187-231), ``ClippedSISDR`` / ``ClippedNegSISDR`` (:233-327).
+Inputs (batch_size, T), (batch_size, n_sources, T) or (batch_size, n_sources, n_mics, T).  ``sisdr`` is differentiable w.r.t. its
+input; ``sdr`` is forward only (evaluation metric)."""
 import torch
 import torch.nn as nn
 
@@ -32,6 +34,23 @@ def sisdr(input, target, eps=EPS):
     scratch = torch.empty(N.ctn_sisdr_pit_scratch_bytes(rows, 1) // 8, dtype=torch.float64, device=dev)
     N.check(N.ctn_sisdr_fwd(x.data_ptr(), t.data_ptr(), rows, T, float(eps), out.data_ptr(), scratch.data_ptr(),
                             N.stream_ptr(dev)), "ctn_sisdr_fwd")
+    return out
+
+
+def sdr(input, target, eps=EPS):
+    n_dims = input.dim()
+    assert n_dims in [2, 3, 4], "Only 2D or 3D or 4D tensor is acceptable, but given {}D tensor.".format(n_dims)
+    if input.shape != target.shape:
+        raise ValueError("input and target must have the same shape")
+    if torch.is_grad_enabled() and (input.requires_grad or target.requires_grad):
+        raise NotImplementedError("sdr() is forward only on the sm_100a path (train with sisdr / NegSISDR)")
+    x, t = input.contiguous(), target.contiguous()
+    dev = N.require_cuda(x, t)
+    T = x.shape[-1]
+    rows = x.numel() // T
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * rows, dtype=torch.float64, device=dev)
+    N.check(N.ctn_sdr_fwd(x.data_ptr(), t.data_ptr(), rows, T, float(eps), out.data_ptr(), scratch.data_ptr(), N.stream_ptr(dev)), "ctn_sdr_fwd")
     return out
 
 
@@ -69,6 +88,58 @@ class NegSISDR(nn.Module):
 
     def forward(self, input, target, batch_mean=True):
         return _reduce(-sisdr(input, target, eps=self.eps), input.dim(), self.reduction, batch_mean)
+
+    @property
+    def maximize(self):
+        return False
+
+
+class _Criterion(nn.Module):
+    def __init__(self, reduction='mean', eps=EPS):
+        super().__init__()
+        if reduction not in ['mean', 'sum', None]:
+            raise ValueError("Invalid reduction type")
+        self.reduction, self.eps = reduction, eps
+
+
+class SDR(_Criterion):
+    def forward(self, input, target, batch_mean=True):
+        return _reduce(sdr(input, target, eps=self.eps), input.dim(), self.reduction, batch_mean)
+
+    @property
+    def maximize(self):
+        return True
+
+
+class NegSDR(_Criterion):
+    def forward(self, input, target, batch_mean=True):
+        return _reduce(-sdr(input, target, eps=self.eps), input.dim(), self.reduction, batch_mean)
+
+    @property
+    def maximize(self):
+        return False
+
+
+class ClippedSISDR(_Criterion):
+    def __init__(self, max=None, reduction='mean', eps=EPS):
+        super().__init__(reduction=reduction, eps=eps)
+        self.max = max
+
+    def forward(self, input, target, batch_mean=True):
+        return _reduce(torch.clamp(sisdr(input, target, eps=self.eps), max=self.max), input.dim(), self.reduction, batch_mean)
+
+    @property
+    def maximize(self):
+        return True
+
+
+class ClippedNegSISDR(_Criterion):
+    def __init__(self, min=None, reduction='mean', eps=EPS):
+        super().__init__(reduction=reduction, eps=eps)
+        self.min = min
+
+    def forward(self, input, target, batch_mean=True):
+        return _reduce(torch.clamp(-sisdr(input, target, eps=self.eps), min=self.min), input.dim(), self.reduction, batch_mean)
 
     @property
     def maximize(self):

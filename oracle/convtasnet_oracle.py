@@ -232,6 +232,12 @@ def sisdr(input: torch.Tensor, target: torch.Tensor, eps: float = EPS) -> torch.
     return 10 * torch.log10(loss)
 
 
+def sdr(input: torch.Tensor, target: torch.Tensor, eps: float = EPS) -> torch.Tensor:
+    """sdr(), src/criterion/sdr.py:6-20: per-row 10 log10((|t|^2 + eps) / (|t - x|^2 + eps)) over the last axis."""
+    d = input.dim() - 1
+    return 10 * torch.log10((torch.sum(target ** 2, dim=d) + eps) / (torch.sum((target - input) ** 2, dim=d) + eps))
+
+
 def neg_sisdr(input, target, batch_mean=True, reduction="mean", eps=EPS):
     """NegSISDR.forward, src/criterion/sdr.py:198-227."""
     loss = -sisdr(input, target, eps=eps)

@@ -272,7 +272,33 @@ def module_cases():
     print("modules ->", os.path.getsize(path), "B")
 
 
+def criteria_case():
+    """SDR / NegSDR (src/criterion/sdr.py:6-110) and the clipped SI-SDR classes (:233-327) of the reference on seeded inputs; the
+    estimates are noisy copies of the targets so that SDR spans roughly -5 .. 35 dB"""
+    from criterion.sdr import SDR, NegSDR, ClippedSISDR, ClippedNegSISDR, sdr
+    g = torch.Generator().manual_seed(77)
+    rec = {}
+    for name, shape in (("2d", (5, 1003)), ("3d", (3, 2, 1600)), ("4d", (2, 3, 2, 801))):
+        tgt = torch.randn(shape, generator=g)
+        noise = torch.randn(shape, generator=g) * torch.logspace(-2, 0.3, shape[0]).view(-1, *([1] * (len(shape) - 1)))
+        est = tgt + noise
+        r = {"input": est, "target": tgt, "sdr": sdr(est, tgt)}
+        for red in ("mean", "sum", None):
+            r[f"SDR_{red}"] = SDR(reduction=red)(est, tgt, batch_mean=False)
+            r[f"NegSDR_{red}_bm"] = NegSDR(reduction=red)(est, tgt, batch_mean=True)
+        r["ClippedSISDR_20"] = ClippedSISDR(max=20.0)(est, tgt, batch_mean=False)
+        r["ClippedNegSISDR_-15"] = ClippedNegSISDR(min=-15.0)(est, tgt, batch_mean=False)
+        r["ClippedNegSISDR_none_bm"] = ClippedNegSISDR(min=-15.0, reduction=None)(est, tgt, batch_mean=True)
+        rec[name] = r
+    path = os.path.join(HERE, "criteria.pt")
+    torch.save(rec, path)
+    print("criteria ->", os.path.getsize(path), "B")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "criteria":
+        criteria_case()
+        return
     paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
                  sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)
     if len(sys.argv) > 1 and sys.argv[1] == "softmax":

@@ -126,3 +126,13 @@ def test_autograd_over_the_oracle_matches_reference_backward(golden_dir):
     assert abs(float(loss64) - rec["loss64"]) < 1e-9
     for k, g in rec["grads"].items():
         assert float((sd64[k].grad.flatten()[::rec["stride"]] - g["sample64"]).abs().max()) <= 1e-9 * max(1.0, g["absmax64"]), k
+
+
+def test_sdr_oracle_vs_reference_golden(golden_dir):
+    """oracle sdr() (src/criterion/sdr.py:6-20) against the values the reference produced (criteria.pt)"""
+    rec = torch.load(os.path.join(golden_dir, "criteria.pt"), weights_only=False)
+    for name, r in rec.items():
+        torch.testing.assert_close(O.sdr(r["input"], r["target"]), r["sdr"], rtol=1e-6, atol=1e-5, msg=lambda m: f"{name}: {m}")
+        torch.testing.assert_close(torch.clamp(O.sisdr(r["input"], r["target"]), max=20.0).mean(dim=tuple(range(1, r["input"].dim() - 1)))
+                                   if r["input"].dim() > 2 else torch.clamp(O.sisdr(r["input"], r["target"]), max=20.0),
+                                   r["ClippedSISDR_20"], rtol=1e-5, atol=1e-4)

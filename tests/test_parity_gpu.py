@@ -560,6 +560,30 @@ def test_reference_checkpoint_runs_on_the_kernels(golden_dir):
     assert torch.equal(perm.cpu(), rec["perm"])
 
 
+def test_sdr_family_vs_reference_golden(golden_dir):
+    """SDR / NegSDR (kernel ctn_sdr_fwd) and ClippedSISDR / ClippedNegSISDR against the reference's outputs (criteria.pt), all
+    reductions, 2-D / 3-D / 4-D inputs; tolerance 1e-4 dB"""
+    from ctn_b200.criterion.sdr import SDR, NegSDR, ClippedSISDR, ClippedNegSISDR, sdr
+    rec = _load(golden_dir, "criteria")
+    for name, r in rec.items():
+        x, t = r["input"].cuda(), r["target"].cuda()
+        torch.testing.assert_close(sdr(x, t).cpu(), r["sdr"], rtol=0, atol=1e-4, msg=lambda m: f"{name}: {m}")
+        torch.testing.assert_close(sdr(x, t).cpu(), O.sdr(r["input"], r["target"]), rtol=0, atol=1e-4)
+        for red in ("mean", "sum", None):
+            torch.testing.assert_close(SDR(reduction=red)(x, t, batch_mean=False).cpu(), r[f"SDR_{red}"], rtol=1e-6, atol=2e-4)
+            torch.testing.assert_close(NegSDR(reduction=red)(x, t, batch_mean=True).cpu(), r[f"NegSDR_{red}_bm"], rtol=1e-6, atol=2e-4)
+        torch.testing.assert_close(ClippedSISDR(max=20.0)(x, t, batch_mean=False).cpu(), r["ClippedSISDR_20"], rtol=0, atol=1e-4)
+        torch.testing.assert_close(ClippedNegSISDR(min=-15.0)(x, t, batch_mean=False).cpu(), r["ClippedNegSISDR_-15"], rtol=0, atol=1e-4)
+        torch.testing.assert_close(ClippedNegSISDR(min=-15.0, reduction=None)(x, t, batch_mean=True).cpu(), r["ClippedNegSISDR_none_bm"],
+                                   rtol=0, atol=1e-4)
+    assert SDR().maximize and not NegSDR().maximize and ClippedSISDR().maximize and not ClippedNegSISDR().maximize
+    e = rec["3d"]["input"].cuda().requires_grad_(True)
+    ClippedNegSISDR(min=-15.0)(e, rec["3d"]["target"].cuda()).backward()          # clipped SI-SDR trains (autograd through the clamp)
+    assert torch.isfinite(e.grad).all() and float(e.grad.abs().sum()) > 0
+    with pytest.raises(NotImplementedError):
+        sdr(e, rec["3d"]["target"].cuda())
+
+
 def test_sisdr_autograd_matches_oracle():
     """sisdr / NegSISDR under autograd (training without PIT): gradient w.r.t. the estimate vs torch autograd over the oracle."""
     g = torch.Generator().manual_seed(3)
