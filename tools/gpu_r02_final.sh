@@ -21,10 +21,10 @@ for n in ('bench_n1', 'bench_ref', 'bench_noreverse', 'bench_reverse', 'cfg4'):
         print(n, 'failed', e)
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/r02fin_launches_cfg4.csv \
-  python bench.py --config cfg4 --steps 1 --warmup 3 --no-cpu-baseline > $O/r02fin_prof_a.log 2>&1
+  python bench.py --config cfg4 --steps 1 --warmup 3 --no-cpu-baseline --no-lib-ab > $O/r02fin_prof_a.log 2>&1
 python tools/summarize_launches.py $O/r02fin_launches_cfg4.csv > $O/r02fin_launches_cfg4_summary.md; head -16 $O/r02fin_launches_cfg4_summary.md
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bilstm --launch-skip 12 --launch-count 2 -o $O/r02fin_lstm \
-  python bench.py --config cfg4 --steps 1 --warmup 1 --no-cpu-baseline > $O/r02fin_prof_b.log 2>&1
+  python bench.py --config cfg4 --steps 1 --warmup 1 --no-cpu-baseline --no-lib-ab > $O/r02fin_prof_b.log 2>&1
 python tools/ncu_summary.py $O/r02fin_lstm.ncu-rep lstm > $O/r02fin_lstm.md 2>&1; cat $O/r02fin_lstm.md
 python tools/ncu_roles.py $O/r02fin_lstm.ncu-rep 0 > $O/r02fin_lstm_roles.txt 2>&1
 for tool in memcheck racecheck synccheck; do
