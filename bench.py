@@ -85,9 +85,41 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
 
+    def _nvml(self):
+        """NVML handle of the GPU (by UUID when torch exposes it, else by index); None -> fall back to the nvidia-smi subprocess."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            return pynvml, h
+        except Exception:
+            return None, None
+
     def _run(self):
+        nv, h = self._nvml()
         while not self.stop.is_set():
             try:
+                if nv is not None:   # in-process NVML: ~10 ms period, several samples inside a 100-ms timed region
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        pw = 0.0
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    act = lambda bit: "Active" if rs & bit else "Not Active"
+                    self.rows.append([str(sm), str(mx), str(pw), act(0x8), act(0x40), act(0x20), act(0x4)])
+                    self.stop.wait(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:

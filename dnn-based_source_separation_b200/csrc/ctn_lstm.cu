@@ -1268,7 +1268,10 @@ extern "C" int ctn_dprnn_norm_res2_fwd(const float* P, const float* fc_bias, con
   const size_t n = (size_t)D1 * D2 * F;
   const float* P1 = P + (size_t)B * n;  // second direction
   int gx = (int)((n / 4 + 256 * 4 - 1) / (256 * 4));
-  if (gx > 592) gx = 592;
+  {  // ~8 resident blocks per SM over the WHOLE batch: longer per-thread streams, 2 double atomics per block on 2B addresses
+    const int cap = 1184 / B > 1 ? 1184 / B : 1;
+    if (gx > cap) gx = cap;
+  }
   if (gx < 1) gx = 1;
   k_sample_stats2<<<dim3(gx, B), 256, 0, st>>>(P, P1, fc_bias, n, F, scratch);
   CTN_COUNT_LAUNCH();
