@@ -681,7 +681,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) k_bilstm_pair(const LstmArgs 
   } else if (warp == 10) {
     // ===================================== SENDER ===========================================================
     if (ptx::elect_one()) {
-      for (int t = 0; t < T; ++t) {
+      // h_{T-1} is only read by the final projection: without one nobody waits for it on the other side, and a copy must never be
+      // left in flight towards a CTA that may already have exited
+      const int t_send = proj ? T : T - 1;
+      for (int t = 0; t < t_send; ++t) {
         const int b = t & 1;
         if (t >= 2) ptx::mbar_wait_cluster(ptx::smem_u32(&hdr->pfree[b]), (uint32_t)((t >> 1) - 1) & 1u);
         for (int c = 0; c < CH; ++c) {
