@@ -59,7 +59,9 @@ struct TmaArgs {
 };
 
 template <int PRO> struct Roles {
-  static constexpr int PROD_WARPS = 8;  // x SUBS * CPW = 4 channel streams per warp and slab
+  // x SUBS * CPW channel streams per warp and slab.  The mask kernel's prologue (PReLU of the skip sum, K = 128) is light: 4 producer
+  // warps keep the CTA at 448 threads, i.e. 144 instead of 96 registers per thread for its heavy epilogue (sigmoid, w * mask, decoder taps)
+  static constexpr int PROD_WARPS = PRO == PRO_PRELU ? 4 : 8;
   static constexpr int EGROUPS = PRO == PRO_DW ? 1 : 2;
   static constexpr int FIRST_PROD = 6;
   static constexpr int THREADS = (4 + 1 + 1 + PROD_WARPS + 4 * (EGROUPS - 1)) * 32;
@@ -519,10 +521,13 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
 #pragma unroll
         for (int i = 0; i < 8; ++i) dacc[i] = make_float2(0.f, 0.f);
       }
-      auto process_dec = [&](const uint32_t (&buf)[16], int c0) {
-        float wv[16];
+      // the 16 encoder values w[n][t] of a column chunk are fetched one chunk AHEAD of their use (L2 / HBM latency ~700 cycles and
+      // only two epilogue warps per scheduler: loading at the point of use left the FMULs below waiting on the scoreboard)
+      auto load_w = [&](float (&wv)[16], int c0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) wv[j] = (c0 + j < nvalid) ? __ldg(Wp + (size_t)(nb0 + c0 + j) * a.pitch) : 0.f;
+      };
+      auto process_dec = [&](const uint32_t (&buf)[16], const float (&wv)[16], int c0) {
         const float osc = ssc_all[n0 + c0];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -539,8 +544,8 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
           }
         }
       };
-      auto process = [&](const uint32_t (&buf)[16], int c0) {
-        if (EPI == EPI_MASKDEC) { process_dec(buf, c0); return; }
+      auto process = [&](const uint32_t (&buf)[16], const float (&wv)[16], int c0) {
+        if (EPI == EPI_MASKDEC) { process_dec(buf, wv, c0); return; }
         float* q = Dp + (size_t)c0 * a.pitch;
         const bool full = (c0 + 16 <= nvalid) && tile_full && do_store;  // warp-uniform
         const float osc = ssc_all[n0 + c0];  // one power-of-two scale per 16-row weight group (and the operand scale)
@@ -584,14 +589,23 @@ __global__ void __launch_bounds__(Roles<PRO>::THREADS, 1) k_pw_tma(const __grid_
         }
       };
       uint32_t bufA[16], bufB[16];
+      float wvA[16], wvB[16];
+      const bool pf = EPI == EPI_MASKDEC && !(g.dbg & 32u);  // dbg 32: load at the point of use (A/B of the prefetch)
+      if (EPI == EPI_MASKDEC && cbeg < ncols) load_w(wvA, cbeg);
       if (cbeg < ncols) ptx::tmem_ld16(taddr + (uint32_t)cbeg, bufA);
       for (int c0 = cbeg; c0 < ncols; c0 += 32) {
         ptx::tmem_ld_wait();
-        if (c0 + 16 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 16), bufB);
-        process(bufA, c0);
+        if (c0 + 16 < ncols) {
+          ptx::tmem_ld16(taddr + (uint32_t)(c0 + 16), bufB);
+          if (pf) load_w(wvB, c0 + 16);
+        }
+        process(bufA, wvA, c0);
         ptx::tmem_ld_wait();
         if (c0 + 32 < ncols) ptx::tmem_ld16(taddr + (uint32_t)(c0 + 32), bufA);
-        if (c0 + 16 < ncols) process(bufB, c0 + 16);
+        if (EPI == EPI_MASKDEC && !pf && c0 + 16 < ncols) load_w(wvB, c0 + 16);
+        if (pf && c0 + 32 < ncols) load_w(wvA, c0 + 32);
+        if (c0 + 16 < ncols) process(bufB, wvB, c0 + 16);
+        if (EPI == EPI_MASKDEC && !pf && c0 + 32 < ncols) load_w(wvA, c0 + 32);
       }
       ptx::tc_fence_before();
       if (PAIR) {  // one arrival per warp, on the LEADER's barrier (its MMA warp overwrites both CTAs' accumulators)
