@@ -484,6 +484,7 @@ static int check_model_cfg(const ctn_config_t* c) {
   if (c->n_basis <= 0 || c->kernel_size <= 0 || c->stride <= 0 || c->n_sources <= 0) return CTN_EINVAL;
   if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
   if (c->mask_softmax && c->mask_softmax != 1) return CTN_EINVAL;
+  if (c->in_channels < 0 || c->in_channels > 64) return CTN_EINVAL;
   return CTN_OK;
 }
 
@@ -604,17 +605,28 @@ extern "C" int ctn_convtasnet_fwd(const ctn_config_t* cfg, const ctn_params_t* p
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(ws.tcn.stats, 0, ws.tcn.stats_bytes, st);
   if (e != cudaSuccess) return (int)e;
+  const int Cin = cfg->in_channels > 1 ? cfg->in_channels : 1;  // x (B,Cin,T), out (B,S,Cin,T): conv_tasnet.py:138-141,167-168
   // encoder (+ gLN0 statistics)
   { StageTimer tm(CTN_ST_ENC, st);
-    CTN_TRY(ctn_encoder_fwd(x, params->enc_w, ws.w, B, T, pl, pr, cfg->n_basis, cfg->kernel_size, cfg->stride, cfg->enc_relu,
-                            pitch, ws.stats0, st)); }
+    if (Cin == 1) {
+      CTN_TRY(ctn_encoder_fwd(x, params->enc_w, ws.w, B, T, pl, pr, cfg->n_basis, cfg->kernel_size, cfg->stride, cfg->enc_relu,
+                              pitch, ws.stats0, st));
+    } else {
+      CTN_TRY(ctn_encoder_mc_fwd(x, params->enc_w, ws.w, B, Cin, T, pl, pr, cfg->n_basis, cfg->kernel_size, cfg->stride, cfg->enc_relu,
+                                 pitch, ws.stats0, st));
+    } }
   DecFuse dec{out, pl, T, false};
-  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, nullptr, st, latent ? nullptr : &dec));
+  CTN_TRY(run_separator(cfg, params, &ws, B, frames, pitch, nullptr, st, (latent || Cin > 1) ? nullptr : &dec));
   if (!dec.fused) {
     // decoder + crop (conv_tasnet.py:163-169)
     StageTimer tm(CTN_ST_DEC, st);
-    CTN_TRY(ctn_decoder_fwd(ws.what, params->dec_w, out, B * cfg->n_sources, cfg->n_basis, frames, pitch, cfg->kernel_size,
-                            cfg->stride, pl, T, st));
+    if (Cin == 1) {
+      CTN_TRY(ctn_decoder_fwd(ws.what, params->dec_w, out, B * cfg->n_sources, cfg->n_basis, frames, pitch, cfg->kernel_size,
+                              cfg->stride, pl, T, st));
+    } else {
+      CTN_TRY(ctn_decoder_mc_fwd(ws.what, params->dec_w, out, B * cfg->n_sources, Cin, cfg->n_basis, frames, pitch, cfg->kernel_size,
+                                 cfg->stride, pl, T, st));
+    }
   }
   if (latent) CTN_TRY(ctn_copy_from_pitch(ws.what, latent, B * cfg->n_sources * cfg->n_basis, frames, pitch, st));
   return CTN_OK;
@@ -774,6 +786,7 @@ extern "C" int ctn_convtasnet_loss_host(const ctn_config_t* cfg, const ctn_param
                                         int64_t* perm_host, void* dev_io, size_t dev_io_bytes, void* workspace,
                                         size_t workspace_bytes, float loss_eps, ctn_stream_t stream) {
   LaunchScope scope(dev_io);
+  if (cfg && cfg->in_channels > 1) return CTN_EUNSUPPORTED;  // host-buffer entry: monaural mixtures
   if (!cfg || !x_host || !tgt_host || !loss_mean_host || !perm_host || !dev_io || B <= 0 || T <= 0) return CTN_EINVAL;
   if (((uintptr_t)dev_io) & 255) return CTN_EALIGN;
   if (dev_io_bytes < ctn_host_io_bytes(cfg, B, T)) return CTN_EWORKSPACE;

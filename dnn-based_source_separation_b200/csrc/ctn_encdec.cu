@@ -300,3 +300,89 @@ extern "C" int ctn_decoder_fwd(const float* w_hat, const float* dec_w, float* y,
   CTN_RETURN_IF_CUDA_ERR();
   return CTN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Multichannel filter banks (in_channels = n_mics > 1: the 4-D input form of conv_tasnet.py:138-141, 167-168; MUSDB18 recipes).
+// Forward only, straightforward kernels (thread = frame / output sample): this is the widened input format, not the measured path.
+//   encoder: w[b][n][f] = sum_c sum_k W[n][c][k] * xpad[b][c][f*stride + k]      (Conv1d(C, N, L, stride), filterbank.py:212,222-229)
+//   decoder: y[bs][c][t] = sum_n sum_{f,k: f*stride + k = t + crop} what[bs][n][f] * Wd[n][c][k]  (ConvTranspose1d(N, C, L, stride))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_encoder_mc(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ w, int C,
+                                                    int T, int pad_left, int N, int L, int stride, int frames, int pitch, int relu,
+                                                    double* __restrict__ stats) {
+  __shared__ double red[64];
+  const int b = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = f < frames, inb = f < pitch;
+  const float* xb = x + (size_t)b * C * T;
+  double s = 0.0, ss = 0.0;
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.f;
+    if (valid)
+      for (int c = 0; c < C; ++c) {
+        const float* wr = W + ((size_t)n * C + c) * L;
+        const float* xc = xb + (size_t)c * T;
+        for (int k = 0; k < L; ++k) {
+          const int t = f * stride + k - pad_left;
+          if (t >= 0 && t < T) acc = fmaf(__ldg(wr + k), __ldg(xc + t), acc);
+        }
+      }
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (inb) w[((size_t)b * N + n) * pitch + f] = valid ? acc : 0.f;
+    if (valid) { s += acc; ss += (double)acc * acc; }
+  }
+  if (stats != nullptr) {
+    block_sum2_d(s, ss, red);
+    if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], s); atomicAdd(&stats[2 * b + 1], ss); }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_decoder_mc(const float* __restrict__ what, const float* __restrict__ Wd, float* __restrict__ y, int C,
+                                                    int N, int frames, int in_pitch, int L, int stride, int crop_left, int T_out) {
+  const int bs = blockIdx.z, c = blockIdx.y, t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T_out) return;
+  const int tau = t + crop_left;
+  int f_hi = tau / stride;
+  if (f_hi > frames - 1) f_hi = frames - 1;
+  int f_lo = (tau - L + stride) / stride;  // smallest f with tau - f*stride <= L - 1
+  if (tau - L + 1 <= 0) f_lo = 0;
+  float acc = 0.f;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const int k = tau - f * stride;
+    if (k < 0 || k >= L) continue;
+    const float* wh = what + (size_t)bs * N * in_pitch + f;
+    const float* wd = Wd + (size_t)c * L + k;
+    for (int n = 0; n < N; ++n) acc = fmaf(__ldg(wh + (size_t)n * in_pitch), __ldg(wd + (size_t)n * C * L), acc);
+  }
+  y[((size_t)bs * C + c) * T_out + t] = acc;
+}
+
+extern "C" int ctn_encoder_mc_fwd(const float* x, const float* enc_w, float* w, int B, int C, int T, int pad_left, int pad_right, int N, int L,
+                                  int stride, int relu, int w_pitch, double* stats, ctn_stream_t stream) {
+  LaunchScope scope(w);
+  if (!x || !enc_w || !w || B <= 0 || C <= 0 || T <= 0 || N <= 0 || L <= 0 || stride <= 0) return CTN_EINVAL;
+  const int Tp = T + pad_left + pad_right;
+  if (Tp < L || (Tp - L) % stride != 0) return CTN_EINVAL;
+  const int frames = (Tp - L) / stride + 1;
+  if (w_pitch < frames) return CTN_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_encoder_mc<<<dim3((w_pitch + 127) / 128, B), 128, 0, st>>>(x, enc_w, w, C, T, pad_left, N, L, stride, frames, w_pitch, relu, stats);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}
+
+extern "C" int ctn_decoder_mc_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int C, int N, int frames, int in_pitch, int L,
+                                  int stride, int crop_left, int T_out, ctn_stream_t stream) {
+  LaunchScope scope(w_hat);
+  if (!w_hat || !dec_w || !y || BS <= 0 || C <= 0 || C > 65535 || BS > 65535 || N <= 0 || frames <= 0 || L <= 0 || stride <= 0 ||
+      L % stride != 0)
+    return CTN_EINVAL;
+  if (in_pitch < frames) return CTN_EINVAL;
+  const int full = (frames - 1) * stride + L;
+  if (crop_left < 0 || T_out <= 0 || crop_left + T_out > full) return CTN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_decoder_mc<<<dim3((T_out + 127) / 128, C, BS), 128, 0, st>>>(w_hat, dec_w, y, C, N, frames, in_pitch, L, stride, crop_left, T_out);
+  CTN_COUNT_LAUNCH();
+  CTN_RETURN_IF_CUDA_ERR();
+  return CTN_OK;
+}

@@ -765,7 +765,7 @@ int check_train_cfg(const ctn_config_t* c) {
     return CTN_EINVAL;
   if (c->kernel_size % c->stride != 0) return CTN_EINVAL;
   if (c->num_layers > 20 || c->num_blocks * c->num_layers > CTN_MAX_BLOCKS) return CTN_EUNSUPPORTED;
-  if (c->causal || c->mask_softmax || c->sep_kernel > CTN_MAX_P) return CTN_EUNSUPPORTED;  // softmax masks: forward only
+  if (c->causal || c->mask_softmax || c->in_channels > 1 || c->sep_kernel > CTN_MAX_P) return CTN_EUNSUPPORTED;  // softmax masks, multichannel: forward only
   if (c->math != CTN_MATH_FP32 && c->math != CTN_MATH_TF32X3 && c->math != CTN_MATH_TF32 && c->math != CTN_MATH_F16X3) return CTN_EINVAL;
   return CTN_OK;
 }

@@ -157,6 +157,27 @@ class ConvTasNet(nn.Module):
         """input (batch_size, 1, T) -> output (batch_size, n_sources, T), latent (batch_size, n_sources, n_basis, T')"""
         return self._run(input, want_latent=True)
 
+    def _run_multichannel(self, x, want_latent):
+        """x (batch, n_mics, T) -> (batch, n_sources, n_mics, T): same C call, multichannel filter banks (forward only)"""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("multichannel models (in_channels > 1) are forward only: call under torch.no_grad()")
+        x = x.contiguous()
+        dev = N.require_cuda(x)
+        B, Cin, T = x.shape
+        frames, _, _ = N.frames_of(T, self.kernel_size, self.stride)
+        cfg = self.native_config()
+        params, keep = self.native_params(dev)
+        need = C.c_size_t(0)
+        N.check(N.ctn_workspace_bytes(C.byref(cfg), B, T, C.byref(need)), "ctn_workspace_bytes")
+        ws = N.workspace(dev, need.value)
+        base = (ws.data_ptr() + 255) & ~255
+        out = torch.empty(B, self.n_sources, Cin, T, dtype=torch.float32, device=dev)
+        latent = torch.empty(B, self.n_sources, self.n_basis, frames, dtype=torch.float32, device=dev) if want_latent else None
+        N.check(N.ctn_convtasnet_fwd(C.byref(cfg), C.byref(params), x.data_ptr(), B, T, out.data_ptr(), N.ptr(latent), base,
+                                     ws.numel() - (base - ws.data_ptr()), N.stream_ptr(dev)), "ctn_convtasnet_fwd")
+        self.last_launches = N.ctn_last_launch_count()
+        return out, latent
+
     def get_config(self):
         return {
             'in_channels': self.in_channels, 'n_basis': self.n_basis, 'kernel_size': self.kernel_size, 'stride': self.stride,
@@ -308,6 +329,7 @@ class ConvTasNet(nn.Module):
             cfg = sep.native_config(kernel_size=self.kernel_size, stride=self.stride, enc_relu=self.encoder.nonlinear)
         finally:
             sep.math = saved
+        cfg.in_channels = int(self.in_channels)
         return cfg
 
     def native_params(self, dev):
@@ -319,14 +341,18 @@ class ConvTasNet(nn.Module):
             assert input.size(1) == 1, "input.size() is expected (?, 1, ?), but given {}".format(input.size())
         elif n_dims == 4:
             # (batch, 1, n_mics, T) -> view (batch, n_mics, T) (conv_tasnet.py:138-141): the encoder consumes n_mics = in_channels
-            # channels; the kernels are single-channel, so n_mics must be 1 and the output gets the mic axis back (:167-168)
+            # channels and the output gets the mic axis back (:167-168)
             assert input.size(1) == 1, "input.size() is expected (?, 1, ?, ?), but given {}".format(input.size())
-            if input.size(2) != 1:
-                raise NotImplementedError("multichannel input (n_mics = in_channels > 1) is outside the sm_100a kernel envelope")
-            out, latent = self._run(input.reshape(input.size(0), 1, input.size(3)), want_latent)
-            return out.unsqueeze(2), latent
+            if input.size(2) != self.in_channels:
+                raise ValueError("n_mics={} does not match in_channels={}".format(input.size(2), self.in_channels))
+            if self.in_channels == 1:
+                out, latent = self._run(input.reshape(input.size(0), 1, input.size(3)), want_latent)
+                return out.unsqueeze(2), latent
+            return self._run_multichannel(input.reshape(input.size(0), input.size(2), input.size(3)), want_latent)
         else:
             raise ValueError("Not support {} dimension input".format(n_dims))
+        if self.in_channels != 1:
+            raise ValueError("a model with in_channels={} takes the 4-D input (batch, 1, n_mics, T)".format(self.in_channels))
         x = input.contiguous()
         dev = N.require_cuda(x)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

@@ -67,6 +67,7 @@ typedef struct ctn_config {
   int32_t math;         /* enum ctn_math */
   float eps;            /* Separator head norm eps (ConvTasNet eps)            */
   float eps_tcn;        /* eps of the norms inside the TDCN (reference passes the default 1e-12) */
+  int32_t in_channels;  /* C = n_mics of the 4-D input form (conv_tasnet.py:75,138-141); 0 or 1: monaural.  > 1: forward only */
 } ctn_config_t;
 
 /* Parameters of one ResidualBlock1d (+ its DepthwiseSeparableConv1d), src/models/tdcn.py:77-196.
@@ -126,6 +127,12 @@ int ctn_encoder_fwd(const float* x, const float* enc_w, float* w, int B, int T, 
  * crop of conv_tasnet.py:169: y[bs][t] = full[bs][t + crop_left], t in [0,T_out).  w_hat (BS,N,in_pitch). */
 int ctn_decoder_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int N, int frames, int in_pitch,
                     int L, int stride, int crop_left, int T_out, ctn_stream_t stream);
+/* Multichannel filter banks, src/models/filterbank.py:212,241 with in_channels = C > 1 (the 4-D input of conv_tasnet.py:138-141):
+ * x (B,C,T), enc_w (N,C,L) -> w (B,N,w_pitch) [+ gLN statistics]; w_hat (BS,N,in_pitch), dec_w (N,C,L) -> y (BS,C,T_out), cropped. */
+int ctn_encoder_mc_fwd(const float* x, const float* enc_w, float* w, int B, int C, int T, int pad_left, int pad_right, int N, int L,
+                       int stride, int relu, int w_pitch, double* stats, ctn_stream_t stream);
+int ctn_decoder_mc_fwd(const float* w_hat, const float* dec_w, float* y, int BS, int C, int N, int frames, int in_pitch, int L,
+                       int stride, int crop_left, int T_out, ctn_stream_t stream);
 
 /* GlobalLayerNorm.forward, src/modules/norm.py:18,32 (GroupNorm(1,C,eps)).  x,y (B,C,T) contiguous.
  * scratch: double[B][2], zero-initialised by the callee. */

@@ -53,6 +53,7 @@ class OracleConfig:
     n_sources: int = 2
     eps: float = EPS
     enc_nonlinear: Optional[str] = None
+    in_channels: int = 1  # kwargs['in_channels'], conv_tasnet.py:75 (n_mics of the 4-D input form)
 
     def __post_init__(self):
         if self.stride is None:
@@ -201,10 +202,14 @@ def separator_fwd(w, sd, cfg: OracleConfig, prefix="separator."):
 
 def conv_tasnet_fwd(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: OracleConfig) -> Tuple[torch.Tensor, torch.Tensor]:
     """ConvTasNet.extract_latent, src/models/conv_tasnet.py:121-171.  Returns (output, latent)."""
-    if x.dim() != 3:
-        raise ValueError("Not support {} dimension input".format(x.dim()))
+    n_dims = x.dim()
+    if n_dims == 4:  # (B, 1, n_mics, T) -> (B, n_mics, T), :138-141
+        assert x.shape[1] == 1
+        x = x.reshape(x.shape[0], x.shape[2], x.shape[3])
+    elif n_dims != 3:
+        raise ValueError("Not support {} dimension input".format(n_dims))
     B, C_in, T = x.shape
-    assert C_in == 1
+    assert C_in == (1 if n_dims == 3 else cfg.in_channels)
     K, S = cfg.kernel_size, cfg.stride
     padding = (S - (T - K) % S) % S  # :145
     pl = padding // 2
@@ -215,7 +220,7 @@ def conv_tasnet_fwd(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: OracleCon
     w_hat = w.unsqueeze(1) * mask  # :159-160
     latent = w_hat
     x_hat = decoder_fwd(w_hat.reshape(B * cfg.n_sources, cfg.n_basis, -1), sd["decoder.conv_transpose1d.weight"], S)  # :163-164
-    x_hat = x_hat.view(B, cfg.n_sources, -1)  # :166
+    x_hat = x_hat.view(B, cfg.n_sources, -1) if n_dims == 3 else x_hat.view(B, cfg.n_sources, C_in, -1)  # :165-168
     out = F.pad(x_hat, (-pl, -pr))  # :169
     return out, latent
 
@@ -278,7 +283,7 @@ def state_dict_spec(cfg: OracleConfig):
     """(key, shape) list in the reference's state_dict order (verified by tests/golden/make_golden.py)."""
     N, L = cfg.n_basis, cfg.kernel_size
     Bc, H, Sc, P = cfg.sep_bottleneck_channels, cfg.sep_hidden_channels, cfg.sep_skip_channels, cfg.sep_kernel_size
-    spec = [("encoder.conv1d.weight", (N, 1, L))]
+    spec = [("encoder.conv1d.weight", (N, cfg.in_channels, L))]
 
     def norm_keys(prefix, C):
         if cfg.causal:
@@ -303,7 +308,7 @@ def state_dict_spec(cfg: OracleConfig):
             spec += [(q + "skip_pointwise_conv1d.weight", (Sc, H, 1)), (q + "skip_pointwise_conv1d.bias", (Sc,))]
     spec += [("separator.prelu.weight", (1,)),
              ("separator.mask_conv1d.weight", (cfg.n_sources * N, Sc, 1)), ("separator.mask_conv1d.bias", (cfg.n_sources * N,)),
-             ("decoder.conv_transpose1d.weight", (N, 1, L))]
+             ("decoder.conv_transpose1d.weight", (N, cfg.in_channels, L))]
     return spec
 
 

@@ -45,7 +45,7 @@ def build_reference(cfg: O.OracleConfig):
         sep_skip_channels=cfg.sep_skip_channels, sep_kernel_size=cfg.sep_kernel_size,
         sep_num_blocks=cfg.sep_num_blocks, sep_num_layers=cfg.sep_num_layers,
         dilated=cfg.dilated, separable=cfg.separable, sep_nonlinear=cfg.sep_nonlinear, sep_norm=cfg.sep_norm,
-        mask_nonlinear=cfg.mask_nonlinear, causal=cfg.causal, n_sources=cfg.n_sources, eps=cfg.eps)
+        mask_nonlinear=cfg.mask_nonlinear, causal=cfg.causal, n_sources=cfg.n_sources, eps=cfg.eps, in_channels=cfg.in_channels)
     return m
 
 
@@ -272,6 +272,26 @@ def module_cases():
     print("modules ->", os.path.getsize(path), "B")
 
 
+def multichannel_case():
+    """in_channels = n_mics = 2 (the 4-D input form, conv_tasnet.py:138-141,167-168; the MUSDB18 recipes): reference forward on a seeded
+    stereo mixture, 3 sources"""
+    cfg = O.OracleConfig(n_basis=32, kernel_size=8, sep_hidden_channels=48, sep_bottleneck_channels=16, sep_skip_channels=24,
+                         sep_num_blocks=2, sep_num_layers=3, causal=False, n_sources=3, in_channels=2)
+    ref = build_reference(cfg)
+    assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == [(k, tuple(s)) for k, s in O.state_dict_spec(cfg)]
+    sd = O.synth_state_dict(cfg, seed=31)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    g = torch.Generator().manual_seed(32)
+    mixture = 0.3 * torch.randn(2, 1, 2, 1501, generator=g)
+    with torch.no_grad():
+        out, latent = ref.extract_latent(mixture)
+    rec = {"cfg": cfg.to_dict(), "wseed": 31, "mixture": mixture, "out": out.clone(), "latent": latent.clone()}
+    path = os.path.join(HERE, "tiny_stereo.pt")
+    torch.save(rec, path)
+    print("tiny_stereo: out", tuple(out.shape), "->", os.path.getsize(path), "B")
+
+
 def criteria_case():
     """SDR / NegSDR (src/criterion/sdr.py:6-110) and the clipped SI-SDR classes (:233-327) of the reference on seeded inputs; the
     estimates are noisy copies of the targets so that SDR spans roughly -5 .. 35 dB"""
@@ -298,6 +318,9 @@ def criteria_case():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "criteria":
         criteria_case()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "stereo":
+        multichannel_case()
         return
     paper = dict(n_basis=512, kernel_size=16, sep_hidden_channels=512, sep_bottleneck_channels=128,
                  sep_skip_channels=128, sep_num_blocks=3, sep_num_layers=8)

@@ -174,8 +174,12 @@ def test_constructor_envelope_errors():
         choose_layer_norm('gLN', 8, causal=True)
     with pytest.raises(NotImplementedError):
         choose_layer_norm('foo', 8)
+    assert Encoder(2, 8).conv1d.weight.shape == (8, 2, 16)      # multichannel filter banks are built (forward only)
     with pytest.raises(NotImplementedError):
-        Encoder(2, 8)
+        Encoder(65, 8)
+    m2 = ConvTasNet(64, 16, enc_basis='trainable', dec_basis='trainable', enc_nonlinear=None, in_channels=2)
+    assert m2.native_config().in_channels == 2 and m2.get_config()['in_channels'] == 2
+    assert m2.decoder.conv_transpose1d.weight.shape == (64, 2, 16)
     assert isinstance(choose_layer_norm('cLN', 8, causal=True), CumulativeLayerNorm1d)
     assert isinstance(choose_layer_norm('gLN', 8), GlobalLayerNorm)
     enc, dec = choose_filterbank(32, 16, stride=8, enc_basis='trainable', dec_basis='trainable', enc_nonlinear='relu')

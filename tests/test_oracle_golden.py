@@ -136,3 +136,13 @@ def test_sdr_oracle_vs_reference_golden(golden_dir):
         torch.testing.assert_close(torch.clamp(O.sisdr(r["input"], r["target"]), max=20.0).mean(dim=tuple(range(1, r["input"].dim() - 1)))
                                    if r["input"].dim() > 2 else torch.clamp(O.sisdr(r["input"], r["target"]), max=20.0),
                                    r["ClippedSISDR_20"], rtol=1e-5, atol=1e-4)
+
+
+def test_multichannel_oracle_vs_reference_golden(golden_dir):
+    """in_channels = 2 (4-D input, conv_tasnet.py:138-141,167-168): oracle == reference on the stereo fixture"""
+    r = torch.load(os.path.join(golden_dir, "tiny_stereo.pt"), weights_only=False)
+    cfg = O.OracleConfig(**r["cfg"])
+    out, latent = O.conv_tasnet_fwd(r["mixture"], O.synth_state_dict(cfg, seed=r["wseed"]), cfg)
+    assert out.shape == r["out"].shape == (2, 3, 2, 1501)
+    torch.testing.assert_close(out, r["out"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(latent, r["latent"], rtol=1e-5, atol=1e-6)

@@ -184,8 +184,8 @@ def test_model_golden(golden_dir, name, mode):
         loss_b, perm_b = crit(out, sources.cuda(), batch_mean=False)
         # 4-D input (batch, 1, n_mics = 1, T) -> (batch, n_sources, n_mics, T), conv_tasnet.py:138-141, 167-168
         out4 = model(mixture.cuda().unsqueeze(2))
-        with pytest.raises(NotImplementedError):
-            model(torch.cat([mixture, mixture], dim=1).cuda().unsqueeze(1))   # n_mics = 2: the kernels are single-channel
+        with pytest.raises(ValueError):
+            model(torch.cat([mixture, mixture], dim=1).cuda().unsqueeze(1))   # n_mics = 2 into a model built with in_channels = 1
     assert out.shape == (rec["batch"], cfg.n_sources, rec["T"])
     assert out4.shape == (rec["batch"], cfg.n_sources, 1, rec["T"]) and torch.equal(out4.squeeze(2), out2)
     assert torch.allclose(out, out2, rtol=0, atol=1e-6)
@@ -558,6 +558,45 @@ def test_reference_checkpoint_runs_on_the_kernels(golden_dir):
     torch.testing.assert_close(out.cpu(), rec["out"], rtol=RTOL, atol=ATOL)
     torch.testing.assert_close(latent.cpu(), rec["latent"], rtol=RTOL, atol=ATOL)
     assert torch.equal(perm.cpu(), rec["perm"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_multichannel_model_vs_reference_golden(golden_dir, mode):
+    """in_channels = n_mics = 2 through the 4-D input form: multichannel encoder / decoder kernels around the same separator; also the
+    stand-alone Encoder / Decoder modules with 2 channels, and the loud refusals (training, 3-D input, wrong mic count)"""
+    from ctn_b200.models.filterbank import Encoder, Decoder
+    r = _load(golden_dir, "tiny_stereo")
+    cfg = O.OracleConfig(**r["cfg"])
+    sd = O.synth_state_dict(cfg, seed=r["wseed"])
+    model = ConvTasNet(cfg.n_basis, cfg.kernel_size, enc_basis="trainable", dec_basis="trainable", enc_nonlinear=None,
+                       sep_hidden_channels=cfg.sep_hidden_channels, sep_bottleneck_channels=cfg.sep_bottleneck_channels,
+                       sep_skip_channels=cfg.sep_skip_channels, sep_num_blocks=cfg.sep_num_blocks, sep_num_layers=cfg.sep_num_layers,
+                       causal=False, n_sources=cfg.n_sources, in_channels=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    model.math = mode
+    x = r["mixture"].cuda()
+    with torch.no_grad():
+        out, latent = model.extract_latent(x)
+        enc = Encoder(2, cfg.n_basis, cfg.kernel_size, cfg.stride).cuda()
+        dec = Decoder(cfg.n_basis, 2, cfg.kernel_size, cfg.stride).cuda()
+        enc.conv1d.weight.copy_(sd["encoder.conv1d.weight"]); dec.conv_transpose1d.weight.copy_(sd["decoder.conv_transpose1d.weight"])
+        xe = x.reshape(2, 2, -1)[..., :1496]
+        w = enc(xe)
+        y = dec(w)
+        with pytest.raises(ValueError):
+            model(x[:, :, :1])                    # n_mics != in_channels
+        with pytest.raises(ValueError):
+            model(x.reshape(2, 2, -1)[:, :1])     # 3-D input to a multichannel model
+    assert out.shape == (2, 3, 2, 1501)
+    torch.testing.assert_close(out.cpu(), r["out"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(latent.cpu(), r["latent"], rtol=RTOL, atol=ATOL)
+    w_ref = torch.nn.functional.conv1d(xe.cpu(), sd["encoder.conv1d.weight"], stride=cfg.stride)
+    torch.testing.assert_close(w.cpu(), w_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(y.cpu(), torch.nn.functional.conv_transpose1d(w_ref, sd["decoder.conv_transpose1d.weight"], stride=cfg.stride),
+                               rtol=1e-5, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        model.train()(x)
 
 
 def test_sdr_family_vs_reference_golden(golden_dir):
